@@ -1,0 +1,238 @@
+"""
+GPU parity tests at the C-ABI level (`yawb_count` vs the oracle), the
+equivalent of the reference's `tests/catalog/test_trees.py::TestAngularTree`.
+
+Bar: integer pair counts bit-exact; weighted sums within 1e-12 relative.
+"""
+
+from itertools import product
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import golden_io
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL_WEIGHTED = 1e-12
+DELTA = 1e-9
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from yet_another_wizz_b200 import Engine
+
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def great_circle_points():
+    points = np.array([[0.0, 0.0], [90.0, 0.0], [180.0, 0.0], [270.0, 0.0], [0.0, 90.0], [0.0, -90.0]])
+    base = np.arange(1.0, 90.0, 1.0)
+    for offset in (0.0, 90.0, 180.0, 270.0):
+        points = np.concatenate([points, np.column_stack([base + offset, np.zeros_like(base)])])
+    for sign, ra in product([-1.0, 1.0], [0.0, 180.0]):
+        points = np.concatenate([points, np.column_stack([np.full_like(base, ra), sign * base])])
+    for sign, ra in product([-1.0, 1.0], [90.0, 270.0]):
+        points = np.concatenate([points, np.column_stack([np.full_like(base, ra), sign * base])])
+    radec = np.deg2rad(points)
+    return oracle.radec_to_xyz(radec[:, 0], radec[:, 1])
+
+
+def single_patch_hist(engine, xyz1, w1, xyz2, w2, r2, exact):
+    c1 = engine.upload_catalog(xyz1, np.array([0, len(xyz1)]), weights=w1)
+    c2 = engine.upload_catalog(xyz2, np.array([0, len(xyz2)]), weights=w2)
+    ci, cf, stats = engine.count(c1, c2, [0], [0], r2, exact=exact)
+    c1.free(); c2.free()
+    return ci[0, 0], cf[0, 0], stats
+
+
+@pytest.mark.parametrize("exact", [True, False])
+class TestGreatCircleKAT:
+    """reference tests/catalog/test_trees.py:181-247 through the C ABI"""
+
+    @pytest.mark.parametrize("ang_max", [1.0, 2.0, 10.0, 89.0])
+    def test_count_single(self, engine, ang_max, exact):
+        pts = great_circle_points()
+        single = oracle.radec_to_xyz(np.array([0.0]), np.array([0.0]))
+        amax = ang_max + DELTA
+        r2 = oracle.chord_sq_edges(np.deg2rad([amax - 1.0, amax]))
+        ci, cf, _ = single_patch_hist(engine, pts, np.full(len(pts), 2.0), single, np.array([2.0]), r2, exact)
+        assert ci[0] == 4
+        assert cf[0] == 4 * 2.0**2
+
+    @pytest.mark.parametrize("ang_max", [2.0, 10.0, 89.0])
+    def test_count_bins(self, engine, ang_max, exact):
+        pts = great_circle_points()
+        single = oracle.radec_to_xyz(np.array([0.0]), np.array([0.0]))
+        edges = np.deg2rad(np.concatenate([[0.0], np.arange(1.0, ang_max)]) + DELTA)
+        r2 = oracle.chord_sq_edges(edges)
+        ci, cf, _ = single_patch_hist(engine, pts, None, single, None, r2, exact)
+        assert_array_equal(ci, np.full(len(edges) - 1, 4))
+        assert_array_equal(cf, np.full(len(edges) - 1, 4.0))
+
+    def test_count_dualtree(self, engine, exact):
+        pts = great_circle_points()
+        r2 = oracle.chord_sq_edges(np.deg2rad([0.0, 1.0]) + DELTA)
+        ci, _, _ = single_patch_hist(engine, pts, None, pts, None, r2, exact)
+        assert ci[0] == 4 * 6 + 2 * (len(pts) - 6)
+
+    def test_count_empty(self, engine, exact):
+        empty = np.empty((0, 3))
+        r2 = oracle.chord_sq_edges(np.array([0.1, 0.5, 1.0]))
+        ci, cf, _ = single_patch_hist(engine, empty, None, empty, None, r2, exact)
+        assert_array_equal(ci, [0, 0])
+        pts = great_circle_points()
+        ci, cf, _ = single_patch_hist(engine, pts, None, empty, None, r2, exact)
+        assert_array_equal(ci, [0, 0])
+
+
+def engine_inputs(cat: dict, zedges, closed, binned: bool):
+    xyz = oracle.radec_to_xyz(cat["ra"], cat["dec"])
+    n_patch = len(cat["radii"])
+    order = np.argsort(cat["patch"], kind="stable")
+    patch_off = np.concatenate([[0], np.cumsum(np.bincount(cat["patch"], minlength=n_patch))])
+    zbin = None
+    if binned:
+        zbin = (np.digitize(cat["z"], zedges, right=(closed == "right")) - 1)[order].astype(np.int32)
+    w = None if cat["w"] is None else cat["w"][order]
+    return xyz[order], patch_off, w, zbin
+
+
+def oracle_hists(cat1, cat2, pairs, zedges, closed, r2, binned2):
+    """brute-force sub-bin histograms per (pair, z-bin) with the oracle"""
+    n_bins = len(zedges) - 1
+    xyz1 = oracle.radec_to_xyz(cat1["ra"], cat1["dec"])
+    xyz2 = oracle.radec_to_xyz(cat2["ra"], cat2["dec"])
+    b1 = np.digitize(cat1["z"], zedges, right=(closed == "right")) - 1
+    b2 = np.digitize(cat2["z"], zedges, right=(closed == "right")) - 1 if binned2 else None
+    weighted = cat1["w"] is not None or cat2["w"] is not None
+    out = np.zeros((len(pairs), n_bins, r2.shape[1] - 1), dtype=np.float64 if weighted else np.int64)
+    for k, (i, j) in enumerate(pairs):
+        for b in range(n_bins):
+            m1 = (cat1["patch"] == i) & (b1 == b)
+            m2 = (cat2["patch"] == j) & ((b2 == b) if binned2 else True)
+            w1 = None if cat1["w"] is None else cat1["w"][m1]
+            w2 = None if cat2["w"] is None else cat2["w"][m2]
+            out[k, b] = oracle.pair_histogram(xyz1[m1], xyz2[m2], w1, w2, r2[b])
+    return out
+
+
+def r2_table(cfg):
+    rows = []
+    for b in range(len(cfg["zedges"]) - 1):
+        lim = oracle.parse_ang_limits(cfg["ang_min"][b], cfg["ang_max"][b])
+        rows.append(oracle.chord_sq_edges(oracle.get_ang_bins(lim, cfg["rweight"], cfg["resolution"])))
+    return np.array(rows)
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("name", ["cross_unweighted", "cross_weighted_multiscale"])
+def test_cross_histograms_match_oracle(engine, name, exact):
+    g = golden_io.load(name)
+    cfg = golden_io.config_of(g)
+    r2 = r2_table(cfg)
+    pairs = [tuple(p) for p in g["links"]]
+    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
+    n_bins = len(cfg["zedges"]) - 1
+    for a, b in (("ref", "unk"), ("ref", "unk_rand"), ("ref_rand", "unk"), ("ref_rand", "unk_rand")):
+        ca, cb = golden_io.catalog_arrays(g, a), golden_io.catalog_arrays(g, b)
+        xyz1, off1, w1, z1 = engine_inputs(ca, cfg["zedges"], cfg["closed"], True)
+        xyz2, off2, w2, _ = engine_inputs(cb, cfg["zedges"], cfg["closed"], False)
+        d1 = engine.upload_catalog(xyz1, off1, weights=w1, zbin=z1, n_bins=n_bins)
+        d2 = engine.upload_catalog(xyz2, off2, weights=w2)
+        ci, cf, stats = engine.count(d1, d2, pi, pj, r2, exact=exact)
+        want = oracle_hists(ca, cb, pairs, cfg["zedges"], cfg["closed"], r2, False)
+        if want.dtype == np.int64:
+            assert_array_equal(ci, want)
+            assert_array_equal(cf, want.astype(np.float64))
+        else:
+            assert_allclose(cf, want, rtol=RTOL_WEIGHTED, atol=0)
+        assert want.sum() > 0
+        # sum of weights, trees.py:225-234
+        sw = d1.sum_weights()
+        for b in range(n_bins):
+            for p in range(len(ca["radii"])):
+                m = (ca["patch"] == p) & (np.digitize(ca["z"], cfg["zedges"], right=cfg["closed"] == "right") - 1 == b)
+                exp = m.sum() if ca["w"] is None else ca["w"][m].sum()
+                assert_allclose(sw[b, p], exp, rtol=1e-13)
+        d1.free(); d2.free()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("name", ["auto_unweighted", "auto_rweight_polewrap"])
+def test_auto_histograms_match_oracle(engine, name, exact):
+    g = golden_io.load(name)
+    cfg = golden_io.config_of(g)
+    r2 = r2_table(cfg)
+    pairs = [tuple(p) for p in g["links"]]
+    pi = np.array([p[0] for p in pairs]); pj = np.array([p[1] for p in pairs])
+    n_bins = len(cfg["zedges"]) - 1
+    data, rand = golden_io.catalog_arrays(g, "data"), golden_io.catalog_arrays(g, "rand")
+    for ca, cb in ((data, data), (data, rand), (rand, rand)):
+        xyz1, off1, w1, z1 = engine_inputs(ca, cfg["zedges"], cfg["closed"], True)
+        xyz2, off2, w2, z2 = engine_inputs(cb, cfg["zedges"], cfg["closed"], True)
+        d1 = engine.upload_catalog(xyz1, off1, weights=w1, zbin=z1, n_bins=n_bins)
+        d2 = engine.upload_catalog(xyz2, off2, weights=w2, zbin=z2, n_bins=n_bins)
+        ci, cf, stats = engine.count(d1, d2, pi, pj, r2, exact=exact)
+        want = oracle_hists(ca, cb, pairs, cfg["zedges"], cfg["closed"], r2, True)
+        if want.dtype == np.int64:
+            assert_array_equal(ci, want)
+        else:
+            assert_allclose(cf, want, rtol=RTOL_WEIGHTED, atol=0)
+        d1.free(); d2.free()
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_edge_adversarial(engine, exact):
+    """pairs within a few ulp of a bin edge: only the reference's FP64 evaluation
+    order reproduces scipy; golden counts from the reference"""
+    g = golden_io.load("edge_adversarial")
+    a = oracle.radec_to_xyz(g["a_radec"][:, 0], g["a_radec"][:, 1])
+    b = oracle.radec_to_xyz(g["b_radec"][:, 0], g["b_radec"][:, 1])
+    for key in ("upper", "lower"):
+        r2 = oracle.chord_sq_edges(np.array([g[f"{key}_ang_min"][0], g[f"{key}_ang_max"][0]]))
+        ci, _, stats = single_patch_hist(engine, a, None, b, None, r2, exact)
+        assert ci[0] == int(g[f"{key}_counts"][0])
+    theta = float(g["theta"])
+    r2 = oracle.chord_sq_edges(np.array([theta / 10, theta, theta * 3]))
+    ci, _, stats = single_patch_hist(engine, a, None, b, None, r2, exact)
+    assert_array_equal(ci, g["multi_counts"].astype(np.int64))
+    if not exact:
+        assert stats["rechecks"] > 0  # the FP64 recheck path was exercised
+
+
+def test_random_dense_fast_vs_exact(engine):
+    """property test: pruned FP32+recheck kernel == unpruned FP64 kernel, several patches, bins, edges"""
+    rng = np.random.default_rng(42)
+    n_patch, n_bins = 5, 3
+    n1, n2 = 20000, 30000
+    def cat(n, binned, weighted):
+        ra = rng.uniform(0.0, 0.05, n); dec = np.arcsin(rng.uniform(-0.02, 0.02, n))
+        patch = np.minimum((ra / 0.05 * n_patch).astype(int), n_patch - 1)
+        order = np.argsort(patch, kind="stable")
+        xyz = oracle.radec_to_xyz(ra, dec)[order]
+        off = np.concatenate([[0], np.cumsum(np.bincount(patch, minlength=n_patch))])
+        zbin = rng.integers(-1, n_bins + 1, n).astype(np.int32) if binned else None
+        w = rng.uniform(0.5, 1.5, n) if weighted else None
+        return xyz, off, w, zbin
+    pi, pj = np.meshgrid(np.arange(n_patch), np.arange(n_patch), indexing="ij")
+    pi, pj = pi.ravel(), pj.ravel()
+    for weighted in (False, True):
+        for n_edges in (2, 7):
+            r2 = np.sort(rng.uniform(1e-8, 4e-6, (n_bins, n_edges)), axis=1)
+            x1, o1, w1, z1 = cat(n1, True, weighted)
+            x2, o2, w2, _ = cat(n2, False, False)
+            d1 = engine.upload_catalog(x1, o1, weights=w1, zbin=z1, n_bins=n_bins)
+            d2 = engine.upload_catalog(x2, o2, weights=w2)
+            fi, ff, fs = engine.count(d1, d2, pi, pj, r2)
+            ei, ef, es = engine.count(d1, d2, pi, pj, r2, exact=True)
+            assert_array_equal(fi, ei)
+            assert_allclose(ff, ef, rtol=RTOL_WEIGHTED, atol=0)
+            assert ei.sum() > 1000
+            assert fs["pair_tests"] < es["pair_tests"]  # pruning happened
+            assert es["pair_tests"] == es["pair_tests_naive"]
+            d1.free(); d2.free()

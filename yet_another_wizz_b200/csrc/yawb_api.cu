@@ -1,0 +1,329 @@
+// C ABI of libyawb.so (see include/yawb.h for the contract of every entry point).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "yawb_internal.cuh"
+
+namespace {
+thread_local char g_err[1024] = "";
+
+__global__ void k_u64_to_f64(const unsigned long long *__restrict__ in, double *__restrict__ out, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+}  // namespace
+
+void yawb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+const char *yawb_last_error(void) { return g_err; }
+
+int yawb_version(void) { return 100; }
+
+int yawb_create(int device, yawb_ctx **out) {
+    YAWB_REQUIRE(out != nullptr, "yawb_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        yawb_set_error("yawb_create: no CUDA device available (%s); this engine has no CPU fallback",
+                       cudaGetErrorString(e));
+        return 3;
+    }
+    YAWB_REQUIRE(device >= 0 && device < n_dev, "yawb_create: device %d out of range (0..%d)", device, n_dev - 1);
+    YAWB_CUDA(cudaSetDevice(device));
+    yawb_ctx *ctx = new (std::nothrow) yawb_ctx();
+    YAWB_REQUIRE(ctx != nullptr, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    YAWB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sms = prop.multiProcessorCount;
+    YAWB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev0));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev1));
+    YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    *out = ctx;
+    return 0;
+}
+
+int yawb_destroy(yawb_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_counters);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int yawb_device_sms(const yawb_ctx *ctx) { return ctx ? ctx->sms : 0; }
+
+int yawb_sync(yawb_ctx *ctx) {
+    YAWB_REQUIRE(ctx != nullptr, "yawb_sync: ctx is NULL");
+    YAWB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int yawb_host_alloc(void **ptr, uint64_t bytes) {
+    YAWB_REQUIRE(ptr != nullptr, "yawb_host_alloc: ptr is NULL");
+    YAWB_CUDA(cudaHostAlloc(ptr, std::max<uint64_t>(bytes, 1), cudaHostAllocDefault));
+    return 0;
+}
+
+int yawb_host_free(void *ptr) {
+    if (ptr) YAWB_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
+                        const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+    YAWB_REQUIRE(ctx && out && patch_off, "yawb_upload_catalog: NULL argument");
+    *out = nullptr;
+    YAWB_REQUIRE(n_patch >= 1 && n_patch <= 65535, "n_patch must be in 1..65535 (got %d)", n_patch);
+    if (!zbin) n_bins = 1;
+    YAWB_REQUIRE(n_bins >= 1 && n_bins <= 4096, "n_bins must be in 1..4096 (got %d)", n_bins);
+    YAWB_REQUIRE(patch_off[0] == 0, "patch_off[0] must be 0");
+    for (int p = 0; p < n_patch; ++p)
+        YAWB_REQUIRE(patch_off[p + 1] >= patch_off[p], "patch_off must be non-decreasing");
+    const int64_t n = patch_off[n_patch];
+    YAWB_REQUIRE(n < (1ll << 31) - 1024, "catalogs are limited to 2^31 rows (got %lld)", (long long)n);
+    YAWB_REQUIRE(n == 0 || xyz != nullptr, "xyz is NULL");
+    YAWB_CUDA(cudaSetDevice(ctx->device));
+
+    yawb_cat *cat = new (std::nothrow) yawb_cat();
+    YAWB_REQUIRE(cat != nullptr, "out of host memory");
+    cat->ctx = ctx;
+    cat->n_in = n;
+    cat->n_patch = n_patch;
+    cat->n_bins = n_bins;
+    cat->binned = zbin != nullptr;
+    cat->weighted = w != nullptr;
+    if (yawb_index_upload(ctx, cat, xyz, w, zbin, patch_off)) {
+        yawb_index_free(cat, true);
+        delete cat;
+        return 1;
+    }
+    *out = cat;
+    return 0;
+}
+
+int yawb_free_catalog(yawb_cat *cat) {
+    if (!cat) return 0;
+    cudaSetDevice(cat->ctx->device);
+    cudaStreamSynchronize(cat->ctx->stream);
+    yawb_index_free(cat, true);
+    delete cat;
+    return 0;
+}
+
+int yawb_build_index(yawb_cat *cat, int role, double *ms) {
+    YAWB_REQUIRE(cat != nullptr, "yawb_build_index: cat is NULL");
+    YAWB_REQUIRE(role == YAWB_ROLE_FIRST || role == YAWB_ROLE_SECOND, "unknown role %d", role);
+    yawb_ctx *ctx = cat->ctx;
+    YAWB_CUDA(cudaSetDevice(ctx->device));
+    YAWB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = role == YAWB_ROLE_FIRST ? yawb_index_build_first(cat) : yawb_index_build_second(cat);
+    if (rc) return rc;
+    YAWB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    YAWB_CUDA(cudaEventSynchronize(ctx->ev1));
+    float t = 0.f;
+    YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+    if (ms) *ms = (double)t;
+    return 0;
+}
+
+int yawb_drop_index(yawb_cat *cat) {
+    YAWB_REQUIRE(cat != nullptr, "yawb_drop_index: cat is NULL");
+    YAWB_CUDA(cudaSetDevice(cat->ctx->device));
+    YAWB_CUDA(cudaStreamSynchronize(cat->ctx->stream));
+    yawb_index_free(cat, false);
+    return 0;
+}
+
+int yawb_catalog_info(const yawb_cat *cat, int64_t *n_rows, int64_t *device_bytes) {
+    YAWB_REQUIRE(cat != nullptr, "yawb_catalog_info: cat is NULL");
+    if (n_rows) *n_rows = cat->n;
+    if (device_bytes) *device_bytes = cat->device_bytes;
+    return 0;
+}
+
+int yawb_sum_weights(const yawb_cat *cat, double *out) {
+    YAWB_REQUIRE(cat && out, "yawb_sum_weights: NULL argument");
+    std::memcpy(out, cat->h_sumw.data(), cat->h_sumw.size() * sizeof(double));
+    return 0;
+}
+
+int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pair_i, const int32_t *pair_j,
+               int n_pairs, const double *r2_edges, int n_edges, uint32_t flags, double *out_f64,
+               int64_t *out_i64, yawb_stats *stats) {
+    YAWB_REQUIRE(ctx && cat1 && cat2, "yawb_count: NULL context or catalog");
+    YAWB_REQUIRE(cat1->ctx == ctx && cat2->ctx == ctx, "catalogs belong to a different context");
+    YAWB_REQUIRE(n_pairs >= 0, "n_pairs < 0");
+    YAWB_REQUIRE(n_edges >= 2 && n_edges <= YAWB_MAX_EDGES, "n_edges must be in 2..%d (got %d)", YAWB_MAX_EDGES, n_edges);
+    YAWB_REQUIRE(r2_edges != nullptr, "r2_edges is NULL");
+    YAWB_REQUIRE(cat1->n_patch == cat2->n_patch, "catalogs have different numbers of patches (%d vs %d)",
+                 cat1->n_patch, cat2->n_patch);
+    YAWB_REQUIRE(!(cat2->binned && !cat1->binned), "a binned second catalog needs a binned first catalog");
+    YAWB_REQUIRE(!cat2->binned || cat2->n_bins == cat1->n_bins, "z-bin counts differ (%d vs %d)", cat1->n_bins,
+                 cat2->n_bins);
+    YAWB_REQUIRE(n_pairs == 0 || (pair_i && pair_j), "pair lists are NULL");
+    const int B = cat1->n_bins, P = cat1->n_patch, nsub = n_edges - 1;
+    for (int k = 0; k < n_pairs; ++k)
+        YAWB_REQUIRE(pair_i[k] >= 0 && pair_i[k] < P && pair_j[k] >= 0 && pair_j[k] < P,
+                     "patch pair %d = (%d, %d) out of range", k, pair_i[k], pair_j[k]);
+    for (int b = 0; b < B; ++b)
+        for (int e = 0; e + 1 < n_edges; ++e)
+            YAWB_REQUIRE(r2_edges[(size_t)b * n_edges + e] <= r2_edges[(size_t)b * n_edges + e + 1] &&
+                             r2_edges[(size_t)b * n_edges + e] >= 0.0,
+                         "r2_edges of z-bin %d are not sorted / non-negative", b);
+    YAWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    yawb_stats s{};
+
+    // indexes (lazy)
+    float t_idx = 0.f;
+    if (!cat1->has_sindex || !cat2->has_rtiles) {
+        YAWB_CUDA(cudaEventRecord(ctx->ev0, st));
+        if (yawb_index_build_first(cat1)) return 1;
+        if (yawb_index_build_second(cat2)) return 1;
+        YAWB_CUDA(cudaEventRecord(ctx->ev1, st));
+        YAWB_CUDA(cudaEventSynchronize(ctx->ev1));
+        YAWB_CUDA(cudaEventElapsedTime(&t_idx, ctx->ev0, ctx->ev1));
+    }
+    s.index_ms = t_idx;
+
+    const bool weighted = cat1->weighted || cat2->weighted;
+    const size_t n_out = (size_t)n_pairs * B * nsub;
+
+    // host-side preparation of thresholds and the item table
+    std::vector<BinPar> binpar(B);
+    std::vector<float> r2f((size_t)B * n_edges);
+    for (int b = 0; b < B; ++b) {
+        const double lo = r2_edges[(size_t)b * n_edges], hi = r2_edges[(size_t)b * n_edges + nsub];
+        BinPar &bp = binpar[b];
+        bp.lo = lo;
+        bp.hi = hi;
+        bp.rmax = std::sqrt(hi) * (1.0 + 1e-9) + 1e-14;
+        bp.mid = (float)(0.5 * (lo + hi));
+        bp.h = (float)(0.5 * (hi - lo));
+        bp.empty = !(hi > lo);
+        bp.pad = 0;
+        for (int e = 0; e < n_edges; ++e) r2f[(size_t)b * n_edges + e] = (float)r2_edges[(size_t)b * n_edges + e];
+    }
+    std::vector<long long> item_base(n_pairs + 1, 0);
+    for (int k = 0; k < n_pairs; ++k) {
+        const int q = pair_j[k];
+        item_base[k + 1] = item_base[k] + (cat2->h_ptile_off[q + 1] - cat2->h_ptile_off[q]);
+        const int p = pair_i[k];
+        for (int b = 0; b < B; ++b) {
+            const long long n1 = cat1->h_counts[(size_t)b * P + p];
+            long long n2 = 0;
+            if (cat2->binned) n2 = cat2->h_counts[(size_t)b * P + q];
+            else n2 = cat2->h_counts[q];
+            s.pair_tests_naive += (uint64_t)(n1 * n2);
+        }
+    }
+
+    int *d_pi = nullptr, *d_pj = nullptr;
+    long long *d_base = nullptr;
+    double *d_r2 = nullptr, *d_w = nullptr;
+    float *d_r2f = nullptr;
+    BinPar *d_bp = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_pi); cudaFree(d_pj); cudaFree(d_base); cudaFree(d_r2); cudaFree(d_r2f); cudaFree(d_bp);
+        cudaFree(d_cnt); cudaFree(d_w);
+    };
+#define TRY(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t err__ = (call);                                                      \
+        if (err__ != cudaSuccess) {                                                      \
+            yawb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+            cleanup();                                                                   \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+    const size_t np1 = std::max(n_pairs, 1);
+    TRY(cudaMalloc(&d_pi, np1 * sizeof(int)));
+    TRY(cudaMalloc(&d_pj, np1 * sizeof(int)));
+    TRY(cudaMalloc(&d_base, (np1 + 1) * sizeof(long long)));
+    TRY(cudaMalloc(&d_r2, (size_t)B * n_edges * sizeof(double)));
+    TRY(cudaMalloc(&d_r2f, (size_t)B * n_edges * sizeof(float)));
+    TRY(cudaMalloc(&d_bp, B * sizeof(BinPar)));
+    TRY(cudaMalloc(&d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long)));
+    if (weighted) TRY(cudaMalloc(&d_w, std::max<size_t>(n_out, 1) * sizeof(double)));
+    if (n_pairs) {
+        TRY(cudaMemcpyAsync(d_pi, pair_i, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(d_pj, pair_j, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    TRY(cudaMemcpyAsync(d_base, item_base.data(), (n_pairs + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_r2, r2_edges, (size_t)B * n_edges * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_r2f, r2f.data(), (size_t)B * n_edges * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(d_bp, binpar.data(), B * sizeof(BinPar), cudaMemcpyHostToDevice, st));
+    TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
+    if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
+    TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+
+    CountArgs a{};
+    a.c1 = cat1; a.c2 = cat2;
+    a.d_pair_i = d_pi; a.d_pair_j = d_pj; a.d_pair_item_base = d_base;
+    a.n_items = item_base[n_pairs];
+    a.n_pairs = n_pairs; a.n_bins = B; a.n_edges = n_edges;
+    a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp;
+    a.d_out_cnt = d_cnt; a.d_out_w = d_w; a.weighted = weighted;
+
+    int launches = 0;
+    TRY(cudaEventRecord(ctx->ev0, st));
+    int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
+                                                  : yawb_launch_count_fast(ctx, a, &launches);
+    if (rc) { cleanup(); return rc; }
+    TRY(cudaEventRecord(ctx->ev1, st));
+
+    // results
+    const cudaMemcpyKind kind = (flags & YAWB_FLAG_OUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (out_i64 && n_out) TRY(cudaMemcpyAsync(out_i64, d_cnt, n_out * sizeof(int64_t), kind, st));
+    if (out_f64 && n_out) {
+        if (weighted) {
+            TRY(cudaMemcpyAsync(out_f64, d_w, n_out * sizeof(double), kind, st));
+        } else if (flags & YAWB_FLAG_OUT_DEVICE) {
+            k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, out_f64, (long long)n_out);
+            launches += 1;
+        } else {
+            double *d_tmp = nullptr;
+            TRY(cudaMalloc(&d_tmp, n_out * sizeof(double)));
+            k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, d_tmp, (long long)n_out);
+            launches += 1;
+            cudaError_t e = cudaMemcpyAsync(out_f64, d_tmp, n_out * sizeof(double), kind, st);
+            cudaStreamSynchronize(st);
+            cudaFree(d_tmp);
+            TRY(e);
+        }
+    }
+    unsigned long long h_counters[8] = {0};
+    TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    TRY(cudaGetLastError());
+    float t_k = 0.f;
+    TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));
+#undef TRY
+    cleanup();
+    s.kernel_ms = t_k;
+    s.pair_tests = h_counters[1];
+    s.rechecks = h_counters[2];
+    s.work_items = h_counters[3];
+    s.launches = (uint64_t)launches;
+    if (stats) *stats = s;
+    return 0;
+}
+
+}  // extern "C"

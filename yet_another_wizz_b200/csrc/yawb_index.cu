@@ -1,0 +1,593 @@
+// Catalog upload and device-side index construction.
+//
+// Replaces the reference's tree build (src/yaw/catalog/trees.py:365-429,
+// BinnedTrees.build :483-545, Catalog.build_trees catalog.py:1406-1460): instead of
+// one pickled cKDTree per (patch, z-bin) the rows stay resident in HBM in two sort
+// orders, each built with one key kernel + one radix sort + one gather:
+//
+//   first role  (cat1 of yawb_count): rows sorted by global sky-cell id
+//               (patch, z-bin, row-major cell of a per-patch tangent-plane grid),
+//               plus cell_start[] -- a range query is one contiguous run per cell row;
+//   second role (cat2): rows sorted by (patch, z-bin, Morton code) and cut into
+//               register tiles of YAWB_TILE compact points with a bounding sphere.
+//
+// Everything here is HBM-bound streaming work: coalesced SoA double arrays, one pass
+// per step, grids sized from the row count.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "yawb_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr double kTargetPerCell = 8.0;
+constexpr long long kMaxCellsPerPatchBin = 1ll << 22;
+
+inline int blocks_for(int64_t n, int per_block = kThreads) {
+    return (int)std::min<int64_t>((n + per_block - 1) / per_block, 1 << 30);
+}
+
+template <typename T>
+int dev_alloc(yawb_cat *cat, T **ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    YAWB_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
+    cat->device_bytes += (int64_t)(count * sizeof(T));
+    return 0;
+}
+
+template <typename T>
+void dev_free(yawb_cat *cat, T *&ptr, size_t count) {
+    if (ptr) {
+        cudaFree(ptr);
+        cat->device_bytes -= (int64_t)(std::max<size_t>(count, 1) * sizeof(T));
+        ptr = nullptr;
+    }
+}
+
+// order-preserving map double -> uint64 so atomicMin/Max work on doubles
+__device__ __forceinline__ unsigned long long enc_double(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+inline double dec_double(unsigned long long b) {
+    b = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
+    double v;
+    memcpy(&v, &b, sizeof(v));
+    return v;
+}
+
+// ---- upload kernels ---------------------------------------------------------------------
+
+// AoS (n x 3) -> SoA, plus the patch id of every row from the row offsets
+__global__ void k_deinterleave(const double *__restrict__ xyz, const long long *__restrict__ patch_off,
+                               int n_patch, long long n, double *__restrict__ x, double *__restrict__ y,
+                               double *__restrict__ z, int *__restrict__ patch) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = xyz[3 * i];
+    y[i] = xyz[3 * i + 1];
+    z[i] = xyz[3 * i + 2];
+    int lo = 0, hi = n_patch;  // last p with patch_off[p] <= i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (patch_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    patch[i] = lo;
+}
+
+// per patch: sum of unit vectors; per (bin, patch): row count and sum of weights
+__global__ void k_patch_sums(const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const double *__restrict__ w,
+                             const int *__restrict__ bin, const int *__restrict__ patch, long long n,
+                             int n_patch, int n_bins, double *__restrict__ sums /*[n_patch][3]*/,
+                             unsigned long long *__restrict__ counts, double *__restrict__ sumw) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    bool live = i < n;
+    int p = live ? patch[i] : -1;
+    double px = live ? x[i] : 0.0, py = live ? y[i] : 0.0, pz = live ? z[i] : 0.0;
+    int p0 = __shfl_sync(full, p, 0);
+    if (__all_sync(full, p == p0)) {  // common case: whole warp inside one patch
+        for (int o = 16; o; o >>= 1) {
+            px += __shfl_xor_sync(full, px, o);
+            py += __shfl_xor_sync(full, py, o);
+            pz += __shfl_xor_sync(full, pz, o);
+        }
+        if ((threadIdx.x & 31) == 0 && p0 >= 0) {
+            atomicAdd(&sums[3 * p0], px);
+            atomicAdd(&sums[3 * p0 + 1], py);
+            atomicAdd(&sums[3 * p0 + 2], pz);
+        }
+    } else if (live) {
+        atomicAdd(&sums[3 * p], px);
+        atomicAdd(&sums[3 * p + 1], py);
+        atomicAdd(&sums[3 * p + 2], pz);
+    }
+    if (live) {
+        int b = bin ? bin[i] : 0;
+        if (b >= 0 && b < n_bins) {
+            atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
+            if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
+        }
+    }
+}
+
+// per patch: (u, v) bounding box and max squared chord distance from the centre
+__global__ void k_patch_bbox(const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const int *__restrict__ patch, long long n,
+                             const PatchFrame *__restrict__ frames,
+                             unsigned long long *__restrict__ box /*[n_patch][5]*/) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = patch[i];
+    const PatchFrame &f = frames[p];
+    double dx = x[i] - f.c[0], dy = y[i] - f.c[1], dz = z[i] - f.c[2];
+    double u = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
+    double v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
+    double d2 = dx * dx + dy * dy + dz * dz;
+    const unsigned full = __activemask();
+    int p0 = __shfl_sync(full, p, __ffs(full) - 1);
+    unsigned long long eu = enc_double(u), ev = enc_double(v), ed = enc_double(d2);
+    if (full == 0xffffffffu && __all_sync(full, p == p0)) {
+        unsigned long long umin = eu, umax = eu, vmin = ev, vmax = ev, dmax = ed;
+        for (int o = 16; o; o >>= 1) {
+            umin = min(umin, __shfl_xor_sync(full, umin, o));
+            umax = max(umax, __shfl_xor_sync(full, umax, o));
+            vmin = min(vmin, __shfl_xor_sync(full, vmin, o));
+            vmax = max(vmax, __shfl_xor_sync(full, vmax, o));
+            dmax = max(dmax, __shfl_xor_sync(full, dmax, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&box[5 * p0], umin);
+            atomicMax(&box[5 * p0 + 1], umax);
+            atomicMin(&box[5 * p0 + 2], vmin);
+            atomicMax(&box[5 * p0 + 3], vmax);
+            atomicMax(&box[5 * p0 + 4], dmax);
+        }
+    } else {
+        atomicMin(&box[5 * p], eu);
+        atomicMax(&box[5 * p + 1], eu);
+        atomicMin(&box[5 * p + 2], ev);
+        atomicMax(&box[5 * p + 3], ev);
+        atomicMax(&box[5 * p + 4], ed);
+    }
+}
+
+// ---- sort keys ----------------------------------------------------------------------------
+
+__device__ __forceinline__ void local_uv(const PatchFrame &f, double X, double Y, double Z, double &u,
+                                         double &v) {
+    double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
+    u = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
+    v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
+}
+
+__global__ void k_keys_first(const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const int *__restrict__ bin,
+                             const int *__restrict__ patch, long long n, int n_bins,
+                             const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
+                             unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vals[i] = (unsigned)i;
+    int b = bin ? bin[i] : 0;
+    if (b < 0 || b >= n_bins) {
+        keys[i] = ~0ull;
+        return;
+    }
+    int p = patch[i];
+    double u, v;
+    local_uv(frames[p], x[i], y[i], z[i], u, v);
+    const SGrid g = grids[p];
+    // clamp in double first: the product can exceed the int range for degenerate patches
+    int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_c), 0.0), (double)(g.gu - 1));
+    int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_c), 0.0), (double)(g.gv - 1));
+    keys[i] = (unsigned long long)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
+}
+
+__device__ __forceinline__ unsigned spread16(unsigned v) {
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+__global__ void k_keys_second(const double *__restrict__ x, const double *__restrict__ y,
+                              const double *__restrict__ z, const int *__restrict__ bin,
+                              const int *__restrict__ patch, long long n, int n_bins,
+                              const PatchFrame *__restrict__ frames,
+                              unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vals[i] = (unsigned)i;
+    int b = bin ? bin[i] : 0;
+    if (b < 0 || b >= n_bins) {
+        keys[i] = ~0ull;
+        return;
+    }
+    int p = patch[i];
+    const PatchFrame &f = frames[p];
+    double u, v;
+    local_uv(f, x[i], y[i], z[i], u, v);
+    double su = f.umax > f.umin ? 65535.0 / (f.umax - f.umin) : 0.0;
+    double sv = f.vmax > f.vmin ? 65535.0 / (f.vmax - f.vmin) : 0.0;
+    // isotropic quantisation keeps Morton blocks square in (u, v)
+    double s = fmin(su > 0.0 ? su : sv, sv > 0.0 ? sv : su);
+    int qu = min(max((int)((u - f.umin) * s), 0), 65535);
+    int qv = min(max((int)((v - f.vmin) * s), 0), 65535);
+    unsigned morton = spread16((unsigned)qu) | (spread16((unsigned)qv) << 1);
+    keys[i] = ((unsigned long long)((long long)p * n_bins + b) << 32) | morton;
+}
+
+__global__ void k_gather(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
+                         const double *__restrict__ y, const double *__restrict__ z,
+                         const double *__restrict__ w, double *__restrict__ ox, double *__restrict__ oy,
+                         double *__restrict__ oz, double *__restrict__ ow) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned j = perm[i];
+    ox[i] = x[j];
+    oy[i] = y[j];
+    oz[i] = z[j];
+    if (w) ow[i] = w[j];
+}
+
+// cell_start[g] = first sorted row whose key is >= g (one thread per cell, binary search)
+__global__ void k_cell_start(const unsigned long long *__restrict__ keys, long long n, long long n_cells,
+                             int *__restrict__ cell_start) {
+    long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g > n_cells) return;
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (keys[mid] < (unsigned long long)g) lo = mid + 1; else hi = mid;
+    }
+    cell_start[g] = (int)lo;
+}
+
+// bounding sphere of each register tile: one warp per tile
+__global__ void k_tile_spheres(const double *__restrict__ x, const double *__restrict__ y,
+                               const double *__restrict__ z, Tile *__restrict__ tiles, int n_tiles) {
+    int t = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    Tile tl = tiles[t];
+    const unsigned full = 0xffffffffu;
+    double sx = 0, sy = 0, sz = 0;
+    for (int k = lane; k < tl.count; k += 32) {
+        sx += x[tl.start + k];
+        sy += y[tl.start + k];
+        sz += z[tl.start + k];
+    }
+    for (int o = 16; o; o >>= 1) {
+        sx += __shfl_xor_sync(full, sx, o);
+        sy += __shfl_xor_sync(full, sy, o);
+        sz += __shfl_xor_sync(full, sz, o);
+    }
+    double inv = 1.0 / (double)tl.count;
+    float cx = (float)(sx * inv), cy = (float)(sy * inv), cz = (float)(sz * inv);
+    double r2 = 0.0;  // radius about the float-rounded centre, so the stored sphere is sound
+    for (int k = lane; k < tl.count; k += 32) {
+        double dx = x[tl.start + k] - (double)cx, dy = y[tl.start + k] - (double)cy,
+               dz = z[tl.start + k] - (double)cz;
+        r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
+    }
+    for (int o = 16; o; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(full, r2, o));
+    if (lane == 0) {
+        tl.cx = cx;
+        tl.cy = cy;
+        tl.cz = cz;
+        tl.rad = (float)(sqrt(r2) * (1.0 + 1e-6) + 1e-12);
+        if ((double)tl.rad < sqrt(r2)) tl.rad = nextafterf(tl.rad, 1e30f);
+        tiles[t] = tl;
+    }
+}
+
+int sort_pairs(yawb_ctx *ctx, unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
+               unsigned *vals_out, long long n, int end_bit) {
+    size_t temp_bytes = 0;
+    YAWB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, vals_in, vals_out,
+                                              (int)n, 0, end_bit, ctx->stream));
+    void *temp = nullptr;
+    YAWB_CUDA(cudaMalloc(&temp, std::max<size_t>(temp_bytes, 16)));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out,
+                                                    (int)n, 0, end_bit, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(temp);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        yawb_set_error("radix sort failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return 1;
+    }
+    return 0;
+}
+
+int bits_for(unsigned long long max_key) {
+    int b = 1;
+    while (b < 64 && (max_key >> b)) ++b;
+    return b;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------
+int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
+                      const int32_t *zbin, const int64_t *patch_off) {
+    const long long n = cat->n_in;
+    const int P = cat->n_patch, B = cat->n_bins;
+    cudaStream_t st = ctx->stream;
+
+    if (dev_alloc(cat, &cat->x, n) || dev_alloc(cat, &cat->y, n) || dev_alloc(cat, &cat->z, n) ||
+        dev_alloc(cat, &cat->patch, n))
+        return 1;
+    if (w && dev_alloc(cat, &cat->w, n)) return 1;
+    if (zbin && dev_alloc(cat, &cat->bin, n)) return 1;
+
+    double *d_xyz = nullptr;
+    long long *d_poff = nullptr;
+    double *d_sums = nullptr, *d_sumw = nullptr;
+    unsigned long long *d_counts = nullptr, *d_box = nullptr;
+    YAWB_CUDA(cudaMalloc(&d_xyz, std::max<size_t>(n * 3 * sizeof(double), 8)));
+    YAWB_CUDA(cudaMalloc(&d_poff, (P + 1) * sizeof(long long)));
+    YAWB_CUDA(cudaMalloc(&d_sums, P * 3 * sizeof(double)));
+    YAWB_CUDA(cudaMalloc(&d_sumw, (size_t)B * P * sizeof(double)));
+    YAWB_CUDA(cudaMalloc(&d_counts, (size_t)B * P * sizeof(unsigned long long)));
+    YAWB_CUDA(cudaMalloc(&d_box, P * 5 * sizeof(unsigned long long)));
+
+    YAWB_CUDA(cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    YAWB_CUDA(cudaMemcpyAsync(d_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (w) YAWB_CUDA(cudaMemcpyAsync(cat->w, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (zbin) YAWB_CUDA(cudaMemcpyAsync(cat->bin, zbin, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    YAWB_CUDA(cudaMemsetAsync(d_sums, 0, P * 3 * sizeof(double), st));
+    YAWB_CUDA(cudaMemsetAsync(d_sumw, 0, (size_t)B * P * sizeof(double), st));
+    YAWB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)B * P * sizeof(unsigned long long), st));
+
+    if (n > 0) {
+        k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(d_xyz, d_poff, P, n, cat->x, cat->y, cat->z,
+                                                           cat->patch);
+        k_patch_sums<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin, cat->patch,
+                                                         n, P, B, d_sums, d_counts, d_sumw);
+    }
+    std::vector<double> sums(P * 3);
+    std::vector<unsigned long long> counts((size_t)B * P);
+    cat->h_sumw.assign((size_t)B * P, 0.0);
+    YAWB_CUDA(cudaMemcpyAsync(sums.data(), d_sums, P * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (size_t)B * P * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaMemcpyAsync(cat->h_sumw.data(), d_sumw, (size_t)B * P * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_xyz);
+
+    cat->h_counts.assign((size_t)B * P, 0);
+    cat->n = 0;
+    for (size_t k = 0; k < counts.size(); ++k) {
+        cat->h_counts[k] = (long long)counts[k];
+        cat->n += (long long)counts[k];
+        if (!w) cat->h_sumw[k] = (double)counts[k];  // trees.py:225-227
+    }
+    // rows of (patch p, bin b) in both sort orders: patch-major, bin-minor
+    cat->h_seg_off.assign((size_t)P * B + 1, 0);
+    for (int p = 0; p < P; ++p)
+        for (int b = 0; b < B; ++b)
+            cat->h_seg_off[(size_t)p * B + b + 1] =
+                cat->h_seg_off[(size_t)p * B + b] + (int)cat->h_counts[(size_t)b * P + p];
+    if (dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1)) return 1;
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int),
+                              cudaMemcpyHostToDevice, st));
+
+    // frames: centre = mean direction, e1/e2 any orthonormal tangent basis
+    cat->h_frames.assign(P, PatchFrame{});
+    for (int p = 0; p < P; ++p) {
+        PatchFrame &f = cat->h_frames[p];
+        double cx = sums[3 * p], cy = sums[3 * p + 1], cz = sums[3 * p + 2];
+        double nrm = std::sqrt(cx * cx + cy * cy + cz * cz);
+        if (!(nrm > 1e-12)) { cx = 0; cy = 0; cz = 1; nrm = 1; }  // empty or antipodally balanced patch
+        f.c[0] = cx / nrm; f.c[1] = cy / nrm; f.c[2] = cz / nrm;
+        double ax = 0, ay = 0, az = 1;  // helper axis least aligned with c
+        if (std::fabs(f.c[2]) > 0.9) { ax = 1; az = 0; }
+        double e1x = ay * f.c[2] - az * f.c[1], e1y = az * f.c[0] - ax * f.c[2], e1z = ax * f.c[1] - ay * f.c[0];
+        double n1 = std::sqrt(e1x * e1x + e1y * e1y + e1z * e1z);
+        f.e1[0] = e1x / n1; f.e1[1] = e1y / n1; f.e1[2] = e1z / n1;
+        f.e2[0] = f.c[1] * f.e1[2] - f.c[2] * f.e1[1];
+        f.e2[1] = f.c[2] * f.e1[0] - f.c[0] * f.e1[2];
+        f.e2[2] = f.c[0] * f.e1[1] - f.c[1] * f.e1[0];
+    }
+    if (dev_alloc(cat, &cat->d_frames, P)) return 1;
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_frames, cat->h_frames.data(), P * sizeof(PatchFrame),
+                              cudaMemcpyHostToDevice, st));
+
+    // bounding boxes / radii
+    std::vector<unsigned long long> box(P * 5);
+    for (int p = 0; p < P; ++p) {
+        box[5 * p] = box[5 * p + 2] = ~0ull;
+        box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
+    }
+    YAWB_CUDA(cudaMemcpyAsync(d_box, box.data(), P * 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    if (n > 0)
+        k_patch_bbox<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n, cat->d_frames,
+                                                         d_box);
+    YAWB_CUDA(cudaMemcpyAsync(box.data(), d_box, P * 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < P; ++p) {
+        PatchFrame &f = cat->h_frames[p];
+        if (box[5 * p] == ~0ull) {  // no rows
+            f.umin = f.umax = f.vmin = f.vmax = 0.0;
+            f.radius = 0.0;
+        } else {
+            f.umin = dec_double(box[5 * p]);
+            f.umax = dec_double(box[5 * p + 1]);
+            f.vmin = dec_double(box[5 * p + 2]);
+            f.vmax = dec_double(box[5 * p + 3]);
+            f.radius = std::sqrt(dec_double(box[5 * p + 4])) * (1.0 + 1e-12) + 1e-15;
+        }
+    }
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_frames, cat->h_frames.data(), P * sizeof(PatchFrame),
+                              cudaMemcpyHostToDevice, st));
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_poff);
+    cudaFree(d_sums);
+    cudaFree(d_sumw);
+    cudaFree(d_counts);
+    cudaFree(d_box);
+    YAWB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------
+int yawb_index_build_first(yawb_cat *cat) {
+    if (cat->has_sindex) return 0;
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    const long long n_in = cat->n_in, n = cat->n;
+    const int P = cat->n_patch, B = cat->n_bins;
+
+    // grid per patch: cell edge from the mean density of one z-bin of this patch
+    cat->h_sgrid.assign(P, SGrid{});
+    long long base = 0;
+    for (int p = 0; p < P; ++p) {
+        const PatchFrame &f = cat->h_frames[p];
+        long long np = cat->h_seg_off[(size_t)(p + 1) * B] - cat->h_seg_off[(size_t)p * B];
+        double du = std::max(f.umax - f.umin, 0.0), dv = std::max(f.vmax - f.vmin, 0.0);
+        double per_bin = std::max((double)np / B, 1.0);
+        double area = std::max(du * dv, 1e-30);
+        double c = std::sqrt(kTargetPerCell * area / per_bin);
+        double span = std::max(du, dv);
+        if (!(c > 0.0) || span <= 0.0) c = 1.0;
+        c = std::max(c, span / 2048.0);  // bound the grid, <= 2048 x 2048 cells
+        SGrid &g = cat->h_sgrid[p];
+        g.u0 = f.umin;
+        g.v0 = f.vmin;
+        g.inv_c = 1.0 / c;
+        g.gu = std::max(1, (int)std::floor(du / c) + 1);
+        g.gv = std::max(1, (int)std::floor(dv / c) + 1);
+        while ((long long)g.gu * g.gv > kMaxCellsPerPatchBin) {  // defensive; unreachable with the bound above
+            c *= 2.0; g.inv_c = 1.0 / c;
+            g.gu = std::max(1, (int)std::floor(du / c) + 1);
+            g.gv = std::max(1, (int)std::floor(dv / c) + 1);
+        }
+        g.cell_base = base;
+        base += (long long)B * g.gu * g.gv;
+    }
+    cat->n_cells = base;
+    YAWB_REQUIRE(base < (1ll << 40), "sky-cell index too large (%lld cells)", base);
+    if (dev_alloc(cat, &cat->d_sgrid, P)) return 1;
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid), cudaMemcpyHostToDevice, st));
+
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    unsigned *v0 = nullptr, *v1 = nullptr;
+    size_t nn = std::max<long long>(n_in, 1);
+    YAWB_CUDA(cudaMalloc(&k0, nn * 8)); YAWB_CUDA(cudaMalloc(&k1, nn * 8));
+    YAWB_CUDA(cudaMalloc(&v0, nn * 4)); YAWB_CUDA(cudaMalloc(&v1, nn * 4));
+    if (n_in > 0) {
+        k_keys_first<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in,
+                                                            B, cat->d_frames, cat->d_sgrid, k0, v0);
+        // dropped rows carry key ~0: sort all 64 bits only if something was dropped
+        int end_bit = (n == n_in) ? bits_for((unsigned long long)std::max<long long>(base, 1)) : 64;
+        if (sort_pairs(ctx, k0, k1, v0, v1, n_in, end_bit)) return 1;
+    }
+    if (dev_alloc(cat, &cat->sx, n) || dev_alloc(cat, &cat->sy, n) || dev_alloc(cat, &cat->sz, n)) return 1;
+    if (cat->weighted && dev_alloc(cat, &cat->sw, n)) return 1;
+    if (dev_alloc(cat, &cat->cell_start, base + 1)) return 1;
+    if (n > 0)
+        k_gather<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->sx, cat->sy,
+                                                     cat->sz, cat->sw);
+    k_cell_start<<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, cat->cell_start);
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
+    YAWB_CUDA(cudaGetLastError());
+    cat->has_sindex = true;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------
+int yawb_index_build_second(yawb_cat *cat) {
+    if (cat->has_rtiles) return 0;
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    const long long n_in = cat->n_in, n = cat->n;
+    const int P = cat->n_patch, B = cat->n_bins;
+
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    unsigned *v0 = nullptr, *v1 = nullptr;
+    size_t nn = std::max<long long>(n_in, 1);
+    YAWB_CUDA(cudaMalloc(&k0, nn * 8)); YAWB_CUDA(cudaMalloc(&k1, nn * 8));
+    YAWB_CUDA(cudaMalloc(&v0, nn * 4)); YAWB_CUDA(cudaMalloc(&v1, nn * 4));
+    if (n_in > 0) {
+        k_keys_second<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch,
+                                                             n_in, B, cat->d_frames, k0, v0);
+        int end_bit = (n == n_in) ? 32 + bits_for((unsigned long long)std::max<long long>((long long)P * B, 1)) : 64;
+        if (sort_pairs(ctx, k0, k1, v0, v1, n_in, std::min(end_bit, 64))) return 1;
+    }
+    if (dev_alloc(cat, &cat->rx, n) || dev_alloc(cat, &cat->ry, n) || dev_alloc(cat, &cat->rz, n)) return 1;
+    if (cat->weighted && dev_alloc(cat, &cat->rw, n)) return 1;
+    if (n > 0)
+        k_gather<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->rx, cat->ry,
+                                                     cat->rz, cat->rw);
+
+    // tiles: chunks of YAWB_TILE rows inside each (patch, bin) segment
+    std::vector<Tile> tiles;
+    cat->h_ptile_off.assign(P + 1, 0);
+    for (int p = 0; p < P; ++p) {
+        cat->h_ptile_off[p] = (int)tiles.size();
+        for (int b = 0; b < B; ++b) {
+            int s = cat->h_seg_off[(size_t)p * B + b], e = cat->h_seg_off[(size_t)p * B + b + 1];
+            for (int t = s; t < e; t += YAWB_TILE) {
+                Tile tl{};
+                tl.start = t;
+                tl.count = std::min(YAWB_TILE, e - t);
+                tl.patch = p;
+                tl.bin = cat->binned ? b : -1;
+                tiles.push_back(tl);
+            }
+        }
+    }
+    cat->h_ptile_off[P] = (int)tiles.size();
+    cat->n_tiles = (int)tiles.size();
+    if (dev_alloc(cat, &cat->d_tiles, tiles.size()) || dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
+    if (!tiles.empty())
+        YAWB_CUDA(cudaMemcpyAsync(cat->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int),
+                              cudaMemcpyHostToDevice, st));
+    if (cat->n_tiles > 0)
+        k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz,
+                                                                                      cat->d_tiles, cat->n_tiles);
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
+    YAWB_CUDA(cudaGetLastError());
+    cat->has_rtiles = true;
+    return 0;
+}
+
+void yawb_index_free(yawb_cat *cat, bool everything) {
+    const size_t n = (size_t)cat->n, P = (size_t)cat->n_patch;
+    if (cat->has_sindex || everything) {
+        dev_free(cat, cat->sx, n); dev_free(cat, cat->sy, n); dev_free(cat, cat->sz, n);
+        dev_free(cat, cat->sw, n);
+        dev_free(cat, cat->d_sgrid, P);
+        dev_free(cat, cat->cell_start, (size_t)cat->n_cells + 1);
+        cat->has_sindex = false;
+    }
+    if (cat->has_rtiles || everything) {
+        dev_free(cat, cat->rx, n); dev_free(cat, cat->ry, n); dev_free(cat, cat->rz, n);
+        dev_free(cat, cat->rw, n);
+        dev_free(cat, cat->d_tiles, (size_t)cat->n_tiles);
+        dev_free(cat, cat->d_ptile_off, P + 1);
+        cat->has_rtiles = false;
+    }
+    if (everything) {
+        const size_t ni = (size_t)cat->n_in;
+        dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
+        dev_free(cat, cat->w, ni);
+        dev_free(cat, cat->bin, ni);
+        dev_free(cat, cat->patch, ni);
+        dev_free(cat, cat->d_frames, P);
+        dev_free(cat, cat->d_seg_off, P * (size_t)cat->n_bins + 1);
+    }
+}

@@ -1,0 +1,150 @@
+// Internal declarations shared by the translation units of libyawb.so.
+// Nothing here is part of the C ABI (see include/yawb.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "yawb.h"
+
+void yawb_set_error(const char *fmt, ...);
+
+#define YAWB_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess) {                                                            \
+            yawb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                       \
+                           cudaGetErrorString(err__));                                         \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define YAWB_REQUIRE(cond, ...)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            yawb_set_error(__VA_ARGS__);                                                       \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// ---- geometry of one patch: orthonormal frame at the mean direction --------------------
+struct PatchFrame {
+    double c[3];   // unit vector of the patch centre (mean direction)
+    double e1[3];  // tangent basis; (u, v, t) = ((P-c).e1, (P-c).e2, (P-c).c)
+    double e2[3];
+    double radius;                    // max chord distance of a patch point from c
+    double umin, umax, vmin, vmax;    // bounding box of the patch in (u, v)
+};
+
+// ---- sky-cell grid of one patch (first-role index); identical for every z-bin ------------
+struct SGrid {
+    double u0, v0, inv_c;  // cell (iu, iv) covers u0 + iu/inv_c ...
+    int gu, gv;            // cells per row / number of rows
+    long long cell_base;   // global cell id of (bin 0, iv 0, iu 0); bin stride = gu * gv
+};
+
+// ---- register tile of the second-role catalog -------------------------------------------
+struct Tile {
+    int start;   // first row in the Morton-sorted arrays
+    int count;   // <= YAWB_TILE
+    int patch;
+    int bin;     // z-bin of the tile, or -1 for an unbinned catalog
+    float cx, cy, cz;  // bounding sphere (centre rounded to float, radius rounded up)
+    float rad;
+};
+
+// ---- per z-bin thresholds prepared on the host for one yawb_count() call -----------------
+struct BinPar {
+    double lo, hi;  // r2[b][0], r2[b][n_edges-1]
+    double rmax;    // sqrt(hi) * (1 + 1e-9) + 1e-14: chord search radius
+    float mid, h;   // (lo + hi) / 2, (hi - lo) / 2 rounded to float
+    int empty;      // 1 if the bin cannot hold pairs (hi <= lo)
+    int pad;
+};
+
+constexpr int YAWB_RPL = 8;               // second-role points per lane
+constexpr int YAWB_TILE = 32 * YAWB_RPL;  // points per register tile (one warp)
+constexpr int YAWB_LCAP = 256;            // candidate list capacity per warp
+constexpr int YAWB_WARPS = 8;             // warps per CTA in the count kernel
+constexpr int YAWB_MAX_EDGES = 256;
+
+struct yawb_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *d_counters = nullptr;  // [8] work counter + statistics
+};
+
+struct yawb_cat {
+    yawb_ctx *ctx = nullptr;
+    int64_t n_in = 0;     // rows uploaded
+    int64_t n = 0;        // rows kept (z-bin in range)
+    int n_patch = 0;
+    int n_bins = 1;       // 1 for an unbinned catalog
+    bool binned = false;
+    bool weighted = false;
+    int64_t device_bytes = 0;
+
+    // raw rows in upload order (grouped by patch)
+    double *x = nullptr, *y = nullptr, *z = nullptr, *w = nullptr;
+    int32_t *bin = nullptr;    // nullptr if unbinned
+    int32_t *patch = nullptr;
+
+    // per patch
+    std::vector<PatchFrame> h_frames;
+    PatchFrame *d_frames = nullptr;
+    // per (bin, patch): number of rows and sum of weights, host copies
+    std::vector<long long> h_counts;   // [n_bins][n_patch]
+    std::vector<double> h_sumw;        // [n_bins][n_patch]
+    std::vector<int> h_seg_off;        // [(n_patch * n_bins) + 1], patch-major, bin-minor
+    int *d_seg_off = nullptr;
+
+    // first-role index: rows sorted by global sky-cell id
+    bool has_sindex = false;
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *sw = nullptr;
+    std::vector<SGrid> h_sgrid;
+    SGrid *d_sgrid = nullptr;
+    int *cell_start = nullptr;
+    long long n_cells = 0;
+
+    // second-role index: rows sorted by (patch, bin, Morton code), cut into register tiles
+    bool has_rtiles = false;
+    double *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
+    Tile *d_tiles = nullptr;
+    std::vector<int> h_ptile_off;  // [n_patch + 1] first tile of each patch
+    int *d_ptile_off = nullptr;
+    int n_tiles = 0;
+};
+
+// index construction (yawb_index.cu)
+int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
+                      const int32_t *zbin, const int64_t *patch_off);
+int yawb_index_build_first(yawb_cat *cat);
+int yawb_index_build_second(yawb_cat *cat);
+void yawb_index_free(yawb_cat *cat, bool everything);
+
+// pair counting (yawb_count.cu)
+struct CountArgs {
+    const yawb_cat *c1;
+    const yawb_cat *c2;
+    const int *d_pair_i;
+    const int *d_pair_j;
+    const long long *d_pair_item_base;  // [n_pairs + 1] prefix of tiles per pair
+    long long n_items;
+    int n_pairs;
+    int n_bins;
+    int n_edges;
+    const double *d_r2;      // [n_bins][n_edges]
+    const float *d_r2f;      // same, rounded to float
+    const BinPar *d_binpar;  // [n_bins]
+    unsigned long long *d_out_cnt;  // [n_pairs][n_bins][n_edges-1]
+    double *d_out_w;                // same or nullptr if both catalogs are unweighted
+    bool weighted;
+};
+int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches);
+int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches);

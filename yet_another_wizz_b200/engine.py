@@ -1,0 +1,178 @@
+"""
+Thin object wrappers over the C ABI: `Engine` (one per process / GPU) and
+`DeviceCatalog` (one patch-partitioned catalog resident in HBM).
+
+These are the B200 counterparts of the reference's worker pool
+(`src/yaw/utils/parallel.py:318-343`) and of its per-patch `BinnedTrees` cache
+(`src/yaw/catalog/trees.py:432-601`).  All arithmetic happens in libyawb.so.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+class DeviceCatalog:
+    """Handle of a catalog uploaded with `Engine.upload_catalog`."""
+
+    def __init__(self, engine: "Engine", handle: c_void_p, n_patch: int, n_bins: int, binned: bool, weighted: bool):
+        self.engine = engine
+        self._h = handle
+        self.n_patch = n_patch
+        self.n_bins = n_bins
+        self.binned = binned
+        self.weighted = weighted
+
+    def sum_weights(self) -> np.ndarray:
+        """`(n_bins, n_patch)` sum of weights (row counts if unweighted)."""
+        out = np.empty((self.n_bins, self.n_patch), dtype=np.float64)
+        _lib.check(self.engine.lib.yawb_sum_weights(self._h, _ptr(out)))
+        return out
+
+    def info(self) -> tuple[int, int]:
+        n, nbytes = c_int64(), c_int64()
+        _lib.check(self.engine.lib.yawb_catalog_info(self._h, byref(n), byref(nbytes)))
+        return n.value, nbytes.value
+
+    def build_index(self, role: int) -> float:
+        ms = c_double()
+        _lib.check(self.engine.lib.yawb_build_index(self._h, role, byref(ms)))
+        return ms.value
+
+    def drop_index(self) -> None:
+        _lib.check(self.engine.lib.yawb_drop_index(self._h))
+
+    def free(self) -> None:
+        if self._h is not None:
+            self.engine.lib.yawb_free_catalog(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One context on one CUDA device.  Raises if the device or library is missing."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = c_void_p()
+        _lib.check(self.lib.yawb_create(int(device), byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._cats: list[DeviceCatalog] = []
+
+    @property
+    def num_sms(self) -> int:
+        return self.lib.yawb_device_sms(self._h)
+
+    def upload_catalog(
+        self,
+        xyz: np.ndarray,
+        patch_off: np.ndarray,
+        *,
+        weights: np.ndarray | None = None,
+        zbin: np.ndarray | None = None,
+        n_bins: int = 1,
+    ) -> DeviceCatalog:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        patch_off = np.ascontiguousarray(patch_off, dtype=np.int64)
+        n = len(xyz)
+        if patch_off[-1] != n:
+            raise ValueError("patch_off[-1] must equal the number of rows")
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
+            if len(weights) != n:
+                raise ValueError("shape of 'xyz' and 'weights' does not match")
+        if zbin is not None:
+            zbin = np.ascontiguousarray(zbin, dtype=np.int32)
+            if len(zbin) != n:
+                raise ValueError("shape of 'xyz' and 'zbin' does not match")
+        h = c_void_p()
+        _lib.check(
+            self.lib.yawb_upload_catalog(
+                self._h, _ptr(xyz), _ptr(weights), _ptr(zbin), _ptr(patch_off),
+                len(patch_off) - 1, int(n_bins), byref(h),
+            )
+        )
+        cat = DeviceCatalog(self, h, len(patch_off) - 1, int(n_bins) if zbin is not None else 1,
+                            zbin is not None, weights is not None)
+        return cat
+
+    def count(
+        self,
+        cat1: DeviceCatalog,
+        cat2: DeviceCatalog,
+        pair_i: np.ndarray,
+        pair_j: np.ndarray,
+        r2_edges: np.ndarray,
+        *,
+        exact: bool = False,
+    ) -> tuple[np.ndarray, np.ndarray, dict]:
+        """
+        Returns `(counts_i64, sums_f64, stats)`, both arrays shaped
+        `(n_pairs, n_bins, n_edges - 1)`.
+        """
+        pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+        r2_edges = np.ascontiguousarray(r2_edges, dtype=np.float64)
+        n_bins = cat1.n_bins
+        if r2_edges.ndim == 1:
+            r2_edges = np.ascontiguousarray(np.broadcast_to(r2_edges, (n_bins, len(r2_edges))))
+        if r2_edges.shape[0] != n_bins:
+            raise ValueError(f"r2_edges must have shape (n_bins={n_bins}, n_edges)")
+        n_edges = r2_edges.shape[1]
+        n_pairs = len(pair_i)
+        out_i = np.zeros((n_pairs, n_bins, n_edges - 1), dtype=np.int64)
+        out_f = np.zeros((n_pairs, n_bins, n_edges - 1), dtype=np.float64)
+        stats = _lib.YawbStats()
+        flags = _lib.FLAG_EXACT_BRUTEFORCE if exact else 0
+        _lib.check(
+            self.lib.yawb_count(
+                self._h, cat1._h, cat2._h, _ptr(pair_i), _ptr(pair_j), n_pairs, _ptr(r2_edges), n_edges,
+                flags, _ptr(out_f), _ptr(out_i), byref(stats),
+            )
+        )
+        return out_i, out_f, stats.as_dict()
+
+    def count_into_device(self, cat1, cat2, pair_i, pair_j, r2_edges, out_f64_ptr: int, out_i64_ptr: int):
+        """Variant writing into caller-owned device buffers (raw pointers)."""
+        pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+        r2_edges = np.ascontiguousarray(r2_edges, dtype=np.float64)
+        stats = _lib.YawbStats()
+        _lib.check(
+            self.lib.yawb_count(
+                self._h, cat1._h, cat2._h, _ptr(pair_i), _ptr(pair_j), len(pair_i), _ptr(r2_edges),
+                r2_edges.shape[1], _lib.FLAG_OUT_DEVICE,
+                c_void_p(out_f64_ptr) if out_f64_ptr else None,
+                c_void_p(out_i64_ptr) if out_i64_ptr else None, byref(stats),
+            )
+        )
+        return stats.as_dict()
+
+    def sync(self) -> None:
+        _lib.check(self.lib.yawb_sync(self._h))
+
+    def close(self) -> None:
+        if self._h is not None:
+            self.lib.yawb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
