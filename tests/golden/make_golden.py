@@ -199,7 +199,10 @@ def case_edge(name, n=1500, theta=3.7e-3, seed=11):
     A = AngularCoordinates.from_3d(a)
     B = AngularCoordinates.from_3d(b)
     ta, tb = AngularTree(A), AngularTree(B)
-    out = dict(a_radec=A.data, b_radec=B.data, theta=np.array(theta))
+    # store the exact doubles the reference's trees hold: numpy's sin/cos may differ by an
+    # ulp between CPUs, which is enough to flip on-edge pairs
+    out = dict(a_radec=A.data, b_radec=B.data, a_xyz=np.array(ta.data), b_xyz=np.array(tb.data),
+               theta=np.array(theta))
     # edge exactly on theta as upper limit, as lower limit, and both (multi-bin)
     specs = {
         "upper": ([theta / 10], [theta]),

@@ -191,16 +191,15 @@ def test_edge_adversarial(engine, exact):
     """pairs within a few ulp of a bin edge: only the reference's FP64 evaluation
     order reproduces scipy; golden counts from the reference"""
     g = golden_io.load("edge_adversarial")
-    a = oracle.radec_to_xyz(g["a_radec"][:, 0], g["a_radec"][:, 1])
-    b = oracle.radec_to_xyz(g["b_radec"][:, 0], g["b_radec"][:, 1])
-    for key in ("upper", "lower"):
-        r2 = oracle.chord_sq_edges(np.array([g[f"{key}_ang_min"][0], g[f"{key}_ang_max"][0]]))
+    a, b = g["a_xyz"], g["b_xyz"]  # exact doubles of the reference trees
+    # edges exactly as the reference forms them: limits -> log10 -> unique -> 10** (trees.py:107-117)
+    for key in ("upper", "lower", "multi"):
+        lim = oracle.parse_ang_limits(g[f"{key}_ang_min"], g[f"{key}_ang_max"])
+        ang_bins = oracle.get_ang_bins(lim, None, 50)
+        r2 = oracle.chord_sq_edges(ang_bins)
         ci, _, stats = single_patch_hist(engine, a, None, b, None, r2, exact)
-        assert ci[0] == int(g[f"{key}_counts"][0])
-    theta = float(g["theta"])
-    r2 = oracle.chord_sq_edges(np.array([theta / 10, theta, theta * 3]))
-    ci, _, stats = single_patch_hist(engine, a, None, b, None, r2, exact)
-    assert_array_equal(ci, g["multi_counts"].astype(np.int64))
+        got = oracle.get_counts_for_limits(ci.astype(np.float64), ang_bins, lim)
+        assert_array_equal(got, g[f"{key}_counts"])
     if not exact:
         assert stats["rechecks"] > 0  # the FP64 recheck path was exercised
 
