@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""
+Benchmark of the pair-counting hot path: one "step" = one full `crosscorrelate` counting pass
+(index build + DD + DR + RD + RR) over the synthetic workload named by BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3]
+
+Prints ONE JSON line (rank 0).  Metric: effective pair tests per second =
+(sum over count types, linked patch pairs and z-bins of n1*n2, a property of the workload)
+/ step time.  The same numerator is used for the GPU arm and for the CPU reference arm, so the
+two lines are directly comparable; `roofline` reports the tests the kernel actually EXECUTED
+(after sky-cell pruning) against the FP32 CUDA-core pair-test roofline of SURVEY.md section 8d.
+
+  value    inputs (raw unit vectors, z-bin ids) already resident in HBM; the timed region covers
+           index build (keys, radix sort, gather, cell table, tiles) + the four count kernels +
+           the D2H of the per-patch-pair results, timed with CUDA events on the engine's stream
+  e2e      the C-ABI calls with HOST buffers: H2D upload of every catalog from pinned memory,
+           index build, counts, D2H of the results -- wall clock around the calls
+  --impl reference   the CPU implementation of the same path (oracle/cpu_port.py: scipy cKDTree
+           dual-tree count_neighbors + multiprocessing task farm, exactly the reference's
+           algorithm; /root/reference itself does not exist on the GPU box) on a bounded sample
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n_ref, n_unk, n_ref_rand, n_unk_rand, grid (nx, ny), zmin, zmax, n_bins   
+    "C1": dict(n=(100_000, 100_000, 1_000_000, 1_000_000), grid=(4, 4), zmin=0.1, zmax=1.0, bins=10),
+    "C3": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30),
+    "C5": dict(n=(10_000_000, 100_000_000, 100_000_000, 100_000_000), grid=(16, 16), zmin=0.07, zmax=1.42, bins=50),
+}
+BOX = (0.0, 40.0, -12.5, 12.5)
+SEEDS = dict(ref=1, unk=2, ref_rand=3, unk_rand=4)
+FP32_INSTR_PER_TEST = 6  # 3 FSUB + FMUL + 2 FFMA, SURVEY.md section 8d
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- workload ------------------------------------------------------------------------------------
+def make_workload(name: str, scale: float = 1.0):
+    """BoxRandoms catalogs + configuration + host-prepared arrays of the workload."""
+    import yet_another_wizz_b200 as yb
+    from yet_another_wizz_b200.measurements import PatchLinkage, _angles_per_bin, prepare_catalog_arrays
+    from yet_another_wizz_b200.angular import AngularBinPlan
+
+    spec = WORKLOADS[name]
+    nx, ny = spec["grid"]
+    ras = BOX[0] + (np.arange(nx) + 0.5) * (BOX[1] - BOX[0]) / nx
+    decs = BOX[2] + (np.arange(ny) + 0.5) * (BOX[3] - BOX[2]) / ny
+    centers = yb.AngularCoordinates(np.deg2rad([[r, d] for d in decs for r in ras]))
+    pool = np.random.default_rng(7).uniform(spec["zmin"], spec["zmax"], 1_000_000)
+    config = yb.Configuration.create(rmin=100, rmax=1000, zmin=spec["zmin"], zmax=spec["zmax"], num_bins=spec["bins"])
+    binning = config.binning.binning
+
+    t0 = time.perf_counter()
+    cats, arrays = {}, {}
+    for key, n in zip(("ref", "unk", "ref_rand", "unk_rand"), spec["n"]):
+        n = max(int(n * scale), 1000)
+        has_z = key in ("ref", "ref_rand")
+        gen = yb.BoxRandoms(*BOX, redshifts=pool if has_z else None, seed=SEEDS[key])
+        cats[key] = yb.Catalog.from_random(key, gen, n, patch_centers=centers)
+    t_cat = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for key, cat in cats.items():
+        arrays[key] = prepare_catalog_arrays(cat, binning if key in ("ref", "ref_rand") else None)
+    t_prep = time.perf_counter() - t0
+
+    links = PatchLinkage.from_catalogs(config, cats["ref"], cats["unk"], cats["ref_rand"], cats["unk_rand"])
+    pair_i, pair_j = links.get_patch_id_pairs(auto=False)
+    amin, amax = _angles_per_bin(config)
+    plan = AngularBinPlan(amin, amax, None, None)
+
+    # naive linked pair tests per count type
+    naive = {}
+    counts = {k: np.diff(arrays[k]["patch_off"]) for k in arrays}
+    binned_counts = {}
+    for k in ("ref", "ref_rand"):
+        zb, off = arrays[k]["zbin"], arrays[k]["patch_off"]
+        ok = (zb >= 0) & (zb < len(binning))
+        binned_counts[k] = np.add.reduceat(ok.astype(np.int64), off[:-1])
+    for tag, (a, b) in dict(DD=("ref", "unk"), DR=("ref", "unk_rand"), RD=("ref_rand", "unk"),
+                            RR=("ref_rand", "unk_rand")).items():
+        naive[tag] = int((binned_counts[a][pair_i].astype(np.float64) * counts[b][pair_j]).sum())
+    return dict(name=name, spec=spec, config=config, cats=cats, arrays=arrays, pair_i=pair_i, pair_j=pair_j,
+                plan=plan, naive=naive, t_catalogs=t_cat, t_host_prep=t_prep, n_patch=nx * ny)
+
+
+COUNT_TYPES = dict(DD=("ref", "unk"), DR=("ref", "unk_rand"), RD=("ref_rand", "unk"), RR=("ref_rand", "unk_rand"))
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.rows, self._stop, self.index = [], threading.Event(), index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
+                    samples=len(self.rows), power_w_max=max(float(r[2]) for r in self.rows))
+
+
+# ---- CPU arm (oracle port of the reference's dual-tree path) --------------------------------------------
+def cpu_sample(wl, budget_s: float, workers: int | None = None, fixed_m: int | None = None):
+    """Time the CPU implementation on a bounded sample: the first `m` patches' diagonal pairs plus all
+    their links, all four count types, trees built for exactly the patches touched."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_port
+
+    workers = workers or cpu_port.physical_cores()
+    pi, pj = wl["pair_i"], wl["pair_j"]
+    n_bins = len(wl["config"].binning.binning)
+    plan = wl["plan"]
+    ang_min = np.array([lim[:, 0] for lim in plan.limits])
+    ang_max = np.array([lim[:, 1] for lim in plan.limits])
+
+    def rows_of(key, patches, binned):
+        a = wl["arrays"][key]
+        out = {}
+        for p in patches:
+            s, e = a["patch_off"][p], a["patch_off"][p + 1]
+            out[p] = (a["xyz"][s:e], None if a["weights"] is None else a["weights"][s:e],
+                      a["zbin"][s:e] if binned else None)
+        return out
+
+    def run(m):
+        first = set(range(m))
+        sel = [(int(i), int(j)) for i, j in zip(pi, pj) if int(i) in first]
+        need1 = sorted({i for i, _ in sel})
+        need2 = sorted({j for _, j in sel})
+        t_build = t_count = 0.0
+        naive = 0
+        trees = {}
+        for key, binned, need in (("ref", True, need1), ("ref_rand", True, need1), ("unk", False, need2),
+                                  ("unk_rand", False, need2)):
+            rows = rows_of(key, need, binned)
+            built, dt = cpu_port.build_catalog_trees([rows[p] for p in need], n_bins if binned else None)
+            trees[key] = dict(zip(need, built))
+            t_build += dt
+        for tag, (a, b) in COUNT_TYPES.items():
+            _, dt = cpu_port.count_pairs(trees[a], trees[b], sel, ang_min, ang_max, workers=workers)
+            t_count += dt
+            ca, cb = wl["arrays"][a], wl["arrays"][b]
+            for i, j in sel:
+                zb = ca["zbin"][ca["patch_off"][i]:ca["patch_off"][i + 1]]
+                n1 = int(((zb >= 0) & (zb < n_bins)).sum())
+                naive += n1 * int(cb["patch_off"][j + 1] - cb["patch_off"][j])
+        return dict(patches=m, pairs=len(sel), t_build=t_build, t_count=t_count, naive=naive, workers=workers)
+
+    if fixed_m is not None:
+        return run(fixed_m)
+    # grow the sample until it is worth ~budget_s of CPU work
+    m = 1
+    res = run(m)
+    while res["t_build"] + res["t_count"] < budget_s / 3 and m < wl["n_patch"]:
+        per_patch = (res["t_build"] + res["t_count"]) / m
+        m = int(min(wl["n_patch"], max(m + 1, budget_s / max(per_patch, 1e-3))))
+        res = run(m)
+    return res
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args.workload, args.scale)
+    total_naive = sum(wl["naive"].values())
+    times, last = [], None
+    budget = args.cpu_budget
+    for step in range(args.warmup + args.steps):
+        last = cpu_sample(wl, budget) if last is None else cpu_sample(wl, budget, fixed_m=last["patches"])
+        if step >= args.warmup:
+            times.append(last["t_build"] + last["t_count"])
+    t = float(np.mean(times))
+    value = last["naive"] / t / 1e9
+    line = dict(
+        impl="reference", metric="crosscorrelate_effective_pair_tests_per_s", value=value, unit="Gpairs/s",
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
+        scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=f"{wl['name']} crosscorrelate DD+DR+RD+RR, BoxRandoms, scale={args.scale}",
+                    sample=f"{last['patches']} of {wl['n_patch']} first-catalog patches with all their links "
+                           f"({last['pairs']} patch pairs x 4 count types), tree build included"),
+        cpu_baseline=dict(value=value, unit="Gpairs/s", cores=last["workers"], kind="port",
+                          sample=f"{last['patches']}/{wl['n_patch']} patches, {last['pairs']} patch pairs, "
+                                 f"build {last['t_build']:.2f}s + count {last['t_count']:.2f}s",
+                          extrapolated_full_job_s=t * total_naive / max(last["naive"], 1)),
+        e2e=dict(value=value, unit="Gpairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0,
+    )
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import yet_another_wizz_b200 as yb
+    from yet_another_wizz_b200 import _lib
+    from yet_another_wizz_b200.sharding import assign_pairs_lpt, pair_costs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+
+    wl = make_workload(args.workload, args.scale)
+    if rank == 0:
+        log(f"[bench] workload {wl['name']} scale {args.scale}: catalogs {wl['t_catalogs']:.1f}s, "
+            f"host prep {wl['t_host_prep']:.1f}s, {len(wl['pair_i'])} linked patch pairs, naive tests {wl['naive']}")
+    eng = yb.Engine(local_rank)
+    pi, pj, plan = wl["pair_i"], wl["pair_j"], wl["plan"]
+    total_naive = sum(wl["naive"].values())
+
+    # this rank's share of the patch pairs (static LPT on the cost model)
+    own = np.arange(len(pi))
+    if world > 1:
+        n1 = np.diff(wl["arrays"]["ref_rand"]["patch_off"])
+        n2 = np.diff(wl["arrays"]["unk_rand"]["patch_off"])
+        own = assign_pairs_lpt(pair_costs(pi, pj, n1, n2), world)[rank]
+    opi, opj = pi[own], pj[own]
+
+    # pinned host staging of the inputs (what a caller holding host buffers hands to the C ABI)
+    host = {}
+    h2d_bytes = 0
+    for key, a in wl["arrays"].items():
+        h = {}
+        for name in ("xyz", "weights", "zbin"):
+            if a[name] is None:
+                h[name] = None
+                continue
+            buf = eng.pinned_empty(a[name].shape, a[name].dtype)
+            buf[...] = a[name]
+            h[name] = buf
+            h2d_bytes += buf.nbytes
+        h["patch_off"], h["n_bins"] = a["patch_off"], a["n_bins"]
+        host[key] = h
+
+    def upload_all():
+        return {k: eng.upload_catalog(h["xyz"], h["patch_off"], weights=h["weights"], zbin=h["zbin"], n_bins=h["n_bins"])
+                for k, h in host.items()}
+
+    n_out = len(pi) * plan.n_bins * (plan.n_edges - 1)
+    d2h_bytes = 4 * len(opi) * plan.n_bins * (plan.n_edges - 1) * 16
+
+    def reduce_results(results):
+        if world == 1:
+            return results
+        import torch
+
+        full = np.zeros((4, len(pi), plan.n_bins, plan.n_edges - 1), dtype=np.int64)
+        for t, tag in enumerate(COUNT_TYPES):
+            full[t, own] = results[tag]
+        ten = torch.from_numpy(full).cuda()
+        dist.reduce(ten, dst=0, op=dist.ReduceOp.SUM)  # the single NCCL reduce of the count tensors
+        torch.cuda.synchronize()
+        return {tag: ten[t].cpu().numpy() for t, tag in enumerate(COUNT_TYPES)}
+
+    def count_all(dev):
+        results, stats = {}, {}
+        for tag, (a, b) in COUNT_TYPES.items():
+            ci, _, st = eng.count(dev[a], dev[b], opi, opj, plan.r2)
+            results[tag], stats[tag] = ci, st
+        return results, stats
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        eng.sync()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: raw inputs resident in HBM -> index build + counts ----
+    dev = upload_all()
+    step_ms, kernel_ms, index_ms, stats_last, launches = [], [], [], None, 0
+    clocks = ClockSampler(local_rank)
+    results = None
+    with clocks:
+        for step in range(args.warmup + args.steps):
+            for d in dev.values():
+                d.drop_index()
+            barrier()
+            eng.timer_start()
+            t_idx = 0.0
+            for key, d in dev.items():
+                t_idx += d.build_index(_lib.ROLE_FIRST if key in ("ref", "ref_rand") else _lib.ROLE_SECOND)
+            results, stats = count_all(dev)
+            ms = eng.timer_stop()
+            results = reduce_results(results)
+            barrier()
+            if step >= args.warmup:
+                step_ms.append(max_over_ranks(ms))
+                kernel_ms.append(sum(s["kernel_ms"] for s in stats.values()))
+                index_ms.append(t_idx)
+                stats_last = stats
+                launches += sum(s["launches"] for s in stats.values())
+    for d in dev.values():
+        d.free()
+
+    # ---- e2e: host buffers through the C ABI ----
+    e2e_s = []
+    for step in range(max(1, min(args.warmup, 1)) + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        dev = upload_all()
+        results_e2e, _ = count_all(dev)
+        results_e2e = reduce_results(results_e2e)
+        barrier()
+        dt = time.perf_counter() - t0
+        for d in dev.values():
+            d.free()
+        if step >= 1:
+            e2e_s.append(max_over_ranks(dt))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- report ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    sms = eng.num_sms
+    peak_tests = sms * 128 * sm_max_mhz * 1e6 / FP32_INSTR_PER_TEST
+    t_step = float(np.mean(step_ms)) / 1e3
+    t_kernel = float(np.mean(kernel_ms)) / 1e3
+    executed = sum(s["pair_tests"] for s in stats_last.values())
+    achieved = executed / max(t_kernel, 1e-12)
+    in_scale = {tag: int(results[tag].sum()) for tag in COUNT_TYPES}
+    clk = clocks.summary()
+
+    line = dict(
+        metric="crosscorrelate_effective_pair_tests_per_s", value=total_naive / t_step / 1e9, unit="Gpairs/s",
+        n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=t_step * 1e3, higher_is_better=True,
+        scaling="strong", vs_baseline=None, dtype="f32+f64", data="synthetic",
+        config=dict(
+            workload=f"{wl['name']} crosscorrelate DD+DR+RD+RR: {wl['spec']['n']} rows x scale {args.scale}, "
+                     f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, 100-1000 kpc, BoxRandoms {BOX}",
+            linked_patch_pairs=int(len(pi)), naive_pair_tests=wl["naive"], pairs_in_scale=in_scale,
+            l2="inputs (>= 1 GB of catalog rows) exceed the 126 MB L2; every step rebuilds the index from the raw rows",
+            parallelism=f"patch-pair LPT sharding over {world} GPU(s), catalogs replicated, one NCCL reduce",
+        ),
+        breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=t_kernel * 1e3,
+                          per_count={tag: stats_last[tag]["kernel_ms"] for tag in COUNT_TYPES},
+                          host_prep_s=wl["t_host_prep"], catalogs_s=wl["t_catalogs"]),
+        roofline=dict(
+            bound="fp32", achieved=achieved / 1e9, peak=peak_tests / 1e9, unit="Gtests/s",
+            frac=achieved / peak_tests, traffic=None,
+            note=f"pair-count kernels of rank 0; executed (non-pruned) tests / kernel time vs {sms} SMs x 128 lanes x "
+                 f"{sm_max_mhz:.0f} MHz / {FP32_INSTR_PER_TEST} FP32 instr per test (MEASURED_PEAKS.json sm_max_mhz)",
+            executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(sum(
+                s["pair_tests_naive"] for s in stats_last.values()), 1),
+            useful_fraction=sum(in_scale.values()) / max(executed, 1),
+            fp64_rechecks=int(sum(s["rechecks"] for s in stats_last.values())),
+        ),
+        e2e=dict(value=total_naive / float(np.mean(e2e_s)) / 1e9, unit="Gpairs/s", ms_per_step=float(np.mean(e2e_s)) * 1e3,
+                 h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+        gpu_launches=int(launches),
+        clocks=clk,
+    )
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_sample(wl, args.cpu_budget)
+        t_cpu = cpu["t_build"] + cpu["t_count"]
+        line["cpu_baseline"] = dict(
+            value=cpu["naive"] / t_cpu / 1e9, unit="Gpairs/s", cores=cpu["workers"], kind="port",
+            sample=f"{cpu['patches']}/{wl['n_patch']} first-catalog patches with all links ({cpu['pairs']} patch pairs "
+                   f"x 4 count types): tree build {cpu['t_build']:.2f}s + count {cpu['t_count']:.2f}s",
+            extrapolated_full_job_s=t_cpu * total_naive / max(cpu["naive"], 1),
+        )
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=list(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every catalog (development only)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

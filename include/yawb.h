@@ -131,6 +131,11 @@ int yawb_host_free(void *ptr);
 /* Block until all work of the context has finished. */
 int yawb_sync(yawb_ctx *ctx);
 
+/* Device-side stopwatch on the context's stream (CUDA events), for benchmarks: everything the
+ * context enqueues between start and stop is covered.  stop waits for the stream. */
+int yawb_timer_start(yawb_ctx *ctx);
+int yawb_timer_stop(yawb_ctx *ctx, double *ms);
+
 /* Library version and number of SMs of the context's device. */
 int yawb_version(void);
 int yawb_device_sms(const yawb_ctx *ctx);

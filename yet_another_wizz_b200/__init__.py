@@ -8,7 +8,18 @@ that path.  There is no CPU fallback.
 """
 
 from ._lib import YawbError
+from .binning import Binning
+from .catalog import Catalog, InconsistentPatchesError
+from .config import Configuration
+from .coordinates import AngularCoordinates, AngularDistances
+from .corrfunc import CorrFunc
 from .engine import DeviceCatalog, Engine
+from .measurements import PatchLinkage, autocorrelate, crosscorrelate
+from .randoms import BoxRandoms
 
-__all__ = ["DeviceCatalog", "Engine", "YawbError"]
+__all__ = [
+    "AngularCoordinates", "AngularDistances", "Binning", "BoxRandoms", "Catalog", "Configuration", "CorrFunc",
+    "DeviceCatalog", "Engine", "InconsistentPatchesError", "PatchLinkage", "YawbError", "autocorrelate",
+    "crosscorrelate",
+]
 __version__ = "0.1.0"

@@ -25,6 +25,7 @@ EXPORTS = (
     "yawb_last_error", "yawb_create", "yawb_destroy", "yawb_upload_catalog", "yawb_free_catalog",
     "yawb_build_index", "yawb_drop_index", "yawb_catalog_info", "yawb_sum_weights", "yawb_count",
     "yawb_host_alloc", "yawb_host_free", "yawb_sync", "yawb_version", "yawb_device_sms",
+    "yawb_timer_start", "yawb_timer_stop",
 )
 
 
@@ -73,6 +74,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.yawb_destroy.argtypes = [c_void_p]
     lib.yawb_device_sms.argtypes = [c_void_p]
     lib.yawb_sync.argtypes = [c_void_p]
+    lib.yawb_timer_start.argtypes = [c_void_p]
+    lib.yawb_timer_stop.argtypes = [c_void_p, POINTER(c_double)]
     lib.yawb_host_alloc.argtypes = [POINTER(c_void_p), c_uint64]
     lib.yawb_host_free.argtypes = [c_void_p]
     lib.yawb_upload_catalog.argtypes = [

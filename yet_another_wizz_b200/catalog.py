@@ -141,13 +141,10 @@ def _nearest_center(xyz: np.ndarray, centers_xyz: np.ndarray) -> np.ndarray:
     """index of the nearest patch centre in Euclidean xyz (what
     `scipy.cluster.vq.vq` computes in `assign_patch_centers`,
     `src/yaw/catalog/catalog.py:229-249`), evaluated in row blocks"""
-    ids = np.empty(len(xyz), dtype=np.int32)
-    step = max(1, 4_000_000 // max(len(centers_xyz), 1))
-    for lo in range(0, len(xyz), step):
-        blk = xyz[lo : lo + step]
-        d2 = ((blk[:, None, :] - centers_xyz[None, :, :]) ** 2).sum(axis=2)
-        ids[lo : lo + step] = np.argmin(d2, axis=1)
-    return ids
+    from scipy.cluster import vq
+
+    ids, _ = vq.vq(xyz, centers_xyz)
+    return ids.astype(np.int32)
 
 
 class Catalog(Mapping):
@@ -173,16 +170,17 @@ class Catalog(Mapping):
             ra, dec = np.deg2rad(ra), np.deg2rad(dec)
         weights = None if weights is None else np.asarray(weights, dtype=np.float64)
         redshifts = None if redshifts is None else np.asarray(redshifts, dtype=np.float64)
-        if (patch_centers is None) == (patch_ids is None):
-            raise ValueError("exactly one of 'patch_centers' and 'patch_ids' must be provided")
+        if patch_centers is None and patch_ids is None:
+            raise ValueError("one of 'patch_centers' and 'patch_ids' must be provided")
         centers = None
         if patch_centers is not None:
             if isinstance(patch_centers, Mapping):  # another catalog
                 patch_centers = patch_centers.get_centers()
             centers = patch_centers if isinstance(patch_centers, AngularCoordinates) else AngularCoordinates(
                 getattr(patch_centers, "data", patch_centers))
-            xyz = AngularCoordinates(np.column_stack([ra, dec])).to_3d()
-            patch_ids = _nearest_center(xyz, centers.to_3d())
+            if patch_ids is None:  # with both given, the ids assign rows and the centres fix the meta data
+                xyz = AngularCoordinates(np.column_stack([ra, dec])).to_3d()
+                patch_ids = _nearest_center(xyz, centers.to_3d())
         patch_ids = np.asarray(patch_ids)
         order = np.argsort(patch_ids, kind="stable")
         sorted_ids = patch_ids[order]

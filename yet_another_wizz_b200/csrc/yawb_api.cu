@@ -49,6 +49,8 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     YAWB_CUDA(cudaEventCreate(&ctx->ev0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev1));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_t1));
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
     *out = ctx;
     return 0;
@@ -61,6 +63,8 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaFree(ctx->d_counters);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_t0);
+    cudaEventDestroy(ctx->ev_t1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -71,6 +75,22 @@ int yawb_device_sms(const yawb_ctx *ctx) { return ctx ? ctx->sms : 0; }
 int yawb_sync(yawb_ctx *ctx) {
     YAWB_REQUIRE(ctx != nullptr, "yawb_sync: ctx is NULL");
     YAWB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int yawb_timer_start(yawb_ctx *ctx) {
+    YAWB_REQUIRE(ctx != nullptr, "yawb_timer_start: ctx is NULL");
+    YAWB_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return 0;
+}
+
+int yawb_timer_stop(yawb_ctx *ctx, double *ms) {
+    YAWB_REQUIRE(ctx && ms, "yawb_timer_stop: NULL argument");
+    YAWB_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    YAWB_CUDA(cudaEventSynchronize(ctx->ev_t1));
+    float t = 0.f;
+    YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev_t0, ctx->ev_t1));
+    *ms = (double)t;
     return 0;
 }
 

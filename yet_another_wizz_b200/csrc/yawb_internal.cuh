@@ -77,6 +77,7 @@ struct yawb_ctx {
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user stopwatch
     unsigned long long *d_counters = nullptr;  // [8] work counter + statistics
 };
 

@@ -72,7 +72,7 @@ class Engine:
         _lib.check(self.lib.yawb_create(int(device), byref(h)))
         self._h = h
         self.device = int(device)
-        self._cats: list[DeviceCatalog] = []
+        self._pinned: list[c_void_p] = []
 
     @property
     def num_sms(self) -> int:
@@ -163,11 +163,33 @@ class Engine:
         )
         return stats.as_dict()
 
+    def timer_start(self) -> None:
+        _lib.check(self.lib.yawb_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """milliseconds of device time since `timer_start` (CUDA events on the engine's stream)"""
+        ms = c_double()
+        _lib.check(self.lib.yawb_timer_stop(self._h, byref(ms)))
+        return ms.value
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed with the engine)"""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ptr = c_void_p()
+        _lib.check(self.lib.yawb_host_alloc(byref(ptr), nbytes))
+        self._pinned.append(ptr)
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def sync(self) -> None:
         _lib.check(self.lib.yawb_sync(self._h))
 
     def close(self) -> None:
         if self._h is not None:
+            for ptr in self._pinned:
+                self.lib.yawb_host_free(ptr)
+            self._pinned.clear()
             self.lib.yawb_destroy(self._h)
             self._h = None
 
