@@ -342,6 +342,9 @@ def run_gpu_arm(args):
             ms = eng.timer_stop()
             results = reduce_results(results)
             barrier()
+            if rank == 0:
+                log(f"[bench] step {step}: {ms:.2f} ms (index {t_idx:.2f}, kernels "
+                    f"{sum(s['kernel_ms'] for s in stats.values()):.2f})")
             if step >= args.warmup:
                 step_ms.append(max_over_ranks(ms))
                 kernel_ms.append(sum(s["kernel_ms"] for s in stats.values()))
@@ -363,6 +366,8 @@ def run_gpu_arm(args):
         dt = time.perf_counter() - t0
         for d in dev.values():
             d.free()
+        if rank == 0:
+            log(f"[bench] e2e step {step}: {dt * 1e3:.1f} ms")
         if step >= 1:
             e2e_s.append(max_over_ranks(dt))
 

@@ -52,6 +52,12 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t1));
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    {   // keep freed blocks in the stream-ordered pool: index rebuilds then reuse them without driver calls
+        cudaMemPool_t pool;
+        YAWB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        YAWB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     *out = ctx;
     return 0;
 }
@@ -61,6 +67,10 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_counters);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_t0);
@@ -240,6 +250,9 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
         bp.pad = 0;
         for (int e = 0; e < n_edges; ++e) r2f[(size_t)b * n_edges + e] = (float)r2_edges[(size_t)b * n_edges + e];
     }
+    double rmax_all = 0.0;
+    for (int b = 0; b < B; ++b)
+        if (!binpar[b].empty) rmax_all = std::max(rmax_all, binpar[b].rmax);
     std::vector<long long> item_base(n_pairs + 1, 0);
     for (int k = 0; k < n_pairs; ++k) {
         const int q = pair_j[k];
@@ -261,8 +274,9 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     BinPar *d_bp = nullptr;
     unsigned long long *d_cnt = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_pi); cudaFree(d_pj); cudaFree(d_base); cudaFree(d_r2); cudaFree(d_r2f); cudaFree(d_bp);
-        cudaFree(d_cnt); cudaFree(d_w);
+        for (void *p : {(void *)d_pi, (void *)d_pj, (void *)d_base, (void *)d_r2, (void *)d_r2f, (void *)d_bp,
+                        (void *)d_cnt, (void *)d_w})
+            if (p) cudaFreeAsync(p, st);
     };
 #define TRY(call)                                                                        \
     do {                                                                                 \
@@ -274,14 +288,14 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
         }                                                                                \
     } while (0)
     const size_t np1 = std::max(n_pairs, 1);
-    TRY(cudaMalloc(&d_pi, np1 * sizeof(int)));
-    TRY(cudaMalloc(&d_pj, np1 * sizeof(int)));
-    TRY(cudaMalloc(&d_base, (np1 + 1) * sizeof(long long)));
-    TRY(cudaMalloc(&d_r2, (size_t)B * n_edges * sizeof(double)));
-    TRY(cudaMalloc(&d_r2f, (size_t)B * n_edges * sizeof(float)));
-    TRY(cudaMalloc(&d_bp, B * sizeof(BinPar)));
-    TRY(cudaMalloc(&d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long)));
-    if (weighted) TRY(cudaMalloc(&d_w, std::max<size_t>(n_out, 1) * sizeof(double)));
+    TRY(cudaMallocAsync(&d_pi, np1 * sizeof(int), st));
+    TRY(cudaMallocAsync(&d_pj, np1 * sizeof(int), st));
+    TRY(cudaMallocAsync(&d_base, (np1 + 1) * sizeof(long long), st));
+    TRY(cudaMallocAsync(&d_r2, (size_t)B * n_edges * sizeof(double), st));
+    TRY(cudaMallocAsync(&d_r2f, (size_t)B * n_edges * sizeof(float), st));
+    TRY(cudaMallocAsync(&d_bp, B * sizeof(BinPar), st));
+    TRY(cudaMallocAsync(&d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
+    if (weighted) TRY(cudaMallocAsync(&d_w, std::max<size_t>(n_out, 1) * sizeof(double), st));
     if (n_pairs) {
         TRY(cudaMemcpyAsync(d_pi, pair_i, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
         TRY(cudaMemcpyAsync(d_pj, pair_j, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -299,7 +313,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     a.d_pair_i = d_pi; a.d_pair_j = d_pj; a.d_pair_item_base = d_base;
     a.n_items = item_base[n_pairs];
     a.n_pairs = n_pairs; a.n_bins = B; a.n_edges = n_edges;
-    a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp;
+    a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp; a.rmax_all = rmax_all;
     a.d_out_cnt = d_cnt; a.d_out_w = d_w; a.weighted = weighted;
 
     int launches = 0;
@@ -320,12 +334,11 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
             launches += 1;
         } else {
             double *d_tmp = nullptr;
-            TRY(cudaMalloc(&d_tmp, n_out * sizeof(double)));
+            TRY(cudaMallocAsync(&d_tmp, n_out * sizeof(double), st));
             k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, d_tmp, (long long)n_out);
             launches += 1;
             cudaError_t e = cudaMemcpyAsync(out_f64, d_tmp, n_out * sizeof(double), kind, st);
-            cudaStreamSynchronize(st);
-            cudaFree(d_tmp);
+            cudaFreeAsync(d_tmp, st);
             TRY(e);
         }
     }

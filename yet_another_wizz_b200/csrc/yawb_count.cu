@@ -33,6 +33,7 @@ constexpr float FAR = 1.0e15f;          // coordinates of padding points (never 
 struct FastParams {
     // first catalog (sky-cell index)
     const double *sx, *sy, *sz, *sw;
+    const double *su, *sv, *st;  // the same rows in the frame of their own patch
     const int *cell_start;
     const SGrid *sgrid;
     const PatchFrame *sframe;
@@ -48,6 +49,7 @@ struct FastParams {
     const double *r2;
     const float *r2f;
     const BinPar *binpar;
+    double rmax_all;  // largest search radius over the z-bins
     unsigned long long *out_cnt;
     double *out_w;
     unsigned long long *counters;  // [0] next item, [1] tests, [2] rechecks, [3] live items
@@ -82,37 +84,104 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// per-warp shared memory
+// ---- per-warp shared memory -------------------------------------------------------------------
+constexpr int CCAP = 128;  // (z-bin, cell-row) combinations resolved per batch
+
 template <bool WEIGHTED>
 struct WarpSmem {
-    float4 *list;                // [LCAP] staged candidates
-    int *lidx;                   // [LCAP] their row in the sorted first catalog
-    double *lw;                  // [LCAP] their weights (WEIGHTED)
-    unsigned long long *acc;     // [n_bins * nsub] pair counts of the current patch pair
-    double *accw;                // same, weighted sums (WEIGHTED)
-    unsigned *hist;              // [nsub] scratch histogram of the current bin (MULTI)
-    double *histw;               // [nsub] (MULTI && WEIGHTED)
+    float4 *list;             // [LCAP] staged candidates (-2x, -2y, -2z, |s|^2 - mid)
+    double *lw;               // [LCAP] their weights (WEIGHTED)
+    unsigned long long *acc;  // [n_bins * nsub] pair counts of the current patch pair
+    double *accw;             // same, weighted sums (WEIGHTED)
+    double *histw;            // [nsub] scratch histogram of one z-bin (MULTI && WEIGHTED)
+    float4 *binrec;           // [n_bins] half extents of the query box (x, y, z) and mid
+    float2 *binthr;           // [n_bins] (h - eps, h + eps)
+    int *lidx;                // [LCAP] row of the candidate in the sorted first catalog
+    int *bin_iv0;             // [n_bins] first cell row of the query box
+    int *bin_iu;              // [n_bins] iu0 | iu1 << 16
+    int *cstart;              // [n_bins + 1] prefix of cell rows per z-bin
+    int *rs0;                 // [CCAP] first candidate row of a (bin, cell-row) run
+    int *rpre;                // [CCAP] inclusive prefix of run lengths
+    int *cbin;                // [CCAP] z-bin of the run
+    unsigned *hist;           // [nsub] (MULTI)
+    unsigned short *lbin;     // [LCAP] z-bin of the candidate
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(bool weighted, bool multi, int n_bins, int nsub) {
-    size_t b = YAWB_LCAP * (sizeof(float4) + sizeof(int));
+    size_t b = YAWB_LCAP * sizeof(float4);
     if (weighted) b += YAWB_LCAP * sizeof(double);
     b += (size_t)n_bins * nsub * sizeof(unsigned long long);
     if (weighted) b += (size_t)n_bins * nsub * sizeof(double);
-    if (multi) b += (size_t)nsub * sizeof(unsigned) + (weighted ? (size_t)nsub * sizeof(double) : 0);
+    if (multi && weighted) b += (size_t)nsub * sizeof(double);
+    b += (size_t)n_bins * (sizeof(float4) + sizeof(float2));
+    b += YAWB_LCAP * sizeof(int);
+    b += (size_t)(3 * n_bins + 1) * sizeof(int);
+    b += 3 * CCAP * sizeof(int);
+    if (multi) b += (size_t)nsub * sizeof(unsigned);
+    b += YAWB_LCAP * sizeof(unsigned short);
     return (b + 15) & ~(size_t)15;
 }
 
-// ---- phase 2, single sub-bin (n_edges == 2): the hot loop ----------------------------------
 template <bool WEIGHTED>
-__device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int L,
+__device__ __forceinline__ void carve_smem(WarpSmem<WEIGHTED> &S, unsigned char *p, bool multi, int n_bins, int nsub) {
+    const size_t nacc = (size_t)n_bins * nsub;
+    // 16-byte objects first, then 8-, 4- and 2-byte ones, so every array is naturally aligned
+    S.list = (float4 *)p; p += YAWB_LCAP * sizeof(float4);
+    S.binrec = (float4 *)p; p += (size_t)n_bins * sizeof(float4);
+    S.lw = nullptr; S.accw = nullptr; S.histw = nullptr; S.hist = nullptr;
+    if (WEIGHTED) { S.lw = (double *)p; p += YAWB_LCAP * sizeof(double); }
+    S.acc = (unsigned long long *)p; p += nacc * sizeof(unsigned long long);
+    if (WEIGHTED) { S.accw = (double *)p; p += nacc * sizeof(double); }
+    if (multi && WEIGHTED) { S.histw = (double *)p; p += (size_t)nsub * sizeof(double); }
+    S.binthr = (float2 *)p; p += (size_t)n_bins * sizeof(float2);
+    S.lidx = (int *)p; p += YAWB_LCAP * sizeof(int);
+    S.bin_iv0 = (int *)p; p += (size_t)n_bins * sizeof(int);
+    S.bin_iu = (int *)p; p += (size_t)n_bins * sizeof(int);
+    S.cstart = (int *)p; p += (size_t)(n_bins + 1) * sizeof(int);
+    S.rs0 = (int *)p; p += CCAP * sizeof(int);
+    S.rpre = (int *)p; p += CCAP * sizeof(int);
+    S.cbin = (int *)p; p += CCAP * sizeof(int);
+    if (multi) { S.hist = (unsigned *)p; p += (size_t)nsub * sizeof(unsigned); }
+    S.lbin = (unsigned short *)p;
+}
+
+// ---- exact re-evaluation of one lane's share of a chunk, done by the whole warp ----------------
+// Lane `src` saw a test inside the FP32 uncertainty band.  Its (YAWB_RPL x chunk) tests are
+// re-evaluated with the reference's FP64 expression, two or more per lane, and summed.
+template <bool WEIGHTED>
+__device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSmem<WEIGHTED> &S, int e0, int e1,
+                                              const Tile &tl, int lane, int src, double lo, double hi,
+                                              unsigned &cnt_out, double &w_out, unsigned &n_recheck) {
+    unsigned cnt = 0;
+    double wsum = 0.0;
+    for (int t = lane; t < CHUNK * YAWB_RPL; t += 32) {
+        const int e = e0 + (t & (CHUNK - 1));
+        const int k = src + 32 * (t / CHUNK);
+        if (e < e1 && k < tl.count) {
+            const int i = S.lidx[e], j = tl.start + k;
+            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+            if (d2 > lo && d2 <= hi) {
+                cnt += 1;
+                if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
+            }
+            n_recheck += 1;
+        }
+    }
+    cnt_out = __reduce_add_sync(FULL, cnt);
+    if (WEIGHTED) w_out = warp_sum(wsum);
+}
+
+// ---- phase 2, single sub-bin (n_edges == 2): the hot loop ----------------------------------
+// entries [ea, eb) of the list belong to one z-bin with thresholds (h_in, h_out)
+template <bool WEIGHTED>
+__device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
                                               const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
                                               const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
-                                              const double (&wr)[YAWB_RPL], float h_in, float h_out,
-                                              const Tile &tl, int lane, const BinPar &bp,
-                                              unsigned &cnt_total, double &w_total, unsigned &n_recheck) {
-    for (int e0 = 0; e0 < L; e0 += CHUNK) {
-        const int e1 = min(e0 + CHUNK, L);
+                                              float h_in, float h_out, const Tile &tl, int lane, double lo,
+                                              double hi, unsigned &cnt_total, double &w_total,
+                                              unsigned &n_recheck) {
+    for (int e0 = ea; e0 < eb; e0 += CHUNK) {
+        const int e1 = min(e0 + CHUNK, eb);
         float c_in = 0.f, c_maybe = 0.f;
         double ws[YAWB_RPL];
         if (WEIGHTED) {
@@ -143,30 +212,22 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
         double wsum = 0.0;
         if (WEIGHTED) {
 #pragma unroll
-            for (int r = 0; r < YAWB_RPL; ++r) wsum += wr[r] * ws[r];
-        }
-        if (c_in != c_maybe) {
-            // some test of this lane fell inside the FP32 uncertainty band of an edge:
-            // redo the lane's share of the chunk exactly (reference arithmetic)
-            c = 0;
-            wsum = 0.0;
             for (int r = 0; r < YAWB_RPL; ++r) {
                 const int k = lane + 32 * r;
-                if (k >= tl.count) break;
-                const int j = tl.start + k;
-                const double bx = P.rx[j], by = P.ry[j], bz = P.rz[j];
-                double wj = 1.0;
-                if (WEIGHTED) wj = wr[r];
-                for (int e = e0; e < e1; ++e) {
-                    const int i = S.lidx[e];
-                    const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], bx, by, bz);
-                    if (d2 > bp.lo && d2 <= bp.hi) {
-                        c += 1;
-                        if (WEIGHTED) wsum += S.lw[e] * wj;
-                    }
-                }
+                if (ws[r] != 0.0) wsum += ws[r] * (P.rw ? P.rw[tl.start + min(k, tl.count - 1)] : 1.0);
             }
-            n_recheck += (unsigned)((e1 - e0) * YAWB_RPL);
+        }
+        unsigned flagged = __ballot_sync(FULL, c_in != c_maybe);
+        while (flagged) {  // warp-uniform: some lane met the uncertainty band of an edge
+            const int src = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            unsigned cx = 0;
+            double wx = 0.0;
+            recheck_chunk<WEIGHTED>(P, S, e0, e1, tl, lane, src, lo, hi, cx, wx, n_recheck);
+            if (lane == src) {
+                c = cx;
+                wsum = wx;
+            }
         }
         cnt_total += c;
         if (WEIGHTED) w_total += wsum;
@@ -175,16 +236,15 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
 
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
 template <bool WEIGHTED>
-__device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem<WEIGHTED> &S, int L,
+__device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
                                              const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
                                              const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
-                                             const double (&wr)[YAWB_RPL], float h_out, float eps,
-                                             const Tile &tl, int lane, const BinPar &bp, int b,
+                                             float h_out, float eps, float mid, const Tile &tl, int lane, int b,
                                              unsigned &n_recheck) {
     const int ne = P.n_edges;
     const float *ef = P.r2f + (size_t)b * ne;
     const double *ed = P.r2 + (size_t)b * ne;
-    for (int e = 0; e < L; ++e) {
+    for (int e = ea; e < eb; ++e) {
         const float4 s = S.list[e];
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
@@ -193,20 +253,19 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
             u = fmaf(ry[r], s.y, u);
             u = fmaf(rz[r], s.z, u);
             if (fabsf(u) < h_out) {  // possibly inside [lo, hi]
-                const float d2f = u + bp.mid;
+                const float d2f = u + mid;
                 int lo = 0, hi = ne;  // edges strictly below d2f (float copy of the edges)
                 while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (ef[mid] < d2f) lo = mid + 1; else hi = mid;
+                    int m = (lo + hi) >> 1;
+                    if (ef[m] < d2f) lo = m + 1; else hi = m;
                 }
                 int k = lo;
                 // distance to the neighbouring edges decides whether FP32 was good enough
                 float gap = FLT_MAX;
                 if (k > 0) gap = fminf(gap, d2f - ef[k - 1]);
                 if (k < ne) gap = fminf(gap, ef[k] - d2f);
+                const int j = tl.start + min(lane + 32 * r, tl.count - 1);
                 if (!(gap > eps)) {
-                    const int kk = lane + 32 * r;
-                    const int j = tl.start + min(kk, tl.count - 1);
                     const int i = S.lidx[e];
                     const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
                     k = edges_below(ed, ne, d2);
@@ -214,7 +273,7 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
                 }
                 if (k >= 1 && k < ne) {
                     atomicAdd(&S.hist[k - 1], 1u);
-                    if (WEIGHTED) atomicAdd(&S.histw[k - 1], S.lw[e] * wr[r]);
+                    if (WEIGHTED) atomicAdd(&S.histw[k - 1], S.lw[e] * (P.rw ? P.rw[j] : 1.0));
                 }
             }
         }
@@ -223,7 +282,7 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
 
 // ---- the kernel -------------------------------------------------------------------------------
 template <bool WEIGHTED, bool MULTI>
-__global__ void __launch_bounds__(YAWB_WARPS * 32, 2) k_count_fast(const FastParams P) {
+__global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_fast(const FastParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -231,17 +290,8 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, 2) k_count_fast(const FastPar
     const int nacc = P.n_bins * nsub;
 
     WarpSmem<WEIGHTED> S;
-    {
-        unsigned char *p = smem_raw + (size_t)warp * warp_smem_bytes(WEIGHTED, MULTI, P.n_bins, nsub);
-        S.list = (float4 *)p; p += YAWB_LCAP * sizeof(float4);
-        S.lw = nullptr; S.accw = nullptr; S.hist = nullptr; S.histw = nullptr;
-        if (WEIGHTED) { S.lw = (double *)p; p += YAWB_LCAP * sizeof(double); }
-        S.acc = (unsigned long long *)p; p += (size_t)nacc * sizeof(unsigned long long);
-        if (WEIGHTED) { S.accw = (double *)p; p += (size_t)nacc * sizeof(double); }
-        if (MULTI && WEIGHTED) { S.histw = (double *)p; p += (size_t)nsub * sizeof(double); }
-        S.lidx = (int *)p; p += YAWB_LCAP * sizeof(int);
-        if (MULTI) { S.hist = (unsigned *)p; }
-    }
+    carve_smem<WEIGHTED>(S, smem_raw + (size_t)warp * warp_smem_bytes(WEIGHTED, MULTI, P.n_bins, nsub), MULTI,
+                         P.n_bins, nsub);
     for (int k = lane; k < nacc; k += 32) {
         S.acc[k] = 0ull;
         if (WEIGHTED) S.accw[k] = 0.0;
@@ -298,35 +348,32 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, 2) k_count_fast(const FastPar
         // bounding-sphere rejection of the whole item (chord distances obey the triangle inequality)
         const int b_lo = tl.bin >= 0 ? tl.bin : 0;
         const int b_hi = tl.bin >= 0 ? tl.bin + 1 : P.n_bins;
-        double rmax_all = 0.0;
-        for (int b = b_lo; b < b_hi; ++b)
-            if (!P.binpar[b].empty) rmax_all = fmax(rmax_all, P.binpar[b].rmax);
         {
             const double dx = (double)tl.cx - F.c[0], dy = (double)tl.cy - F.c[1], dz = (double)tl.cz - F.c[2];
+            const double rmax_all = tl.bin >= 0 ? (P.binpar[tl.bin].empty ? 0.0 : P.binpar[tl.bin].rmax) : P.rmax_all;
             const double reach = F.radius + (double)tl.rad + rmax_all + 1e-9;
             if (rmax_all == 0.0 || dx * dx + dy * dy + dz * dz > reach * reach) continue;
         }
         n_live += 1;
 
-        // second-catalog points of this lane, rotated into the frame of patch p1
-        double lu[YAWB_RPL], lv[YAWB_RPL], lt[YAWB_RPL], wr[YAWB_RPL];
+        // second-catalog points of this lane in the frame of patch p1: pass 1 finds the tile box,
+        // pass 2 re-derives the coordinates relative to the box centre and rounds them ONCE to float
+        const double c0 = F.c[0], c1 = F.c[1], c2 = F.c[2];
+        const double a0 = F.e1[0], a1 = F.e1[1], a2 = F.e1[2];
+        const double g0 = F.e2[0], g1 = F.e2[1], g2 = F.e2[2];
         double umin = DBL_MAX, umax = -DBL_MAX, vmin = DBL_MAX, vmax = -DBL_MAX, tmin = DBL_MAX, tmax = -DBL_MAX;
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
             const int k = lane + 32 * r;
-            wr[r] = 0.0;
             if (k < tl.count) {
                 const int j = tl.start + k;
-                const double dx = P.rx[j] - F.c[0], dy = P.ry[j] - F.c[1], dz = P.rz[j] - F.c[2];
-                lu[r] = dx * F.e1[0] + dy * F.e1[1] + dz * F.e1[2];
-                lv[r] = dx * F.e2[0] + dy * F.e2[1] + dz * F.e2[2];
-                lt[r] = dx * F.c[0] + dy * F.c[1] + dz * F.c[2];
-                umin = fmin(umin, lu[r]); umax = fmax(umax, lu[r]);
-                vmin = fmin(vmin, lv[r]); vmax = fmax(vmax, lv[r]);
-                tmin = fmin(tmin, lt[r]); tmax = fmax(tmax, lt[r]);
-                if (WEIGHTED) wr[r] = P.rw ? P.rw[j] : 1.0;
-            } else {
-                lu[r] = lv[r] = lt[r] = 0.0;
+                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
+                const double lu = dx * a0 + dy * a1 + dz * a2;
+                const double lv = dx * g0 + dy * g1 + dz * g2;
+                const double lt = dx * c0 + dy * c1 + dz * c2;
+                umin = fmin(umin, lu); umax = fmax(umax, lu);
+                vmin = fmin(vmin, lv); vmax = fmax(vmax, lv);
+                tmin = fmin(tmin, lt); tmax = fmax(tmax, lt);
             }
         }
         umin = warp_min(umin); umax = warp_max(umax);
@@ -337,10 +384,13 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, 2) k_count_fast(const FastPar
         float rx[YAWB_RPL], ry[YAWB_RPL], rz[YAWB_RPL], rn[YAWB_RPL];
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
-            if (lane + 32 * r < tl.count) {
-                rx[r] = (float)(lu[r] - ou);
-                ry[r] = (float)(lv[r] - ov);
-                rz[r] = (float)(lt[r] - ot);
+            const int k = lane + 32 * r;
+            if (k < tl.count) {
+                const int j = tl.start + k;
+                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
+                rx[r] = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
+                ry[r] = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
+                rz[r] = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
                 rn[r] = rx[r] * rx[r] + ry[r] * ry[r] + rz[r] * rz[r];
             } else {
                 rx[r] = FAR; ry[r] = FAR; rz[r] = FAR;
@@ -348,98 +398,174 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, 2) k_count_fast(const FastPar
             }
         }
         const SGrid G = P.sgrid[p1];
+        const double eu = 0.5 * (umax - umin), ev = 0.5 * (vmax - vmin), et = 0.5 * (tmax - tmin);
 
-        for (int b = b_lo; b < b_hi; ++b) {
-            const BinPar bp = P.binpar[b];
-            if (bp.empty) continue;
-            // query box = tile box grown by the search radius (sound: |du|,|dv|,|dt| <= chord)
-            const double qu0 = umin - bp.rmax, qu1 = umax + bp.rmax;
-            const double qv0 = vmin - bp.rmax, qv1 = vmax + bp.rmax;
-            const double qt0 = tmin - bp.rmax, qt1 = tmax + bp.rmax;
-            // cell range of the box; floor((x - u0) * inv_c) is the same monotone expression the keys
-            // were made with, so a point inside the box can never sit in a cell outside the range
-            const double fu0 = floor((qu0 - G.u0) * G.inv_c), fu1 = floor((qu1 - G.u0) * G.inv_c);
-            const double fv0 = floor((qv0 - G.v0) * G.inv_c), fv1 = floor((qv1 - G.v0) * G.inv_c);
-            if (fu1 < 0.0 || fv1 < 0.0 || fu0 > (double)(G.gu - 1) || fv0 > (double)(G.gv - 1)) continue;
-            const int iu0 = (int)fmax(fu0, 0.0), iv0 = (int)fmax(fv0, 0.0);
-            const int iu1 = (int)fmin(fu1, (double)(G.gu - 1)), iv1 = (int)fmin(fv1, (double)(G.gv - 1));
-
-            // FP32 error bound of u for this (tile, bin): all staged vectors lie in the query box
-            const float hu = (float)(0.5 * (qu1 - qu0)), hv = (float)(0.5 * (qv1 - qv0)), ht = (float)(0.5 * (qt1 - qt0));
-            const float m2 = hu * hu + hv * hv + ht * ht;
-            const float eps = 64.0f * EPS32 * (m2 + bp.mid) * 1.0001f;
-            const float h_in = bp.h - eps, h_out = bp.h + eps;
-
-            unsigned cnt_total = 0;
-            double w_total = 0.0;
-            if (MULTI) {
-                for (int k = lane; k < nsub; k += 32) {
-                    S.hist[k] = 0u;
-                    if (WEIGHTED) S.histw[k] = 0.0;
-                }
-            }
-            int L = 0;
-            auto run_phase2 = [&]() {
-                __syncwarp();
-                if (MULTI)
-                    phase2_multi<WEIGHTED>(P, S, L, rx, ry, rz, rn, wr, h_out, eps + 4.0f * EPS32 * (float)bp.hi, tl,
-                                           lane, bp, b, n_recheck);
-                else
-                    phase2_single<WEIGHTED>(P, S, L, rx, ry, rz, rn, wr, h_in, h_out, tl, lane, bp, cnt_total,
-                                            w_total, n_recheck);
-                n_tests += (unsigned long long)L * (unsigned long long)tl.count;
-                L = 0;
-                __syncwarp();
-            };
-
-            const long long bin_base = G.cell_base + (long long)b * G.gu * G.gv;
-            for (int iv = iv0; iv <= iv1; ++iv) {
-                const long long row = bin_base + (long long)iv * G.gu;
-                const int s0 = P.cell_start[row + iu0], s1 = P.cell_start[row + iu1 + 1];
-                for (int base = s0; base < s1; base += 32) {
-                    const int i = base + lane;
-                    bool ok = i < s1;
-                    double du = 0, dv = 0, dt = 0;
-                    if (ok) {
-                        const double dx = P.sx[i] - F.c[0], dy = P.sy[i] - F.c[1], dz = P.sz[i] - F.c[2];
-                        du = dx * F.e1[0] + dy * F.e1[1] + dz * F.e1[2];
-                        dv = dx * F.e2[0] + dy * F.e2[1] + dz * F.e2[2];
-                        dt = dx * F.c[0] + dy * F.c[1] + dz * F.c[2];
-                        ok = du >= qu0 && du <= qu1 && dv >= qv0 && dv <= qv1 && dt >= qt0 && dt <= qt1;
+        // ---- step 1: per z-bin query box, thresholds and cell rows (one lane per z-bin) ----
+        int carry = 0;
+        for (int b0 = b_lo; b0 < b_hi; b0 += 32) {
+            const int b = b0 + lane;
+            int nrows = 0;
+            if (b < b_hi) {
+                const BinPar bp = P.binpar[b];
+                if (!bp.empty) {
+                    // query box = tile box grown by the search radius (sound: |du|,|dv|,|dt| <= chord)
+                    const double qu0 = umin - bp.rmax, qu1 = umax + bp.rmax;
+                    const double qv0 = vmin - bp.rmax, qv1 = vmax + bp.rmax;
+                    // cell range of the box; floor((x - u0) * inv_c) is the same monotone expression the
+                    // keys were made with, so a point inside the box cannot sit in a cell outside the range
+                    const double fu0 = floor((qu0 - G.u0) * G.inv_c), fu1 = floor((qu1 - G.u0) * G.inv_c);
+                    const double fv0 = floor((qv0 - G.v0) * G.inv_c), fv1 = floor((qv1 - G.v0) * G.inv_c);
+                    if (!(fu1 < 0.0 || fv1 < 0.0 || fu0 > (double)(G.gu - 1) || fv0 > (double)(G.gv - 1))) {
+                        const int iu0 = (int)fmax(fu0, 0.0), iv0 = (int)fmax(fv0, 0.0);
+                        const int iu1 = (int)fmin(fu1, (double)(G.gu - 1)), iv1 = (int)fmin(fv1, (double)(G.gv - 1));
+                        nrows = iv1 - iv0 + 1;
+                        S.bin_iv0[b] = iv0;
+                        S.bin_iu[b] = iu0 | (iu1 << 16);
                     }
-                    const unsigned m = __ballot_sync(FULL, ok);
-                    if (ok) {
-                        const int pos = L + __popc(m & ((1u << lane) - 1u));
-                        const float fx = (float)(du - ou), fy = (float)(dv - ov), fz = (float)(dt - ot);
-                        const double sn = (double)fx * fx + (double)fy * fy + (double)fz * fz;
-                        S.list[pos] = make_float4(-2.0f * fx, -2.0f * fy, -2.0f * fz, (float)(sn - (double)bp.mid));
-                        S.lidx[pos] = i;
-                        if (WEIGHTED) S.lw[pos] = P.sw ? P.sw[i] : 1.0;
-                    }
-                    L += __popc(m);
-                    if (L > YAWB_LCAP - 32) run_phase2();
+                    // half extents rounded up; they bound every staged vector, hence the FP32 error of u
+                    const float hx = (float)(eu + bp.rmax) * 1.000001f, hy = (float)(ev + bp.rmax) * 1.000001f,
+                                hz = (float)(et + bp.rmax) * 1.000001f;
+                    const float m2 = hx * hx + hy * hy + hz * hz;
+                    const float eps = 64.0f * EPS32 * (m2 + bp.mid) * 1.0001f;
+                    S.binrec[b] = make_float4(hx, hy, hz, bp.mid);
+                    S.binthr[b] = MULTI ? make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi)
+                                        : make_float2(bp.h - eps, bp.h + eps);
                 }
             }
-            if (L > 0) run_phase2();
-
-            // fold this bin into the warp's accumulators of the current patch pair
-            if (MULTI) {
-                __syncwarp();
-                for (int k = lane; k < nsub; k += 32) {
-                    S.acc[(size_t)b * nsub + k] += S.hist[k];
-                    if (WEIGHTED) S.accw[(size_t)b * nsub + k] += S.histw[k];
-                }
-                __syncwarp();
-            } else {
-                const unsigned tot = __reduce_add_sync(FULL, cnt_total);
-                double wtot = 0.0;
-                if (WEIGHTED) wtot = warp_sum(w_total);
-                if (lane == 0) {
-                    S.acc[b] += tot;
-                    if (WEIGHTED) S.accw[b] += wtot;
-                }
+            int incl = nrows;  // inclusive scan of the cell rows over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
             }
+            if (b < b_hi) S.cstart[b + 1] = carry + incl;
+            carry += __shfl_sync(FULL, incl, 31);
         }
+        if (lane == 0) S.cstart[b_lo] = 0;
+        const int n_combo = carry;
+        __syncwarp();
+
+        int L = 0;
+        // ---- consume the staged list: one run of phase 2 per z-bin segment ----
+        auto consume = [&]() {
+            __syncwarp();
+            int ea = 0;
+            while (ea < L) {
+                const int b = S.lbin[ea];
+                int eb = L;  // first entry after ea that belongs to another z-bin
+                for (int base = ea + 1; base < L; base += 32) {
+                    const int e = base + lane;
+                    const unsigned m = __ballot_sync(FULL, e < L && S.lbin[e] != b);
+                    if (m) {
+                        eb = base + __ffs(m) - 1;
+                        break;
+                    }
+                }
+                const float2 thr = S.binthr[b];
+                if (MULTI) {
+                    for (int k = lane; k < nsub; k += 32) {
+                        S.hist[k] = 0u;
+                        if (WEIGHTED) S.histw[k] = 0.0;
+                    }
+                    __syncwarp();
+                    phase2_multi<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, S.binrec[b].w, tl, lane, b,
+                                           n_recheck);
+                    __syncwarp();
+                    for (int k = lane; k < nsub; k += 32) {
+                        S.acc[(size_t)b * nsub + k] += S.hist[k];
+                        if (WEIGHTED) S.accw[(size_t)b * nsub + k] += S.histw[k];
+                    }
+                    __syncwarp();
+                } else {
+                    unsigned cnt_total = 0;
+                    double w_total = 0.0;
+                    phase2_single<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane, P.binpar[b].lo,
+                                            P.binpar[b].hi, cnt_total, w_total, n_recheck);
+                    const unsigned tot = __reduce_add_sync(FULL, cnt_total);
+                    double wtot = 0.0;
+                    if (WEIGHTED) wtot = warp_sum(w_total);
+                    if (lane == 0) {
+                        S.acc[b] += tot;
+                        if (WEIGHTED) S.accw[b] += wtot;
+                    }
+                }
+                ea = eb;
+            }
+            n_tests += (unsigned long long)L * (unsigned long long)tl.count;
+            L = 0;
+            __syncwarp();
+        };
+
+        for (int cb = 0; cb < n_combo; cb += CCAP) {
+            const int nb = min(CCAP, n_combo - cb);
+            // ---- step 2: one lane per (z-bin, cell row): the run of candidate rows it covers ----
+            int running = 0;
+            for (int k0 = 0; k0 < nb; k0 += 32) {
+                const int k = k0 + lane;
+                int cnt = 0, s0 = 0, b = 0;
+                if (k < nb) {
+                    const int c = cb + k;
+                    int lo = b_lo, hi = b_hi;  // last z-bin with cstart[b] <= c
+                    while (hi - lo > 1) {
+                        const int m = (lo + hi) >> 1;
+                        if (S.cstart[m] <= c) lo = m; else hi = m;
+                    }
+                    b = lo;
+                    const int iv = S.bin_iv0[b] + (c - S.cstart[b]);
+                    const int iu = S.bin_iu[b];
+                    const long long row = G.cell_base + ((long long)b * G.gv + iv) * G.gu;
+                    s0 = P.cell_start[row + (iu & 0xffff)];
+                    cnt = P.cell_start[row + (iu >> 16) + 1] - s0;
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (k < nb) {
+                    S.rs0[k] = s0;
+                    S.rpre[k] = running + incl;
+                    S.cbin[k] = b;
+                }
+                running += __shfl_sync(FULL, incl, 31);
+            }
+            const int n_cand = running;
+            __syncwarp();
+
+            // ---- step 3: flattened gather, cull against the z-bin's box, stage as float4 ----
+            int cur = 0;
+            for (int t0 = 0; t0 < n_cand; t0 += 32) {
+                const int t = t0 + lane;
+                bool ok = t < n_cand;
+                int i = 0, b = 0;
+                float fx = 0.f, fy = 0.f, fz = 0.f, mid = 0.f;
+                if (ok) {
+                    while (t >= S.rpre[cur]) ++cur;  // runs are consumed in order; empty runs are skipped
+                    i = S.rs0[cur] + (t - (cur ? S.rpre[cur - 1] : 0));
+                    b = S.cbin[cur];
+                    fx = (float)(P.su[i] - ou);
+                    fy = (float)(P.sv[i] - ov);
+                    fz = (float)(P.st[i] - ot);
+                    const float4 rec = S.binrec[b];
+                    mid = rec.w;
+                    ok = fabsf(fx) <= rec.x && fabsf(fy) <= rec.y && fabsf(fz) <= rec.z;
+                }
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (ok) {
+                    const int pos = L + __popc(m & ((1u << lane) - 1u));
+                    const float sn = fx * fx + fy * fy + fz * fz;
+                    S.list[pos] = make_float4(-2.0f * fx, -2.0f * fy, -2.0f * fz, sn - mid);
+                    S.lidx[pos] = i;
+                    S.lbin[pos] = (unsigned short)b;
+                    if (WEIGHTED) S.lw[pos] = P.sw ? P.sw[i] : 1.0;
+                }
+                L += __popc(m);
+                if (L > YAWB_LCAP - 32) consume();
+            }
+            __syncwarp();
+        }
+        if (L > 0) consume();
     }
     flush_pair();
     if (lane == 0) {
@@ -538,6 +664,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
 int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     FastParams P{};
     P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw;
+    P.su = a.c1->su; P.sv = a.c1->sv; P.st = a.c1->st;
+    P.rmax_all = a.rmax_all;
     P.cell_start = a.c1->cell_start; P.sgrid = a.c1->d_sgrid; P.sframe = a.c1->d_frames;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
     P.tiles = a.c2->d_tiles; P.ptile_off = a.c2->d_ptile_off;
@@ -553,7 +681,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
     // persistent grid: a multiple of the SM count, warps pull items from a global counter
     const long long warps_needed = a.n_items;
-    int ctas = ctx->sms * 2;
+    int ctas = ctx->sms * YAWB_MIN_CTAS;
     ctas = (int)std::min<long long>(ctas, (warps_needed + YAWB_WARPS - 1) / YAWB_WARPS);
     ctas = std::max(ctas, 1);
 

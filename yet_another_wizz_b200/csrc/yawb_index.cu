@@ -31,11 +31,14 @@ inline int blocks_for(int64_t n, int per_block = kThreads) {
     return (int)std::min<int64_t>((n + per_block - 1) / per_block, 1 << 30);
 }
 
+// Catalog buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the context's
+// stream; the pool keeps freed blocks, see yawb_create), so building and dropping indexes costs no
+// device synchronisation and no driver round trips after the first use.
 template <typename T>
 int dev_alloc(yawb_cat *cat, T **ptr, size_t count) {
     *ptr = nullptr;
     if (count == 0) count = 1;
-    YAWB_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
+    YAWB_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), cat->ctx->stream));
     cat->device_bytes += (int64_t)(count * sizeof(T));
     return 0;
 }
@@ -43,24 +46,34 @@ int dev_alloc(yawb_cat *cat, T **ptr, size_t count) {
 template <typename T>
 void dev_free(yawb_cat *cat, T *&ptr, size_t count) {
     if (ptr) {
-        cudaFree(ptr);
+        cudaFreeAsync(ptr, cat->ctx->stream);
         cat->device_bytes -= (int64_t)(std::max<size_t>(count, 1) * sizeof(T));
         ptr = nullptr;
     }
 }
+
+// scratch that lives for one call
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    template <typename T>
+    T *get(size_t count) {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), st) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    ~Scratch() {
+        for (void *p : ptrs) cudaFreeAsync(p, st);
+    }
+};
 
 // order-preserving map double -> uint64 so atomicMin/Max work on doubles
 __device__ __forceinline__ unsigned long long enc_double(double v) {
     unsigned long long b = (unsigned long long)__double_as_longlong(v);
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
-inline double dec_double(unsigned long long b) {
-    b = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
-    double v;
-    memcpy(&v, &b, sizeof(v));
-    return v;
-}
-
 // ---- upload kernels ---------------------------------------------------------------------
 
 // AoS (n x 3) -> SoA, plus the patch id of every row from the row offsets
@@ -80,41 +93,123 @@ __global__ void k_deinterleave(const double *__restrict__ xyz, const long long *
     patch[i] = lo;
 }
 
-// per patch: sum of unit vectors; per (bin, patch): row count and sum of weights
-__global__ void k_patch_sums(const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ z, const double *__restrict__ w,
-                             const int *__restrict__ bin, const int *__restrict__ patch, long long n,
-                             int n_patch, int n_bins, double *__restrict__ sums /*[n_patch][3]*/,
-                             unsigned long long *__restrict__ counts, double *__restrict__ sumw) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const unsigned full = 0xffffffffu;
-    bool live = i < n;
-    int p = live ? patch[i] : -1;
-    double px = live ? x[i] : 0.0, py = live ? y[i] : 0.0, pz = live ? z[i] : 0.0;
-    int p0 = __shfl_sync(full, p, 0);
-    if (__all_sync(full, p == p0)) {  // common case: whole warp inside one patch
-        for (int o = 16; o; o >>= 1) {
-            px += __shfl_xor_sync(full, px, o);
-            py += __shfl_xor_sync(full, py, o);
-            pz += __shfl_xor_sync(full, pz, o);
+// per patch: sum of unit vectors; per (bin, patch): row count and sum of weights.
+// A block owns kSumRows consecutive rows; rows of the block's first patch are accumulated in shared
+// memory (rows are grouped by patch, so that is nearly all of them) and flushed with one global atomic
+// per z-bin; stragglers of the next patch go to global memory directly.
+constexpr int kSumRows = 4096;
+constexpr int kSumMaxBins = 2048;
+
+__global__ void __launch_bounds__(kThreads) k_patch_sums(
+    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+    const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch, long long n,
+    int n_patch, int n_bins, double *__restrict__ sums /*[n_patch][3]*/, unsigned long long *__restrict__ counts,
+    double *__restrict__ sumw) {
+    extern __shared__ unsigned char sm_raw[];
+    double *s_xyz = (double *)sm_raw;                 // [3]
+    double *s_w = s_xyz + 4;                          // [n_bins] (if weighted and it fits)
+    const bool use_smem = n_bins <= kSumMaxBins;
+    unsigned *s_cnt = (unsigned *)(s_w + (w && use_smem ? n_bins : 0));  // [n_bins]
+    const long long row0 = (long long)blockIdx.x * kSumRows;
+    const int p_blk = patch[row0];
+    if (threadIdx.x < 3) s_xyz[threadIdx.x] = 0.0;
+    if (use_smem)
+        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+            s_cnt[b] = 0u;
+            if (w) s_w[b] = 0.0;
         }
-        if ((threadIdx.x & 31) == 0 && p0 >= 0) {
-            atomicAdd(&sums[3 * p0], px);
-            atomicAdd(&sums[3 * p0 + 1], py);
-            atomicAdd(&sums[3 * p0 + 2], pz);
+    __syncthreads();
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int k = threadIdx.x; k < kSumRows; k += blockDim.x) {
+        const long long i = row0 + k;
+        if (i >= n) break;
+        const int p = patch[i];
+        const int b = bin ? bin[i] : 0;
+        const bool in_bin = b >= 0 && b < n_bins;
+        if (p == p_blk) {
+            ax += x[i]; ay += y[i]; az += z[i];
+            if (in_bin) {
+                if (use_smem) {
+                    atomicAdd(&s_cnt[b], 1u);
+                    if (w) atomicAdd(&s_w[b], w[i]);
+                } else {
+                    atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
+                    if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
+                }
+            }
+        } else {
+            atomicAdd(&sums[3 * p], x[i]);
+            atomicAdd(&sums[3 * p + 1], y[i]);
+            atomicAdd(&sums[3 * p + 2], z[i]);
+            if (in_bin) {
+                atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
+                if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
+            }
         }
-    } else if (live) {
-        atomicAdd(&sums[3 * p], px);
-        atomicAdd(&sums[3 * p + 1], py);
-        atomicAdd(&sums[3 * p + 2], pz);
     }
-    if (live) {
-        int b = bin ? bin[i] : 0;
-        if (b >= 0 && b < n_bins) {
-            atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
-            if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
-        }
+    for (int o = 16; o; o >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, o);
+        ay += __shfl_xor_sync(0xffffffffu, ay, o);
+        az += __shfl_xor_sync(0xffffffffu, az, o);
     }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_xyz[0], ax);
+        atomicAdd(&s_xyz[1], ay);
+        atomicAdd(&s_xyz[2], az);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&sums[3 * p_blk + threadIdx.x], s_xyz[threadIdx.x]);
+    if (use_smem)
+        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+            if (s_cnt[b]) atomicAdd(&counts[(size_t)b * n_patch + p_blk], (unsigned long long)s_cnt[b]);
+            if (w && s_w[b] != 0.0) atomicAdd(&sumw[(size_t)b * n_patch + p_blk], s_w[b]);
+        }
+}
+
+// frames from the per-patch sums: centre = mean direction, e1/e2 any orthonormal tangent basis
+__global__ void k_make_frames(const double *__restrict__ sums, int n_patch, PatchFrame *__restrict__ frames) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patch) return;
+    PatchFrame f;
+    double cx = sums[3 * p], cy = sums[3 * p + 1], cz = sums[3 * p + 2];
+    double nrm = sqrt(cx * cx + cy * cy + cz * cz);
+    if (!(nrm > 1e-12)) { cx = 0; cy = 0; cz = 1; nrm = 1; }  // empty or antipodally balanced patch
+    f.c[0] = cx / nrm; f.c[1] = cy / nrm; f.c[2] = cz / nrm;
+    double ax = 0, ay = 0, az = 1;  // helper axis least aligned with c
+    if (fabs(f.c[2]) > 0.9) { ax = 1; az = 0; }
+    double e1x = ay * f.c[2] - az * f.c[1], e1y = az * f.c[0] - ax * f.c[2], e1z = ax * f.c[1] - ay * f.c[0];
+    double n1 = sqrt(e1x * e1x + e1y * e1y + e1z * e1z);
+    f.e1[0] = e1x / n1; f.e1[1] = e1y / n1; f.e1[2] = e1z / n1;
+    f.e2[0] = f.c[1] * f.e1[2] - f.c[2] * f.e1[1];
+    f.e2[1] = f.c[2] * f.e1[0] - f.c[0] * f.e1[2];
+    f.e2[2] = f.c[0] * f.e1[1] - f.c[1] * f.e1[0];
+    f.radius = 0.0;
+    f.umin = f.umax = f.vmin = f.vmax = 0.0;
+    frames[p] = f;
+}
+
+__device__ __forceinline__ double dec_double_dev(unsigned long long b) {
+    b = (b & 0x8000000000000000ull) ? (b & 0x7fffffffffffffffull) : ~b;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void k_init_box(unsigned long long *__restrict__ box, int n_patch) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patch) return;
+    box[5 * p] = box[5 * p + 2] = ~0ull;
+    box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
+}
+
+__global__ void k_finish_frames(const unsigned long long *__restrict__ box, int n_patch,
+                                PatchFrame *__restrict__ frames) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patch) return;
+    if (box[5 * p] == ~0ull) return;  // no rows: extents stay zero
+    frames[p].umin = dec_double_dev(box[5 * p]);
+    frames[p].umax = dec_double_dev(box[5 * p + 1]);
+    frames[p].vmin = dec_double_dev(box[5 * p + 2]);
+    frames[p].vmax = dec_double_dev(box[5 * p + 3]);
+    frames[p].radius = sqrt(dec_double_dev(box[5 * p + 4])) * (1.0 + 1e-12) + 1e-15;
 }
 
 // per patch: (u, v) bounding box and max squared chord distance from the centre
@@ -239,6 +334,28 @@ __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const d
     if (w) ow[i] = w[j];
 }
 
+// first-role gather: also the coordinates of every row in the frame of its own patch
+__global__ void k_gather_local(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
+                               const double *__restrict__ y, const double *__restrict__ z,
+                               const double *__restrict__ w, const int *__restrict__ patch,
+                               const PatchFrame *__restrict__ frames, double *__restrict__ ox,
+                               double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ow,
+                               double *__restrict__ ou, double *__restrict__ ov, double *__restrict__ ot) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned j = perm[i];
+    const double X = x[j], Y = y[j], Z = z[j];
+    ox[i] = X;
+    oy[i] = Y;
+    oz[i] = Z;
+    if (w) ow[i] = w[j];
+    const PatchFrame &f = frames[patch[j]];
+    const double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
+    ou[i] = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
+    ov[i] = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
+    ot[i] = dx * f.c[0] + dy * f.c[1] + dz * f.c[2];
+}
+
 // cell_start[g] = first sorted row whose key is >= g (one thread per cell, binary search)
 __global__ void k_cell_start(const unsigned long long *__restrict__ keys, long long n, long long n_cells,
                              int *__restrict__ cell_start) {
@@ -290,21 +407,15 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     }
 }
 
-int sort_pairs(yawb_ctx *ctx, unsigned long long *keys_in, unsigned long long *keys_out, unsigned *vals_in,
-               unsigned *vals_out, long long n, int end_bit) {
+int sort_pairs(yawb_ctx *ctx, Scratch &scr, unsigned long long *keys_in, unsigned long long *keys_out,
+               unsigned *vals_in, unsigned *vals_out, long long n, int end_bit) {
     size_t temp_bytes = 0;
     YAWB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, vals_in, vals_out,
                                               (int)n, 0, end_bit, ctx->stream));
-    void *temp = nullptr;
-    YAWB_CUDA(cudaMalloc(&temp, std::max<size_t>(temp_bytes, 16)));
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out,
-                                                    (int)n, 0, end_bit, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(temp);
-    if (e != cudaSuccess || e2 != cudaSuccess) {
-        yawb_set_error("radix sort failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
-        return 1;
-    }
+    void *temp = scr.get<unsigned char>(std::max<size_t>(temp_bytes, 16));
+    YAWB_REQUIRE(temp != nullptr, "out of device memory (radix sort scratch)");
+    YAWB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0,
+                                              end_bit, ctx->stream));
     return 0;
 }
 
@@ -322,48 +433,58 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
     cudaStream_t st = ctx->stream;
+    Scratch scr(st);
 
     if (dev_alloc(cat, &cat->x, n) || dev_alloc(cat, &cat->y, n) || dev_alloc(cat, &cat->z, n) ||
         dev_alloc(cat, &cat->patch, n))
         return 1;
     if (w && dev_alloc(cat, &cat->w, n)) return 1;
     if (zbin && dev_alloc(cat, &cat->bin, n)) return 1;
+    if (dev_alloc(cat, &cat->d_frames, P) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1)) return 1;
 
-    double *d_xyz = nullptr;
-    long long *d_poff = nullptr;
-    double *d_sums = nullptr, *d_sumw = nullptr;
-    unsigned long long *d_counts = nullptr, *d_box = nullptr;
-    YAWB_CUDA(cudaMalloc(&d_xyz, std::max<size_t>(n * 3 * sizeof(double), 8)));
-    YAWB_CUDA(cudaMalloc(&d_poff, (P + 1) * sizeof(long long)));
-    YAWB_CUDA(cudaMalloc(&d_sums, P * 3 * sizeof(double)));
-    YAWB_CUDA(cudaMalloc(&d_sumw, (size_t)B * P * sizeof(double)));
-    YAWB_CUDA(cudaMalloc(&d_counts, (size_t)B * P * sizeof(unsigned long long)));
-    YAWB_CUDA(cudaMalloc(&d_box, P * 5 * sizeof(unsigned long long)));
+    double *d_xyz = scr.get<double>((size_t)n * 3);
+    long long *d_poff = scr.get<long long>(P + 1);
+    double *d_sums = scr.get<double>((size_t)P * 3);
+    double *d_sumw = scr.get<double>((size_t)B * P);
+    unsigned long long *d_counts = scr.get<unsigned long long>((size_t)B * P);
+    unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
+    YAWB_REQUIRE(d_xyz && d_poff && d_sums && d_sumw && d_counts && d_box, "out of device memory (upload scratch)");
 
-    YAWB_CUDA(cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n > 0) YAWB_CUDA(cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     YAWB_CUDA(cudaMemcpyAsync(d_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    if (w) YAWB_CUDA(cudaMemcpyAsync(cat->w, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (zbin) YAWB_CUDA(cudaMemcpyAsync(cat->bin, zbin, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (w && n > 0) YAWB_CUDA(cudaMemcpyAsync(cat->w, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (zbin && n > 0) YAWB_CUDA(cudaMemcpyAsync(cat->bin, zbin, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     YAWB_CUDA(cudaMemsetAsync(d_sums, 0, P * 3 * sizeof(double), st));
     YAWB_CUDA(cudaMemsetAsync(d_sumw, 0, (size_t)B * P * sizeof(double), st));
     YAWB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)B * P * sizeof(unsigned long long), st));
 
+    const int pb = (P + 127) / 128;
     if (n > 0) {
         k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(d_xyz, d_poff, P, n, cat->x, cat->y, cat->z,
                                                            cat->patch);
-        k_patch_sums<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin, cat->patch,
-                                                         n, P, B, d_sums, d_counts, d_sumw);
+        const bool use_smem = B <= kSumMaxBins;
+        const size_t smem = 4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (w ? sizeof(double) : 0)) : 0);
+        k_patch_sums<<<blocks_for(n, kSumRows), kThreads, smem, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin,
+                                                                       cat->patch, n, P, B, d_sums, d_counts, d_sumw);
     }
-    std::vector<double> sums(P * 3);
+    k_make_frames<<<pb, 128, 0, st>>>(d_sums, P, cat->d_frames);
+    k_init_box<<<pb, 128, 0, st>>>(d_box, P);
+    if (n > 0)
+        k_patch_bbox<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n, cat->d_frames,
+                                                         d_box);
+    k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
+
+    // the one host round trip of an upload: frames, row counts and sums of weights
     std::vector<unsigned long long> counts((size_t)B * P);
     cat->h_sumw.assign((size_t)B * P, 0.0);
-    YAWB_CUDA(cudaMemcpyAsync(sums.data(), d_sums, P * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cat->h_frames.assign(P, PatchFrame{});
+    YAWB_CUDA(cudaMemcpyAsync(cat->h_frames.data(), cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
     YAWB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (size_t)B * P * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
     YAWB_CUDA(cudaMemcpyAsync(cat->h_sumw.data(), d_sumw, (size_t)B * P * sizeof(double),
                               cudaMemcpyDeviceToHost, st));
     YAWB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_xyz);
+    YAWB_CUDA(cudaGetLastError());
 
     cat->h_counts.assign((size_t)B * P, 0);
     cat->n = 0;
@@ -378,65 +499,8 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
         for (int b = 0; b < B; ++b)
             cat->h_seg_off[(size_t)p * B + b + 1] =
                 cat->h_seg_off[(size_t)p * B + b] + (int)cat->h_counts[(size_t)b * P + p];
-    if (dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1)) return 1;
     YAWB_CUDA(cudaMemcpyAsync(cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int),
                               cudaMemcpyHostToDevice, st));
-
-    // frames: centre = mean direction, e1/e2 any orthonormal tangent basis
-    cat->h_frames.assign(P, PatchFrame{});
-    for (int p = 0; p < P; ++p) {
-        PatchFrame &f = cat->h_frames[p];
-        double cx = sums[3 * p], cy = sums[3 * p + 1], cz = sums[3 * p + 2];
-        double nrm = std::sqrt(cx * cx + cy * cy + cz * cz);
-        if (!(nrm > 1e-12)) { cx = 0; cy = 0; cz = 1; nrm = 1; }  // empty or antipodally balanced patch
-        f.c[0] = cx / nrm; f.c[1] = cy / nrm; f.c[2] = cz / nrm;
-        double ax = 0, ay = 0, az = 1;  // helper axis least aligned with c
-        if (std::fabs(f.c[2]) > 0.9) { ax = 1; az = 0; }
-        double e1x = ay * f.c[2] - az * f.c[1], e1y = az * f.c[0] - ax * f.c[2], e1z = ax * f.c[1] - ay * f.c[0];
-        double n1 = std::sqrt(e1x * e1x + e1y * e1y + e1z * e1z);
-        f.e1[0] = e1x / n1; f.e1[1] = e1y / n1; f.e1[2] = e1z / n1;
-        f.e2[0] = f.c[1] * f.e1[2] - f.c[2] * f.e1[1];
-        f.e2[1] = f.c[2] * f.e1[0] - f.c[0] * f.e1[2];
-        f.e2[2] = f.c[0] * f.e1[1] - f.c[1] * f.e1[0];
-    }
-    if (dev_alloc(cat, &cat->d_frames, P)) return 1;
-    YAWB_CUDA(cudaMemcpyAsync(cat->d_frames, cat->h_frames.data(), P * sizeof(PatchFrame),
-                              cudaMemcpyHostToDevice, st));
-
-    // bounding boxes / radii
-    std::vector<unsigned long long> box(P * 5);
-    for (int p = 0; p < P; ++p) {
-        box[5 * p] = box[5 * p + 2] = ~0ull;
-        box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
-    }
-    YAWB_CUDA(cudaMemcpyAsync(d_box, box.data(), P * 5 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-    if (n > 0)
-        k_patch_bbox<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n, cat->d_frames,
-                                                         d_box);
-    YAWB_CUDA(cudaMemcpyAsync(box.data(), d_box, P * 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaStreamSynchronize(st));
-    for (int p = 0; p < P; ++p) {
-        PatchFrame &f = cat->h_frames[p];
-        if (box[5 * p] == ~0ull) {  // no rows
-            f.umin = f.umax = f.vmin = f.vmax = 0.0;
-            f.radius = 0.0;
-        } else {
-            f.umin = dec_double(box[5 * p]);
-            f.umax = dec_double(box[5 * p + 1]);
-            f.vmin = dec_double(box[5 * p + 2]);
-            f.vmax = dec_double(box[5 * p + 3]);
-            f.radius = std::sqrt(dec_double(box[5 * p + 4])) * (1.0 + 1e-12) + 1e-15;
-        }
-    }
-    YAWB_CUDA(cudaMemcpyAsync(cat->d_frames, cat->h_frames.data(), P * sizeof(PatchFrame),
-                              cudaMemcpyHostToDevice, st));
-    YAWB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_poff);
-    cudaFree(d_sums);
-    cudaFree(d_sumw);
-    cudaFree(d_counts);
-    cudaFree(d_box);
-    YAWB_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -480,27 +544,27 @@ int yawb_index_build_first(yawb_cat *cat) {
     if (dev_alloc(cat, &cat->d_sgrid, P)) return 1;
     YAWB_CUDA(cudaMemcpyAsync(cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid), cudaMemcpyHostToDevice, st));
 
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    unsigned *v0 = nullptr, *v1 = nullptr;
-    size_t nn = std::max<long long>(n_in, 1);
-    YAWB_CUDA(cudaMalloc(&k0, nn * 8)); YAWB_CUDA(cudaMalloc(&k1, nn * 8));
-    YAWB_CUDA(cudaMalloc(&v0, nn * 4)); YAWB_CUDA(cudaMalloc(&v1, nn * 4));
+    Scratch scr(st);
+    const size_t nn = std::max<long long>(n_in, 1);
+    unsigned long long *k0 = scr.get<unsigned long long>(nn), *k1 = scr.get<unsigned long long>(nn);
+    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
+    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
     if (n_in > 0) {
         k_keys_first<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in,
                                                             B, cat->d_frames, cat->d_sgrid, k0, v0);
         // dropped rows carry key ~0: sort all 64 bits only if something was dropped
         int end_bit = (n == n_in) ? bits_for((unsigned long long)std::max<long long>(base, 1)) : 64;
-        if (sort_pairs(ctx, k0, k1, v0, v1, n_in, end_bit)) return 1;
+        if (sort_pairs(ctx, scr, k0, k1, v0, v1, n_in, end_bit)) return 1;
     }
     if (dev_alloc(cat, &cat->sx, n) || dev_alloc(cat, &cat->sy, n) || dev_alloc(cat, &cat->sz, n)) return 1;
+    if (dev_alloc(cat, &cat->su, n) || dev_alloc(cat, &cat->sv, n) || dev_alloc(cat, &cat->st, n)) return 1;
     if (cat->weighted && dev_alloc(cat, &cat->sw, n)) return 1;
     if (dev_alloc(cat, &cat->cell_start, base + 1)) return 1;
     if (n > 0)
-        k_gather<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->sx, cat->sy,
-                                                     cat->sz, cat->sw);
+        k_gather_local<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->patch,
+                                                           cat->d_frames, cat->sx, cat->sy, cat->sz, cat->sw,
+                                                           cat->su, cat->sv, cat->st);
     k_cell_start<<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, cat->cell_start);
-    YAWB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
     YAWB_CUDA(cudaGetLastError());
     cat->has_sindex = true;
     return 0;
@@ -514,16 +578,16 @@ int yawb_index_build_second(yawb_cat *cat) {
     const long long n_in = cat->n_in, n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
 
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    unsigned *v0 = nullptr, *v1 = nullptr;
-    size_t nn = std::max<long long>(n_in, 1);
-    YAWB_CUDA(cudaMalloc(&k0, nn * 8)); YAWB_CUDA(cudaMalloc(&k1, nn * 8));
-    YAWB_CUDA(cudaMalloc(&v0, nn * 4)); YAWB_CUDA(cudaMalloc(&v1, nn * 4));
+    Scratch scr(st);
+    const size_t nn = std::max<long long>(n_in, 1);
+    unsigned long long *k0 = scr.get<unsigned long long>(nn), *k1 = scr.get<unsigned long long>(nn);
+    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
+    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
     if (n_in > 0) {
         k_keys_second<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch,
                                                              n_in, B, cat->d_frames, k0, v0);
         int end_bit = (n == n_in) ? 32 + bits_for((unsigned long long)std::max<long long>((long long)P * B, 1)) : 64;
-        if (sort_pairs(ctx, k0, k1, v0, v1, n_in, std::min(end_bit, 64))) return 1;
+        if (sort_pairs(ctx, scr, k0, k1, v0, v1, n_in, std::min(end_bit, 64))) return 1;
     }
     if (dev_alloc(cat, &cat->rx, n) || dev_alloc(cat, &cat->ry, n) || dev_alloc(cat, &cat->rz, n)) return 1;
     if (cat->weighted && dev_alloc(cat, &cat->rw, n)) return 1;
@@ -532,7 +596,8 @@ int yawb_index_build_second(yawb_cat *cat) {
                                                      cat->rz, cat->rw);
 
     // tiles: chunks of YAWB_TILE rows inside each (patch, bin) segment
-    std::vector<Tile> tiles;
+    std::vector<Tile> &tiles = cat->h_tiles;
+    tiles.clear();
     cat->h_ptile_off.assign(P + 1, 0);
     for (int p = 0; p < P; ++p) {
         cat->h_ptile_off[p] = (int)tiles.size();
@@ -558,8 +623,6 @@ int yawb_index_build_second(yawb_cat *cat) {
     if (cat->n_tiles > 0)
         k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz,
                                                                                       cat->d_tiles, cat->n_tiles);
-    YAWB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1);
     YAWB_CUDA(cudaGetLastError());
     cat->has_rtiles = true;
     return 0;
@@ -570,6 +633,7 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
     if (cat->has_sindex || everything) {
         dev_free(cat, cat->sx, n); dev_free(cat, cat->sy, n); dev_free(cat, cat->sz, n);
         dev_free(cat, cat->sw, n);
+        dev_free(cat, cat->su, n); dev_free(cat, cat->sv, n); dev_free(cat, cat->st, n);
         dev_free(cat, cat->d_sgrid, P);
         dev_free(cat, cat->cell_start, (size_t)cat->n_cells + 1);
         cat->has_sindex = false;

@@ -69,7 +69,8 @@ struct BinPar {
 constexpr int YAWB_RPL = 8;               // second-role points per lane
 constexpr int YAWB_TILE = 32 * YAWB_RPL;  // points per register tile (one warp)
 constexpr int YAWB_LCAP = 256;            // candidate list capacity per warp
-constexpr int YAWB_WARPS = 8;             // warps per CTA in the count kernel
+constexpr int YAWB_WARPS = 4;             // warps per CTA in the count kernel
+constexpr int YAWB_MIN_CTAS = 5;          // CTAs per SM the count kernel is compiled for (register budget)
 constexpr int YAWB_MAX_EDGES = 256;
 
 struct yawb_ctx {
@@ -108,6 +109,7 @@ struct yawb_cat {
     // first-role index: rows sorted by global sky-cell id
     bool has_sindex = false;
     double *sx = nullptr, *sy = nullptr, *sz = nullptr, *sw = nullptr;
+    double *su = nullptr, *sv = nullptr, *st = nullptr;  // rows in the frame of their own patch
     std::vector<SGrid> h_sgrid;
     SGrid *d_sgrid = nullptr;
     int *cell_start = nullptr;
@@ -117,6 +119,7 @@ struct yawb_cat {
     bool has_rtiles = false;
     double *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
     Tile *d_tiles = nullptr;
+    std::vector<Tile> h_tiles;     // host copy of the tile table (source of an async upload)
     std::vector<int> h_ptile_off;  // [n_patch + 1] first tile of each patch
     int *d_ptile_off = nullptr;
     int n_tiles = 0;
@@ -143,6 +146,7 @@ struct CountArgs {
     const double *d_r2;      // [n_bins][n_edges]
     const float *d_r2f;      // same, rounded to float
     const BinPar *d_binpar;  // [n_bins]
+    double rmax_all;         // max search radius over non-empty z-bins
     unsigned long long *d_out_cnt;  // [n_pairs][n_bins][n_edges-1]
     double *d_out_w;                // same or nullptr if both catalogs are unweighted
     bool weighted;
