@@ -35,7 +35,7 @@ typedef struct yawb_cat yawb_cat;
 
 /* roles for yawb_build_index() */
 #define YAWB_ROLE_FIRST 1  /* catalog used as first argument of yawb_count(): sky-cell index        */
-#define YAWB_ROLE_SECOND 2 /* catalog used as second argument: Morton-ordered register tiles        */
+#define YAWB_ROLE_SECOND 2 /* catalog used as second argument: Hilbert-ordered register tiles        */
 
 typedef struct {
     double kernel_ms;          /* device time of the pair-count kernel(s), CUDA events on the ctx stream */

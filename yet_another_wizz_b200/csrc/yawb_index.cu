@@ -8,7 +8,7 @@
 //   first role  (cat1 of yawb_count): rows sorted by global sky-cell id
 //               (patch, z-bin, row-major cell of a per-patch tangent-plane grid),
 //               plus cell_start[] -- a range query is one contiguous run per cell row;
-//   second role (cat2): rows sorted by (patch, z-bin, Morton code) and cut into
+//   second role (cat2): rows sorted by (patch, z-bin, Hilbert index) and cut into
 //               register tiles of YAWB_TILE compact points with a bounding sphere.
 //
 // Everything here is HBM-bound streaming work: coalesced SoA double arrays, one pass
@@ -285,13 +285,27 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
     keys[i] = (unsigned long long)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
 }
 
-__device__ __forceinline__ unsigned spread16(unsigned v) {
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
+// Hilbert index of a cell on a 65536 x 65536 grid.  Unlike the Morton (Z) curve the Hilbert curve has
+// no jumps: consecutive cells are always neighbours, so every run of YAWB_TILE consecutive rows is a
+// compact clump and no register tile straddles a quadrant boundary with a patch-sized bounding box.
+__device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y) {
+    unsigned d = 0;
+#pragma unroll
+    for (unsigned s = 1u << 15; s > 0; s >>= 1) {
+        const unsigned rx = (x & s) ? 1u : 0u;
+        const unsigned ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0u) {
+            if (rx == 1u) {
+                x = 65535u - x;
+                y = 65535u - y;
+            }
+            const unsigned t = x;
+            x = y;
+            y = t;
+        }
+    }
+    return d;
 }
 
 __global__ void k_keys_second(const double *__restrict__ x, const double *__restrict__ y,
@@ -313,12 +327,11 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     local_uv(f, x[i], y[i], z[i], u, v);
     double su = f.umax > f.umin ? 65535.0 / (f.umax - f.umin) : 0.0;
     double sv = f.vmax > f.vmin ? 65535.0 / (f.vmax - f.vmin) : 0.0;
-    // isotropic quantisation keeps Morton blocks square in (u, v)
+    // isotropic quantisation keeps the curve's blocks square in (u, v)
     double s = fmin(su > 0.0 ? su : sv, sv > 0.0 ? sv : su);
     int qu = min(max((int)((u - f.umin) * s), 0), 65535);
     int qv = min(max((int)((v - f.vmin) * s), 0), 65535);
-    unsigned morton = spread16((unsigned)qu) | (spread16((unsigned)qv) << 1);
-    keys[i] = ((unsigned long long)((long long)p * n_bins + b) << 32) | morton;
+    keys[i] = ((unsigned long long)((long long)p * n_bins + b) << 32) | hilbert16((unsigned)qu, (unsigned)qv);
 }
 
 __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,

@@ -49,7 +49,7 @@ struct SGrid {
 
 // ---- register tile of the second-role catalog -------------------------------------------
 struct Tile {
-    int start;   // first row in the Morton-sorted arrays
+    int start;   // first row in the Hilbert-sorted arrays
     int count;   // <= YAWB_TILE
     int patch;
     int bin;     // z-bin of the tile, or -1 for an unbinned catalog
@@ -115,7 +115,7 @@ struct yawb_cat {
     int *cell_start = nullptr;
     long long n_cells = 0;
 
-    // second-role index: rows sorted by (patch, bin, Morton code), cut into register tiles
+    // second-role index: rows sorted by (patch, bin, Hilbert index), cut into register tiles
     bool has_rtiles = false;
     double *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
     Tile *d_tiles = nullptr;
