@@ -235,3 +235,28 @@ def test_random_dense_fast_vs_exact(engine):
             assert fs["pair_tests"] < es["pair_tests"]  # pruning happened
             assert es["pair_tests"] == es["pair_tests_naive"]
             d1.free(); d2.free()
+
+
+@pytest.mark.parametrize("variant", ["sat", "pred"])
+def test_pair_test_variants_exact(engine, variant, monkeypatch):
+    """both FP32 pair-test formulations (7-instruction saturating ramp / 8-instruction predicated) must
+    reproduce the reference's counts on the adversarial on-edge set and on dense random data"""
+    monkeypatch.setenv("YAWB_PAIR_TEST", variant)
+    g = golden_io.load("edge_adversarial")
+    a, b = g["a_xyz"], g["b_xyz"]
+    for key in ("upper", "lower"):
+        lim = oracle.parse_ang_limits(g[f"{key}_ang_min"], g[f"{key}_ang_max"])
+        ang_bins = oracle.get_ang_bins(lim, None, 50)
+        ci, _, stats = single_patch_hist(engine, a, None, b, None, oracle.chord_sq_edges(ang_bins), False)
+        assert ci[0] == int(g[f"{key}_counts"][0])
+        assert stats["rechecks"] > 0
+    # dense small-angle data: thousands of pairs per edge band
+    rng = np.random.default_rng(3)
+    n = 40000
+    ra = rng.uniform(0.0, 0.02, n); dec = np.arcsin(rng.uniform(-0.01, 0.01, n))
+    xyz = oracle.radec_to_xyz(ra, dec)
+    r2 = oracle.chord_sq_edges(np.array([3e-4, 2e-3]))
+    fi, _, fs = single_patch_hist(engine, xyz[: n // 2], None, xyz[n // 2 :], None, r2, False)
+    ei, _, _ = single_patch_hist(engine, xyz[: n // 2], None, xyz[n // 2 :], None, r2, True)
+    assert_array_equal(fi, ei)
+    assert ei[0] > 1e6 and fs["rechecks"] > 0

@@ -20,6 +20,8 @@
 //
 // k_count_exact -- all-pairs FP64 kernel without pruning (validation and cross-check).
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 
 #include "yawb_internal.cuh"
 
@@ -234,6 +236,49 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
     }
 }
 
+// ---- phase 2, single sub-bin, unweighted: 7 FMA-pipe instructions per test ----------------------
+// v = sat(C - K |u|) is a ramp through the uncertainty band: exactly 1 well inside the bin, exactly 0
+// well outside, in [0.375, 0.625] wherever FP32 cannot decide (K = 1 / (8 eps), C = 1/2 + h K).
+// sum(v) and sum(v*v) are accumulated; they are equal iff every v of the chunk was 0 or 1 (then
+// sum(v) is the exact count); any undecidable test makes them differ by >= 0.23 and the lane's share
+// of the chunk is re-evaluated in FP64.  FADD + 3 FFMA + FFMA.SAT + FADD + FFMA, no ALU-pipe work.
+__device__ __forceinline__ void phase2_single_sat(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
+                                                  const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
+                                                  const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
+                                                  float K, float C, const Tile &tl, int lane, double lo, double hi,
+                                                  unsigned &cnt_total, unsigned &n_recheck) {
+    const float nK = -K;
+    for (int e0 = ea; e0 < eb; e0 += CHUNK) {
+        const int e1 = min(e0 + CHUNK, eb);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+            const float4 s = S.list[e];
+#pragma unroll
+            for (int r = 0; r < YAWB_RPL; ++r) {
+                float u = rn[r] + s.w;
+                u = fmaf(rx[r], s.x, u);
+                u = fmaf(ry[r], s.y, u);
+                u = fmaf(rz[r], s.z, u);
+                const float v = __saturatef(fmaf(fabsf(u), nK, C));
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+            }
+        }
+        unsigned c = (unsigned)(s1 + 0.5f);
+        unsigned flagged = __ballot_sync(FULL, s1 != s2);
+        while (flagged) {
+            const int src = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            unsigned cx = 0;
+            double wx = 0.0;
+            recheck_chunk<false>(P, S, e0, e1, tl, lane, src, lo, hi, cx, wx, n_recheck);
+            if (lane == src) c = cx;
+        }
+        cnt_total += c;
+    }
+}
+
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
 template <bool WEIGHTED>
 __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
@@ -281,7 +326,7 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
-template <bool WEIGHTED, bool MULTI>
+template <bool WEIGHTED, bool MULTI, bool SAT>
 __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_fast(const FastParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -428,8 +473,14 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_fast(c
                     const float m2 = hx * hx + hy * hy + hz * hz;
                     const float eps = 64.0f * EPS32 * (m2 + bp.mid) * 1.0001f;
                     S.binrec[b] = make_float4(hx, hy, hz, bp.mid);
-                    S.binthr[b] = MULTI ? make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi)
-                                        : make_float2(bp.h - eps, bp.h + eps);
+                    if (MULTI) {
+                        S.binthr[b] = make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi);
+                    } else if (SAT) {
+                        const float K = 1.0f / (8.0f * eps);
+                        S.binthr[b] = make_float2(K, 0.5f + bp.h * K);
+                    } else {
+                        S.binthr[b] = make_float2(bp.h - eps, bp.h + eps);
+                    }
                 }
             }
             int incl = nrows;  // inclusive scan of the cell rows over the lanes
@@ -479,8 +530,12 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_fast(c
                 } else {
                     unsigned cnt_total = 0;
                     double w_total = 0.0;
-                    phase2_single<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane, P.binpar[b].lo,
-                                            P.binpar[b].hi, cnt_total, w_total, n_recheck);
+                    if constexpr (SAT && !WEIGHTED)
+                        phase2_single_sat(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane, P.binpar[b].lo,
+                                          P.binpar[b].hi, cnt_total, n_recheck);
+                    else
+                        phase2_single<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane,
+                                                P.binpar[b].lo, P.binpar[b].hi, cnt_total, w_total, n_recheck);
                     const unsigned tot = __reduce_add_sync(FULL, cnt_total);
                     double wtot = 0.0;
                     if (WEIGHTED) wtot = warp_sum(w_total);
@@ -685,16 +740,21 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     ctas = (int)std::min<long long>(ctas, (warps_needed + YAWB_WARPS - 1) / YAWB_WARPS);
     ctas = std::max(ctas, 1);
 
-#define LAUNCH(W, M)                                                                                   \
-    do {                                                                                               \
-        YAWB_CUDA(cudaFuncSetAttribute(k_count_fast<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                    \
-        k_count_fast<W, M><<<ctas, YAWB_WARPS * 32, smem, ctx->stream>>>(P);                           \
+#define LAUNCH(W, M, T)                                                                                   \
+    do {                                                                                                  \
+        YAWB_CUDA(cudaFuncSetAttribute(k_count_fast<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                       \
+        k_count_fast<W, M, T><<<ctas, YAWB_WARPS * 32, smem, ctx->stream>>>(P);                           \
     } while (0)
+    // unweighted single-bin counts use the 7-instruction saturating test unless YAWB_PAIR_TEST=pred
+    const char *variant = getenv("YAWB_PAIR_TEST");
+    const bool sat = !(variant && strcmp(variant, "pred") == 0);
     if (a.weighted) {
-        if (multi) LAUNCH(true, true); else LAUNCH(true, false);
+        if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
     } else {
-        if (multi) LAUNCH(false, true); else LAUNCH(false, false);
+        if (multi) LAUNCH(false, true, false);
+        else if (sat) LAUNCH(false, false, true);
+        else LAUNCH(false, false, false);
     }
 #undef LAUNCH
     YAWB_CUDA(cudaGetLastError());
