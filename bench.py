@@ -100,6 +100,19 @@ def make_workload(name: str, scale: float = 1.0):
                 plan=plan, naive=naive, t_catalogs=t_cat, t_host_prep=t_prep, n_patch=nx * ny)
 
 
+def subset_patches(a: dict, keep: np.ndarray) -> dict:
+    """host arrays of one catalog restricted to the patches in `keep` (all others become empty)"""
+    off = a["patch_off"]
+    sizes = np.zeros(len(off) - 1, dtype=np.int64)
+    sizes[keep] = np.diff(off)[keep]
+    sel = np.concatenate([np.arange(off[p], off[p + 1]) for p in keep]) if len(keep) else np.empty(0, dtype=np.int64)
+    return dict(
+        xyz=np.ascontiguousarray(a["xyz"][sel]), patch_off=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
+        weights=None if a["weights"] is None else np.ascontiguousarray(a["weights"][sel]),
+        zbin=None if a["zbin"] is None else np.ascontiguousarray(a["zbin"][sel]), n_bins=a["n_bins"],
+    )
+
+
 COUNT_TYPES = dict(DD=("ref", "unk"), DR=("ref", "unk_rand"), RD=("ref_rand", "unk"), RR=("ref_rand", "unk_rand"))
 
 
@@ -259,18 +272,27 @@ def run_gpu_arm(args):
     pi, pj, plan = wl["pair_i"], wl["pair_j"], wl["plan"]
     total_naive = sum(wl["naive"].values())
 
-    # this rank's share of the patch pairs (static LPT on the cost model)
+    # this rank's share: second-catalog patches are dealt out by LPT on their summed pair cost, a rank
+    # counts every linked pair of its patches and holds only the rows it needs (its own second-catalog
+    # patches, plus the first-catalog patches linked to them)
     own = np.arange(len(pi))
+    arrays = wl["arrays"]
     if world > 1:
-        n1 = np.diff(wl["arrays"]["ref_rand"]["patch_off"])
-        n2 = np.diff(wl["arrays"]["unk_rand"]["patch_off"])
-        own = assign_pairs_lpt(pair_costs(pi, pj, n1, n2), world)[rank]
+        n1 = np.diff(arrays["ref_rand"]["patch_off"])
+        n2 = np.diff(arrays["unk_rand"]["patch_off"])
+        costs = pair_costs(pi, pj, n1, n2)
+        patch_cost = np.bincount(pj, weights=costs, minlength=wl["n_patch"])
+        my_patches = assign_pairs_lpt(patch_cost, world)[rank]
+        own = np.flatnonzero(np.isin(pj, my_patches))
+        need = dict(second=np.unique(pj[own]), first=np.unique(pi[own]))
+        arrays = {k: subset_patches(a, need["first" if k in ("ref", "ref_rand") else "second"])
+                  for k, a in arrays.items()}
     opi, opj = pi[own], pj[own]
 
     # pinned host staging of the inputs (what a caller holding host buffers hands to the C ABI)
     host = {}
     h2d_bytes = 0
-    for key, a in wl["arrays"].items():
+    for key, a in arrays.items():
         h = {}
         for name in ("xyz", "weights", "zbin"):
             if a[name] is None:
@@ -402,7 +424,8 @@ def run_gpu_arm(args):
                      f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, 100-1000 kpc, BoxRandoms {BOX}",
             linked_patch_pairs=int(len(pi)), naive_pair_tests=wl["naive"], pairs_in_scale=in_scale,
             l2="inputs (>= 1 GB of catalog rows) exceed the 126 MB L2; every step rebuilds the index from the raw rows",
-            parallelism=f"patch-pair LPT sharding over {world} GPU(s), catalogs replicated, one NCCL reduce",
+            parallelism=f"second-catalog patches dealt to {world} GPU(s) by LPT, each rank holds only the rows of its "
+                        f"patches and of the first-catalog patches linked to them, one NCCL reduce of the counts",
         ),
         breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=t_kernel * 1e3,
                           per_count={tag: stats_last[tag]["kernel_ms"] for tag in COUNT_TYPES},

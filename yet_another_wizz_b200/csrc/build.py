@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["yawb_api.cu", "yawb_index.cu", "yawb_count.cu"]
-HEADERS = ["yawb_internal.cuh", os.path.join(ROOT, "include", "yawb.h")]
+HEADERS = ["yawb_internal.cuh", "yawb_count_ws.cuh", os.path.join(ROOT, "include", "yawb.h")]
 OUT = os.path.join(HERE, "libyawb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -37,7 +37,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC, *FLAGS, "-o", OUT, *[os.path.join(HERE, s) for s in SOURCES]]
+    extra = os.environ.get("YAWB_NVCC_EXTRA", "").split()
+    cmd = [NVCC, *FLAGS, *extra, "-o", OUT, *[os.path.join(HERE, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

@@ -353,7 +353,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     s.kernel_ms = t_k;
     s.pair_tests = h_counters[1];
     s.rechecks = h_counters[2];
-    s.work_items = h_counters[3];
+    s.work_items = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? (uint64_t)n_pairs * B : h_counters[4];
     s.launches = (uint64_t)launches;
     if (stats) *stats = s;
     return 0;

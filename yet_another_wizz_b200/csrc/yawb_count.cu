@@ -4,7 +4,7 @@
 // (reference src/yaw/catalog/trees.py:348-353) and the per-z-bin loop of
 // process_patch_pair (src/yaw/correlation/measurements.py:109-124).
 //
-// k_count_fast  -- the production kernel.  One warp owns a register tile of YAWB_TILE
+// k_count_uni   -- the production kernel (yawb_count_ws.cuh).  One warp owns a register tile of YAWB_TILE
 //   second-catalog points (YAWB_RPL per lane).  For every z-bin it gathers the
 //   first-catalog points of the linked patch that fall into the tile's bounding box
 //   grown by the bin's search radius (sky-cell rows -> contiguous runs -> per-point
@@ -47,6 +47,8 @@ struct FastParams {
     const int *pair_i, *pair_j;
     const long long *pair_item_base;
     long long n_items;
+    const int2 *live;  // (patch pair, tile) work items that survived the bounding-sphere test
+    int debug;         // development only: 1 = skip the pair tests, 2 = run them twice (timing experiments)
     int n_pairs, n_bins, n_edges;
     const double *r2;
     const float *r2f;
@@ -88,6 +90,7 @@ __device__ __forceinline__ double warp_max(double v) {
 
 // ---- per-warp shared memory -------------------------------------------------------------------
 constexpr int CCAP = 128;  // (z-bin, cell-row) combinations resolved per batch
+constexpr int GRAB = 4;    // work items taken per atomic
 
 template <bool WEIGHTED>
 struct WarpSmem {
@@ -107,45 +110,8 @@ struct WarpSmem {
     int *cbin;                // [CCAP] z-bin of the run
     unsigned *hist;           // [nsub] (MULTI)
     unsigned short *lbin;     // [LCAP] z-bin of the candidate
+    unsigned short *seg;      // [LCAP] first entry of every z-bin segment of the staged list
 };
-
-__host__ __device__ inline size_t warp_smem_bytes(bool weighted, bool multi, int n_bins, int nsub) {
-    size_t b = YAWB_LCAP * sizeof(float4);
-    if (weighted) b += YAWB_LCAP * sizeof(double);
-    b += (size_t)n_bins * nsub * sizeof(unsigned long long);
-    if (weighted) b += (size_t)n_bins * nsub * sizeof(double);
-    if (multi && weighted) b += (size_t)nsub * sizeof(double);
-    b += (size_t)n_bins * (sizeof(float4) + sizeof(float2));
-    b += YAWB_LCAP * sizeof(int);
-    b += (size_t)(3 * n_bins + 1) * sizeof(int);
-    b += 3 * CCAP * sizeof(int);
-    if (multi) b += (size_t)nsub * sizeof(unsigned);
-    b += YAWB_LCAP * sizeof(unsigned short);
-    return (b + 15) & ~(size_t)15;
-}
-
-template <bool WEIGHTED>
-__device__ __forceinline__ void carve_smem(WarpSmem<WEIGHTED> &S, unsigned char *p, bool multi, int n_bins, int nsub) {
-    const size_t nacc = (size_t)n_bins * nsub;
-    // 16-byte objects first, then 8-, 4- and 2-byte ones, so every array is naturally aligned
-    S.list = (float4 *)p; p += YAWB_LCAP * sizeof(float4);
-    S.binrec = (float4 *)p; p += (size_t)n_bins * sizeof(float4);
-    S.lw = nullptr; S.accw = nullptr; S.histw = nullptr; S.hist = nullptr;
-    if (WEIGHTED) { S.lw = (double *)p; p += YAWB_LCAP * sizeof(double); }
-    S.acc = (unsigned long long *)p; p += nacc * sizeof(unsigned long long);
-    if (WEIGHTED) { S.accw = (double *)p; p += nacc * sizeof(double); }
-    if (multi && WEIGHTED) { S.histw = (double *)p; p += (size_t)nsub * sizeof(double); }
-    S.binthr = (float2 *)p; p += (size_t)n_bins * sizeof(float2);
-    S.lidx = (int *)p; p += YAWB_LCAP * sizeof(int);
-    S.bin_iv0 = (int *)p; p += (size_t)n_bins * sizeof(int);
-    S.bin_iu = (int *)p; p += (size_t)n_bins * sizeof(int);
-    S.cstart = (int *)p; p += (size_t)(n_bins + 1) * sizeof(int);
-    S.rs0 = (int *)p; p += CCAP * sizeof(int);
-    S.rpre = (int *)p; p += CCAP * sizeof(int);
-    S.cbin = (int *)p; p += CCAP * sizeof(int);
-    if (multi) { S.hist = (unsigned *)p; p += (size_t)nsub * sizeof(unsigned); }
-    S.lbin = (unsigned short *)p;
-}
 
 // ---- exact re-evaluation of one lane's share of a chunk, done by the whole warp ----------------
 // Lane `src` saw a test inside the FP32 uncertainty band.  Its (YAWB_RPL x chunk) tests are
@@ -174,43 +140,68 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
 }
 
 // ---- phase 2, single sub-bin (n_edges == 2): the hot loop ----------------------------------
-// entries [ea, eb) of the list belong to one z-bin with thresholds (h_in, h_out)
-template <bool WEIGHTED>
+// One candidate against the lane's YAWB_RPL rows:  u = (rn + s.w) + rx s.x + ry s.y + rz s.z = d2 - mid.
+//   predicated: |u| < h - eps, |u| < h + eps (2 FSETP) + 2 predicated FADD, also feeds the weighted sums;
+//   SAT: v = sat(C - K |u|) is a ramp through the uncertainty band: exactly 1 well inside the bin,
+//        exactly 0 well outside, in [0.375, 0.625] wherever FP32 cannot decide (K = 1 / (8 eps),
+//        C = 1/2 + h K).  sum(v) and sum(v*v) are equal iff every v of the chunk was 0 or 1 (then
+//        sum(v) is the exact count); an undecidable test makes them differ by >= 0.23.
+// Two accumulator pairs (even / odd rows) halve the length of the dependent add chains.
+template <bool WEIGHTED, bool SAT>
+__device__ __forceinline__ void test_candidate(const float4 s, double swt, const float (&rx)[YAWB_RPL],
+                                               const float (&ry)[YAWB_RPL], const float (&rz)[YAWB_RPL],
+                                               const float (&rn)[YAWB_RPL], float ta, float tb,
+                                               float (&acc_a)[2], float (&acc_b)[2], double (&ws)[YAWB_RPL]) {
+#pragma unroll
+    for (int r = 0; r < YAWB_RPL; ++r) {
+        float u = rn[r] + s.w;
+        u = fmaf(rx[r], s.x, u);
+        u = fmaf(ry[r], s.y, u);
+        u = fmaf(rz[r], s.z, u);
+        if (SAT) {
+            const float v = __saturatef(fmaf(fabsf(u), ta, tb));  // ta = -K, tb = C
+            acc_a[r & 1] += v;
+            acc_b[r & 1] = fmaf(v, v, acc_b[r & 1]);
+        } else {
+            const float au = fabsf(u);
+            const bool in = au < ta;  // ta = h - eps, tb = h + eps
+            if (in) acc_a[r & 1] += 1.f;
+            if (au < tb) acc_b[r & 1] += 1.f;
+            if (WEIGHTED) {
+                if (in) ws[r] += swt;
+            }
+        }
+    }
+}
+
+// entries [ea, eb) of the list belong to one z-bin
+template <bool WEIGHTED, bool SAT>
 __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
                                               const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
                                               const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
-                                              float h_in, float h_out, const Tile &tl, int lane, double lo,
+                                              float ta, float tb, const Tile &tl, int lane, double lo,
                                               double hi, unsigned &cnt_total, double &w_total,
                                               unsigned &n_recheck) {
     for (int e0 = ea; e0 < eb; e0 += CHUNK) {
         const int e1 = min(e0 + CHUNK, eb);
-        float c_in = 0.f, c_maybe = 0.f;
+        float acc_a[2] = {0.f, 0.f}, acc_b[2] = {0.f, 0.f};
         double ws[YAWB_RPL];
         if (WEIGHTED) {
 #pragma unroll
             for (int r = 0; r < YAWB_RPL; ++r) ws[r] = 0.0;
         }
-#pragma unroll 4
-        for (int e = e0; e < e1; ++e) {
-            const float4 s = S.list[e];
-            double swt = 0.0;
-            if (WEIGHTED) swt = S.lw[e];
+        if (e1 - e0 == CHUNK) {  // common case: fully unrolled, no loop bookkeeping
 #pragma unroll
-            for (int r = 0; r < YAWB_RPL; ++r) {
-                float u = rn[r] + s.w;
-                u = fmaf(rx[r], s.x, u);
-                u = fmaf(ry[r], s.y, u);
-                u = fmaf(rz[r], s.z, u);
-                const float au = fabsf(u);
-                const bool in = au < h_in;
-                if (in) c_in += 1.f;
-                if (au < h_out) c_maybe += 1.f;
-                if (WEIGHTED) {
-                    if (in) ws[r] += swt;
-                }
-            }
+            for (int k = 0; k < CHUNK; ++k)
+                test_candidate<WEIGHTED, SAT>(S.list[e0 + k], WEIGHTED ? S.lw[e0 + k] : 0.0, rx, ry, rz, rn, ta, tb,
+                                              acc_a, acc_b, ws);
+        } else {
+            for (int e = e0; e < e1; ++e)
+                test_candidate<WEIGHTED, SAT>(S.list[e], WEIGHTED ? S.lw[e] : 0.0, rx, ry, rz, rn, ta, tb, acc_a,
+                                              acc_b, ws);
         }
-        unsigned c = (unsigned)c_in;
+        const float sa = acc_a[0] + acc_a[1], sb = acc_b[0] + acc_b[1];
+        unsigned c = (unsigned)(sa + 0.5f);
         double wsum = 0.0;
         if (WEIGHTED) {
 #pragma unroll
@@ -219,7 +210,7 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
                 if (ws[r] != 0.0) wsum += ws[r] * (P.rw ? P.rw[tl.start + min(k, tl.count - 1)] : 1.0);
             }
         }
-        unsigned flagged = __ballot_sync(FULL, c_in != c_maybe);
+        unsigned flagged = __ballot_sync(FULL, sa != sb);
         while (flagged) {  // warp-uniform: some lane met the uncertainty band of an edge
             const int src = __ffs(flagged) - 1;
             flagged &= flagged - 1;
@@ -233,49 +224,6 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
         }
         cnt_total += c;
         if (WEIGHTED) w_total += wsum;
-    }
-}
-
-// ---- phase 2, single sub-bin, unweighted: 7 FMA-pipe instructions per test ----------------------
-// v = sat(C - K |u|) is a ramp through the uncertainty band: exactly 1 well inside the bin, exactly 0
-// well outside, in [0.375, 0.625] wherever FP32 cannot decide (K = 1 / (8 eps), C = 1/2 + h K).
-// sum(v) and sum(v*v) are accumulated; they are equal iff every v of the chunk was 0 or 1 (then
-// sum(v) is the exact count); any undecidable test makes them differ by >= 0.23 and the lane's share
-// of the chunk is re-evaluated in FP64.  FADD + 3 FFMA + FFMA.SAT + FADD + FFMA, no ALU-pipe work.
-__device__ __forceinline__ void phase2_single_sat(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
-                                                  const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
-                                                  const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
-                                                  float K, float C, const Tile &tl, int lane, double lo, double hi,
-                                                  unsigned &cnt_total, unsigned &n_recheck) {
-    const float nK = -K;
-    for (int e0 = ea; e0 < eb; e0 += CHUNK) {
-        const int e1 = min(e0 + CHUNK, eb);
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 4
-        for (int e = e0; e < e1; ++e) {
-            const float4 s = S.list[e];
-#pragma unroll
-            for (int r = 0; r < YAWB_RPL; ++r) {
-                float u = rn[r] + s.w;
-                u = fmaf(rx[r], s.x, u);
-                u = fmaf(ry[r], s.y, u);
-                u = fmaf(rz[r], s.z, u);
-                const float v = __saturatef(fmaf(fabsf(u), nK, C));
-                s1 += v;
-                s2 = fmaf(v, v, s2);
-            }
-        }
-        unsigned c = (unsigned)(s1 + 0.5f);
-        unsigned flagged = __ballot_sync(FULL, s1 != s2);
-        while (flagged) {
-            const int src = __ffs(flagged) - 1;
-            flagged &= flagged - 1;
-            unsigned cx = 0;
-            double wx = 0.0;
-            recheck_chunk<false>(P, S, e0, e1, tl, lane, src, lo, hi, cx, wx, n_recheck);
-            if (lane == src) c = cx;
-        }
-        cnt_total += c;
     }
 }
 
@@ -325,311 +273,36 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
     }
 }
 
-// ---- the kernel -------------------------------------------------------------------------------
-template <bool WEIGHTED, bool MULTI, bool SAT>
-__global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_fast(const FastParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nsub = P.n_edges - 1;
-    const int nacc = P.n_bins * nsub;
-
-    WarpSmem<WEIGHTED> S;
-    carve_smem<WEIGHTED>(S, smem_raw + (size_t)warp * warp_smem_bytes(WEIGHTED, MULTI, P.n_bins, nsub), MULTI,
-                         P.n_bins, nsub);
-    for (int k = lane; k < nacc; k += 32) {
-        S.acc[k] = 0ull;
-        if (WEIGHTED) S.accw[k] = 0.0;
-    }
-    __syncwarp();
-
-    int cur_pair = -1;
-    long long cur_lo = 0, cur_hi = 0;  // item range of cur_pair
-    unsigned long long n_tests = 0;
-    unsigned n_recheck = 0, n_live = 0;
-
-    auto flush_pair = [&]() {
-        if (cur_pair < 0) return;
-        __syncwarp();
-        for (int k = lane; k < nacc; k += 32) {
-            const unsigned long long c = S.acc[k];
-            if (c) {
-                atomicAdd(&P.out_cnt[(size_t)cur_pair * nacc + k], c);
-                S.acc[k] = 0ull;
-            }
-            if (WEIGHTED) {
-                const double w = S.accw[k];
-                if (w != 0.0) {
-                    atomicAdd(&P.out_w[(size_t)cur_pair * nacc + k], w);
-                    S.accw[k] = 0.0;
-                }
-            }
-        }
-        __syncwarp();
-    };
-
-    while (true) {
-        long long item = 0;
-        if (lane == 0) item = (long long)atomicAdd(&P.counters[0], 1ull);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= P.n_items) break;
-
-        if (item < cur_lo || item >= cur_hi) {  // new patch pair: flush, then locate it
-            flush_pair();
-            int lo = 0, hi = P.n_pairs;  // last k with base[k] <= item
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (P.pair_item_base[mid] <= item) lo = mid; else hi = mid;
-            }
-            cur_pair = lo;
-            cur_lo = P.pair_item_base[lo];
-            cur_hi = P.pair_item_base[lo + 1];
-        }
-        const int p1 = P.pair_i[cur_pair];
-        const int p2 = P.pair_j[cur_pair];
-        const Tile tl = P.tiles[P.ptile_off[p2] + (int)(item - cur_lo)];
+// ---- planner: which (patch pair, tile) items can hold pairs at all -------------------------------
+// grid (tile blocks, patch pairs).  A tile of the second catalog survives for pair (p1, p2) if its
+// bounding sphere comes within the largest search radius of the bounding sphere of patch p1 of the first
+// catalog (chord distances obey the triangle inequality).  Survivors are appended to `live` with one
+// atomic per warp; counters[4] ends up holding their number.
+__global__ void k_plan(const FastParams P, int2 *__restrict__ live_out) {
+    const int k = blockIdx.y;
+    const int p1 = P.pair_i[k], p2 = P.pair_j[k];
+    const int t0 = P.ptile_off[p2], nt = P.ptile_off[p2 + 1] - t0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= nt) return;
+    bool ok = false;
+    if (t < nt) {
+        const Tile tl = P.tiles[t0 + t];
         const PatchFrame &F = P.sframe[p1];
-
-        // bounding-sphere rejection of the whole item (chord distances obey the triangle inequality)
-        const int b_lo = tl.bin >= 0 ? tl.bin : 0;
-        const int b_hi = tl.bin >= 0 ? tl.bin + 1 : P.n_bins;
-        {
-            const double dx = (double)tl.cx - F.c[0], dy = (double)tl.cy - F.c[1], dz = (double)tl.cz - F.c[2];
-            const double rmax_all = tl.bin >= 0 ? (P.binpar[tl.bin].empty ? 0.0 : P.binpar[tl.bin].rmax) : P.rmax_all;
-            const double reach = F.radius + (double)tl.rad + rmax_all + 1e-9;
-            if (rmax_all == 0.0 || dx * dx + dy * dy + dz * dz > reach * reach) continue;
-        }
-        n_live += 1;
-
-        // second-catalog points of this lane in the frame of patch p1: pass 1 finds the tile box,
-        // pass 2 re-derives the coordinates relative to the box centre and rounds them ONCE to float
-        const double c0 = F.c[0], c1 = F.c[1], c2 = F.c[2];
-        const double a0 = F.e1[0], a1 = F.e1[1], a2 = F.e1[2];
-        const double g0 = F.e2[0], g1 = F.e2[1], g2 = F.e2[2];
-        double umin = DBL_MAX, umax = -DBL_MAX, vmin = DBL_MAX, vmax = -DBL_MAX, tmin = DBL_MAX, tmax = -DBL_MAX;
-#pragma unroll
-        for (int r = 0; r < YAWB_RPL; ++r) {
-            const int k = lane + 32 * r;
-            if (k < tl.count) {
-                const int j = tl.start + k;
-                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                const double lu = dx * a0 + dy * a1 + dz * a2;
-                const double lv = dx * g0 + dy * g1 + dz * g2;
-                const double lt = dx * c0 + dy * c1 + dz * c2;
-                umin = fmin(umin, lu); umax = fmax(umax, lu);
-                vmin = fmin(vmin, lv); vmax = fmax(vmax, lv);
-                tmin = fmin(tmin, lt); tmax = fmax(tmax, lt);
-            }
-        }
-        umin = warp_min(umin); umax = warp_max(umax);
-        vmin = warp_min(vmin); vmax = warp_max(vmax);
-        tmin = warp_min(tmin); tmax = warp_max(tmax);
-        const double ou = 0.5 * (umin + umax), ov = 0.5 * (vmin + vmax), ot = 0.5 * (tmin + tmax);
-
-        float rx[YAWB_RPL], ry[YAWB_RPL], rz[YAWB_RPL], rn[YAWB_RPL];
-#pragma unroll
-        for (int r = 0; r < YAWB_RPL; ++r) {
-            const int k = lane + 32 * r;
-            if (k < tl.count) {
-                const int j = tl.start + k;
-                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                rx[r] = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
-                ry[r] = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
-                rz[r] = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
-                rn[r] = rx[r] * rx[r] + ry[r] * ry[r] + rz[r] * rz[r];
-            } else {
-                rx[r] = FAR; ry[r] = FAR; rz[r] = FAR;
-                rn[r] = 3.0f * FAR * FAR;
-            }
-        }
-        const SGrid G = P.sgrid[p1];
-        const double eu = 0.5 * (umax - umin), ev = 0.5 * (vmax - vmin), et = 0.5 * (tmax - tmin);
-
-        // ---- step 1: per z-bin query box, thresholds and cell rows (one lane per z-bin) ----
-        int carry = 0;
-        for (int b0 = b_lo; b0 < b_hi; b0 += 32) {
-            const int b = b0 + lane;
-            int nrows = 0;
-            if (b < b_hi) {
-                const BinPar bp = P.binpar[b];
-                if (!bp.empty) {
-                    // query box = tile box grown by the search radius (sound: |du|,|dv|,|dt| <= chord)
-                    const double qu0 = umin - bp.rmax, qu1 = umax + bp.rmax;
-                    const double qv0 = vmin - bp.rmax, qv1 = vmax + bp.rmax;
-                    // cell range of the box; floor((x - u0) * inv_c) is the same monotone expression the
-                    // keys were made with, so a point inside the box cannot sit in a cell outside the range
-                    const double fu0 = floor((qu0 - G.u0) * G.inv_c), fu1 = floor((qu1 - G.u0) * G.inv_c);
-                    const double fv0 = floor((qv0 - G.v0) * G.inv_c), fv1 = floor((qv1 - G.v0) * G.inv_c);
-                    if (!(fu1 < 0.0 || fv1 < 0.0 || fu0 > (double)(G.gu - 1) || fv0 > (double)(G.gv - 1))) {
-                        const int iu0 = (int)fmax(fu0, 0.0), iv0 = (int)fmax(fv0, 0.0);
-                        const int iu1 = (int)fmin(fu1, (double)(G.gu - 1)), iv1 = (int)fmin(fv1, (double)(G.gv - 1));
-                        nrows = iv1 - iv0 + 1;
-                        S.bin_iv0[b] = iv0;
-                        S.bin_iu[b] = iu0 | (iu1 << 16);
-                    }
-                    // half extents rounded up; they bound every staged vector, hence the FP32 error of u
-                    const float hx = (float)(eu + bp.rmax) * 1.000001f, hy = (float)(ev + bp.rmax) * 1.000001f,
-                                hz = (float)(et + bp.rmax) * 1.000001f;
-                    const float m2 = hx * hx + hy * hy + hz * hz;
-                    const float eps = 64.0f * EPS32 * (m2 + bp.mid) * 1.0001f;
-                    S.binrec[b] = make_float4(hx, hy, hz, bp.mid);
-                    if (MULTI) {
-                        S.binthr[b] = make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi);
-                    } else if (SAT) {
-                        const float K = 1.0f / (8.0f * eps);
-                        S.binthr[b] = make_float2(K, 0.5f + bp.h * K);
-                    } else {
-                        S.binthr[b] = make_float2(bp.h - eps, bp.h + eps);
-                    }
-                }
-            }
-            int incl = nrows;  // inclusive scan of the cell rows over the lanes
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (b < b_hi) S.cstart[b + 1] = carry + incl;
-            carry += __shfl_sync(FULL, incl, 31);
-        }
-        if (lane == 0) S.cstart[b_lo] = 0;
-        const int n_combo = carry;
-        __syncwarp();
-
-        int L = 0;
-        // ---- consume the staged list: one run of phase 2 per z-bin segment ----
-        auto consume = [&]() {
-            __syncwarp();
-            int ea = 0;
-            while (ea < L) {
-                const int b = S.lbin[ea];
-                int eb = L;  // first entry after ea that belongs to another z-bin
-                for (int base = ea + 1; base < L; base += 32) {
-                    const int e = base + lane;
-                    const unsigned m = __ballot_sync(FULL, e < L && S.lbin[e] != b);
-                    if (m) {
-                        eb = base + __ffs(m) - 1;
-                        break;
-                    }
-                }
-                const float2 thr = S.binthr[b];
-                if (MULTI) {
-                    for (int k = lane; k < nsub; k += 32) {
-                        S.hist[k] = 0u;
-                        if (WEIGHTED) S.histw[k] = 0.0;
-                    }
-                    __syncwarp();
-                    phase2_multi<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, S.binrec[b].w, tl, lane, b,
-                                           n_recheck);
-                    __syncwarp();
-                    for (int k = lane; k < nsub; k += 32) {
-                        S.acc[(size_t)b * nsub + k] += S.hist[k];
-                        if (WEIGHTED) S.accw[(size_t)b * nsub + k] += S.histw[k];
-                    }
-                    __syncwarp();
-                } else {
-                    unsigned cnt_total = 0;
-                    double w_total = 0.0;
-                    if constexpr (SAT && !WEIGHTED)
-                        phase2_single_sat(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane, P.binpar[b].lo,
-                                          P.binpar[b].hi, cnt_total, n_recheck);
-                    else
-                        phase2_single<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane,
-                                                P.binpar[b].lo, P.binpar[b].hi, cnt_total, w_total, n_recheck);
-                    const unsigned tot = __reduce_add_sync(FULL, cnt_total);
-                    double wtot = 0.0;
-                    if (WEIGHTED) wtot = warp_sum(w_total);
-                    if (lane == 0) {
-                        S.acc[b] += tot;
-                        if (WEIGHTED) S.accw[b] += wtot;
-                    }
-                }
-                ea = eb;
-            }
-            n_tests += (unsigned long long)L * (unsigned long long)tl.count;
-            L = 0;
-            __syncwarp();
-        };
-
-        for (int cb = 0; cb < n_combo; cb += CCAP) {
-            const int nb = min(CCAP, n_combo - cb);
-            // ---- step 2: one lane per (z-bin, cell row): the run of candidate rows it covers ----
-            int running = 0;
-            for (int k0 = 0; k0 < nb; k0 += 32) {
-                const int k = k0 + lane;
-                int cnt = 0, s0 = 0, b = 0;
-                if (k < nb) {
-                    const int c = cb + k;
-                    int lo = b_lo, hi = b_hi;  // last z-bin with cstart[b] <= c
-                    while (hi - lo > 1) {
-                        const int m = (lo + hi) >> 1;
-                        if (S.cstart[m] <= c) lo = m; else hi = m;
-                    }
-                    b = lo;
-                    const int iv = S.bin_iv0[b] + (c - S.cstart[b]);
-                    const int iu = S.bin_iu[b];
-                    const long long row = G.cell_base + ((long long)b * G.gv + iv) * G.gu;
-                    s0 = P.cell_start[row + (iu & 0xffff)];
-                    cnt = P.cell_start[row + (iu >> 16) + 1] - s0;
-                }
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (k < nb) {
-                    S.rs0[k] = s0;
-                    S.rpre[k] = running + incl;
-                    S.cbin[k] = b;
-                }
-                running += __shfl_sync(FULL, incl, 31);
-            }
-            const int n_cand = running;
-            __syncwarp();
-
-            // ---- step 3: flattened gather, cull against the z-bin's box, stage as float4 ----
-            int cur = 0;
-            for (int t0 = 0; t0 < n_cand; t0 += 32) {
-                const int t = t0 + lane;
-                bool ok = t < n_cand;
-                int i = 0, b = 0;
-                float fx = 0.f, fy = 0.f, fz = 0.f, mid = 0.f;
-                if (ok) {
-                    while (t >= S.rpre[cur]) ++cur;  // runs are consumed in order; empty runs are skipped
-                    i = S.rs0[cur] + (t - (cur ? S.rpre[cur - 1] : 0));
-                    b = S.cbin[cur];
-                    fx = (float)(P.su[i] - ou);
-                    fy = (float)(P.sv[i] - ov);
-                    fz = (float)(P.st[i] - ot);
-                    const float4 rec = S.binrec[b];
-                    mid = rec.w;
-                    ok = fabsf(fx) <= rec.x && fabsf(fy) <= rec.y && fabsf(fz) <= rec.z;
-                }
-                const unsigned m = __ballot_sync(FULL, ok);
-                if (ok) {
-                    const int pos = L + __popc(m & ((1u << lane) - 1u));
-                    const float sn = fx * fx + fy * fy + fz * fz;
-                    S.list[pos] = make_float4(-2.0f * fx, -2.0f * fy, -2.0f * fz, sn - mid);
-                    S.lidx[pos] = i;
-                    S.lbin[pos] = (unsigned short)b;
-                    if (WEIGHTED) S.lw[pos] = P.sw ? P.sw[i] : 1.0;
-                }
-                L += __popc(m);
-                if (L > YAWB_LCAP - 32) consume();
-            }
-            __syncwarp();
-        }
-        if (L > 0) consume();
+        const double dx = (double)tl.cx - F.c[0], dy = (double)tl.cy - F.c[1], dz = (double)tl.cz - F.c[2];
+        const double rmax = tl.bin >= 0 ? (P.binpar[tl.bin].empty ? 0.0 : P.binpar[tl.bin].rmax) : P.rmax_all;
+        const double reach = F.radius + (double)tl.rad + rmax + 1e-9;
+        ok = rmax > 0.0 && dx * dx + dy * dy + dz * dz <= reach * reach;
     }
-    flush_pair();
-    if (lane == 0) {
-        if (n_tests) atomicAdd(&P.counters[1], n_tests);
-        if (n_live) atomicAdd(&P.counters[3], (unsigned long long)n_live);
-    }
-    const unsigned rc = __reduce_add_sync(FULL, n_recheck);
-    if (lane == 0 && rc) atomicAdd(&P.counters[2], (unsigned long long)rc);
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&P.counters[4], (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (ok) live_out[base + __popc(m & ((1u << lane) - 1u))] = make_int2(k, t0 + t);
 }
+
+#include "yawb_count_ws.cuh"
 
 // ---- exact all-pairs kernel -------------------------------------------------------------------
 struct ExactParams {
@@ -730,33 +403,72 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.out_cnt = a.d_out_cnt; P.out_w = a.d_out_w; P.counters = ctx->d_counters;
     if (a.n_items == 0) return 0;
 
+    // planner: compact list of the (patch pair, tile) items that can hold pairs
+    int2 *d_live = nullptr;
+    YAWB_CUDA(cudaMallocAsync((void **)&d_live, (size_t)a.n_items * sizeof(int2), ctx->stream));
+    P.live = d_live;
+    int max_tiles = 1;
+    for (size_t p = 0; p + 1 < a.c2->h_ptile_off.size(); ++p)
+        max_tiles = std::max(max_tiles, a.c2->h_ptile_off[p + 1] - a.c2->h_ptile_off[p]);
+    {
+        dim3 grid((unsigned)((max_tiles + 255) / 256), (unsigned)a.n_pairs);
+        k_plan<<<grid, 256, 0, ctx->stream>>>(P, d_live);
+        *launches += 1;
+    }
+
     const bool multi = a.n_edges > 2;
     const int nsub = a.n_edges - 1;
-    const size_t smem = YAWB_WARPS * warp_smem_bytes(a.weighted, multi, a.n_bins, nsub);
-    YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
-    // persistent grid: a multiple of the SM count, warps pull items from a global counter
-    const long long warps_needed = a.n_items;
-    int ctas = ctx->sms * YAWB_MIN_CTAS;
-    ctas = (int)std::min<long long>(ctas, (warps_needed + YAWB_WARPS - 1) / YAWB_WARPS);
-    ctas = std::max(ctas, 1);
-
-#define LAUNCH(W, M, T)                                                                                   \
-    do {                                                                                                  \
-        YAWB_CUDA(cudaFuncSetAttribute(k_count_fast<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                       \
-        k_count_fast<W, M, T><<<ctas, YAWB_WARPS * 32, smem, ctx->stream>>>(P);                           \
-    } while (0)
+    if (const char *dbg = getenv("YAWB_DEBUG_MODE")) P.debug = atoi(dbg);
     // unweighted single-bin counts use the 7-instruction saturating test unless YAWB_PAIR_TEST=pred
     const char *variant = getenv("YAWB_PAIR_TEST");
     const bool sat = !(variant && strcmp(variant, "pred") == 0);
-    if (a.weighted) {
-        if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
+
+    // default: unified kernel (every warp gathers for itself, then tests); YAWB_KERNEL=ws selects the
+    // warp-specialised variant (gather warps + test warps, one CTA per SM) kept for experiments
+    const size_t smem_ws = WS_CONSUMERS * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub);
+    const char *kern = getenv("YAWB_KERNEL");
+    const bool use_ws = smem_ws <= 227 * 1024 && kern && strcmp(kern, "ws") == 0;
+    if (use_ws) {
+#define LAUNCH_WS(W, M, T)                                                                              \
+    do {                                                                                                \
+        cudaFuncAttributes fa;                                                                          \
+        YAWB_CUDA(cudaFuncGetAttributes(&fa, k_count_ws<W, M, T>));                                     \
+        /* setmaxnreg.inc would wait forever if the CTA were launched with fewer registers */           \
+        YAWB_REQUIRE(fa.numRegs >= WS_REGS_LAUNCH, "k_count_ws compiled with %d registers, needs %d",   \
+                     fa.numRegs, WS_REGS_LAUNCH);                                                       \
+        YAWB_CUDA(cudaFuncSetAttribute(k_count_ws<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem_ws));                                                  \
+        k_count_ws<W, M, T><<<ctx->sms, WS_WARPS * 32, smem_ws, ctx->stream>>>(P);                      \
+    } while (0)
+        if (a.weighted) {
+            if (multi) LAUNCH_WS(true, true, false); else LAUNCH_WS(true, false, false);
+        } else {
+            if (multi) LAUNCH_WS(false, true, false);
+            else if (sat) LAUNCH_WS(false, false, true);
+            else LAUNCH_WS(false, false, false);
+        }
+#undef LAUNCH_WS
     } else {
-        if (multi) LAUNCH(false, true, false);
-        else if (sat) LAUNCH(false, false, true);
-        else LAUNCH(false, false, false);
-    }
+        const size_t smem = YAWB_WARPS * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1);
+        YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
+        // persistent grid: a multiple of the SM count, warps pull items from a global counter
+        const int ctas = ctx->sms * YAWB_MIN_CTAS;
+#define LAUNCH(W, M, T)                                                                                   \
+    do {                                                                                                  \
+        YAWB_CUDA(cudaFuncSetAttribute(k_count_uni<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                       \
+        k_count_uni<W, M, T><<<ctas, YAWB_WARPS * 32, smem, ctx->stream>>>(P);                           \
+    } while (0)
+        if (a.weighted) {
+            if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
+        } else {
+            if (multi) LAUNCH(false, true, false);
+            else if (sat) LAUNCH(false, false, true);
+            else LAUNCH(false, false, false);
+        }
 #undef LAUNCH
+    }
+    cudaFreeAsync(d_live, ctx->stream);
     YAWB_CUDA(cudaGetLastError());
     *launches += 1;
     return 0;

@@ -70,7 +70,10 @@ constexpr int YAWB_RPL = 8;               // second-role points per lane
 constexpr int YAWB_TILE = 32 * YAWB_RPL;  // points per register tile (one warp)
 constexpr int YAWB_LCAP = 256;            // candidate list capacity per warp
 constexpr int YAWB_WARPS = 4;             // warps per CTA in the count kernel
-constexpr int YAWB_MIN_CTAS = 5;          // CTAs per SM the count kernel is compiled for (register budget)
+#ifndef YAWB_MIN_CTAS_VALUE
+#define YAWB_MIN_CTAS_VALUE 5
+#endif
+constexpr int YAWB_MIN_CTAS = YAWB_MIN_CTAS_VALUE;  // CTAs per SM the count kernel is compiled for (register budget)
 constexpr int YAWB_MAX_EDGES = 256;
 
 struct yawb_ctx {
