@@ -52,15 +52,17 @@ def log(*a):
 
 
 # ---- workload ------------------------------------------------------------------------------------
-def make_workload(name: str, scale: float = 1.0):
-    """BoxRandoms catalogs + configuration + host-prepared arrays of the workload."""
+def make_workload(name: str, scale: float = 1.0, field: int = 0):
+    """BoxRandoms catalogs + configuration + host-prepared arrays of the workload.  `field` > 0 places an
+    independent realisation of the same survey 45 degrees further east (weak-scaling runs: one field per GPU)."""
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200.measurements import PatchLinkage, _angles_per_bin, prepare_catalog_arrays
     from yet_another_wizz_b200.angular import AngularBinPlan
 
     spec = WORKLOADS[name]
     nx, ny = spec["grid"]
-    ras = BOX[0] + (np.arange(nx) + 0.5) * (BOX[1] - BOX[0]) / nx
+    box = (BOX[0] + 45.0 * field, BOX[1] + 45.0 * field, BOX[2], BOX[3])
+    ras = box[0] + (np.arange(nx) + 0.5) * (box[1] - box[0]) / nx
     decs = BOX[2] + (np.arange(ny) + 0.5) * (BOX[3] - BOX[2]) / ny
     centers = yb.AngularCoordinates(np.deg2rad([[r, d] for d in decs for r in ras]))
     pool = np.random.default_rng(7).uniform(spec["zmin"], spec["zmax"], 1_000_000)
@@ -72,7 +74,7 @@ def make_workload(name: str, scale: float = 1.0):
     for key, n in zip(("ref", "unk", "ref_rand", "unk_rand"), spec["n"]):
         n = max(int(n * scale), 1000)
         has_z = key in ("ref", "ref_rand")
-        gen = yb.BoxRandoms(*BOX, redshifts=pool if has_z else None, seed=SEEDS[key])
+        gen = yb.BoxRandoms(*box, redshifts=pool if has_z else None, seed=SEEDS[key] + 100 * field)
         cats[key] = yb.Catalog.from_random(key, gen, n, patch_centers=centers)
     t_cat = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -233,7 +235,7 @@ def run_reference_arm(args):
     line = dict(
         impl="reference", metric="crosscorrelate_effective_pair_tests_per_s", value=value, unit="Gpairs/s",
         n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
-        scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+        scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
         config=dict(workload=f"{wl['name']} crosscorrelate DD+DR+RD+RR, BoxRandoms, scale={args.scale}",
                     sample=f"{last['patches']} of {wl['n_patch']} first-catalog patches with all their links "
                            f"({last['pairs']} patch pairs x 4 count types), tree build included"),
@@ -251,7 +253,7 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import _lib
-    from yet_another_wizz_b200.sharding import assign_pairs_lpt, pair_costs
+    from yet_another_wizz_b200.sharding import assign_patches_contiguous, pair_costs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,25 +266,39 @@ def run_gpu_arm(args):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
 
-    wl = make_workload(args.workload, args.scale)
+    weak = world > 1 and args.scaling == "weak"
+    wl = make_workload(args.workload, args.scale, field=rank if weak else 0)
     if rank == 0:
         log(f"[bench] workload {wl['name']} scale {args.scale}: catalogs {wl['t_catalogs']:.1f}s, "
             f"host prep {wl['t_host_prep']:.1f}s, {len(wl['pair_i'])} linked patch pairs, naive tests {wl['naive']}")
     eng = yb.Engine(local_rank)
     pi, pj, plan = wl["pair_i"], wl["pair_j"], wl["plan"]
     total_naive = sum(wl["naive"].values())
+    if weak:  # one independent field per GPU: the job is the union of the fields
+        import torch
 
-    # this rank's share: second-catalog patches are dealt out by LPT on their summed pair cost, a rank
+        t = torch.tensor([float(total_naive), float(len(pi)), -float(len(pi))], dtype=torch.float64, device="cuda")
+        tsum, tmax = t.clone(), t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        total_naive = int(tsum[0].item())
+        n_pairs_max = int(tmax[1].item())
+    else:
+        n_pairs_max = len(pi)
+
+    # this rank's share: second-catalog patches are dealt out as spatially compact groups of equal summed
+    # pair cost, a rank
     # counts every linked pair of its patches and holds only the rows it needs (its own second-catalog
     # patches, plus the first-catalog patches linked to them)
     own = np.arange(len(pi))
     arrays = wl["arrays"]
-    if world > 1:
+    if world > 1 and not weak:
         n1 = np.diff(arrays["ref_rand"]["patch_off"])
         n2 = np.diff(arrays["unk_rand"]["patch_off"])
         costs = pair_costs(pi, pj, n1, n2)
         patch_cost = np.bincount(pj, weights=costs, minlength=wl["n_patch"])
-        my_patches = assign_pairs_lpt(patch_cost, world)[rank]
+        centers_xyz = wl["cats"]["unk_rand"].get_centers().to_3d()
+        my_patches = assign_patches_contiguous(patch_cost, centers_xyz, world)[rank]
         own = np.flatnonzero(np.isin(pj, my_patches))
         need = dict(second=np.unique(pj[own]), first=np.unique(pi[own]))
         arrays = {k: subset_patches(a, need["first" if k in ("ref", "ref_rand") else "second"])
@@ -317,13 +333,15 @@ def run_gpu_arm(args):
             return results
         import torch
 
-        full = np.zeros((4, len(pi), plan.n_bins, plan.n_edges - 1), dtype=np.int64)
+        # weak: every field owns one slab of the result tensor; strong: every rank owns its patch pairs
+        slabs = world if weak else 1
+        full = np.zeros((slabs, 4, n_pairs_max, plan.n_bins, plan.n_edges - 1), dtype=np.int64)
         for t, tag in enumerate(COUNT_TYPES):
-            full[t, own] = results[tag]
+            full[rank if weak else 0, t, own] = results[tag]
         ten = torch.from_numpy(full).cuda()
         dist.reduce(ten, dst=0, op=dist.ReduceOp.SUM)  # the single NCCL reduce of the count tensors
         torch.cuda.synchronize()
-        return {tag: ten[t].cpu().numpy() for t, tag in enumerate(COUNT_TYPES)}
+        return {tag: ten[:, t].cpu().numpy() for t, tag in enumerate(COUNT_TYPES)}
 
     def count_all(dev):
         results, stats = {}, {}
@@ -393,6 +411,15 @@ def run_gpu_arm(args):
         if step >= 1:
             e2e_s.append(max_over_ranks(dt))
 
+    # statistics of the last timed step, summed over ranks
+    tot_stats = np.array([sum(s[k] for s in stats_last.values()) for k in ("pair_tests", "pair_tests_naive", "rechecks")],
+                         dtype=np.float64)
+    if dist is not None:
+        import torch
+
+        t = torch.from_numpy(tot_stats).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_stats = t.cpu().numpy()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -410,22 +437,26 @@ def run_gpu_arm(args):
     peak_tests = sms * 128 * sm_max_mhz * 1e6 / FP32_INSTR_PER_TEST
     t_step = float(np.mean(step_ms)) / 1e3
     t_kernel = float(np.mean(kernel_ms)) / 1e3
-    executed = sum(s["pair_tests"] for s in stats_last.values())
-    achieved = executed / max(t_kernel, 1e-12)
+    executed = float(tot_stats[0])
+    achieved = executed / max(t_kernel, 1e-12) / world  # per GPU: rank 0's kernel time, 1/world of the tests
     in_scale = {tag: int(results[tag].sum()) for tag in COUNT_TYPES}
     clk = clocks.summary()
 
     line = dict(
         metric="crosscorrelate_effective_pair_tests_per_s", value=total_naive / t_step / 1e9, unit="Gpairs/s",
         n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=t_step * 1e3, higher_is_better=True,
-        scaling="strong", vs_baseline=None, dtype="f32+f64", data="synthetic",
+        scaling="weak" if (weak or world == 1) else "strong", vs_baseline=None, dtype="f32+f64", data="synthetic",
         config=dict(
             workload=f"{wl['name']} crosscorrelate DD+DR+RD+RR: {wl['spec']['n']} rows x scale {args.scale}, "
-                     f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, 100-1000 kpc, BoxRandoms {BOX}",
+                     f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, 100-1000 kpc, BoxRandoms {BOX}"
+                     + (f"; x {world} independent fields (sky area and rows grow with the GPU count, one field per GPU)"
+                        if weak else ""),
             linked_patch_pairs=int(len(pi)), naive_pair_tests=wl["naive"], pairs_in_scale=in_scale,
             l2="inputs (>= 1 GB of catalog rows) exceed the 126 MB L2; every step rebuilds the index from the raw rows",
-            parallelism=f"second-catalog patches dealt to {world} GPU(s) by LPT, each rank holds only the rows of its "
-                        f"patches and of the first-catalog patches linked to them, one NCCL reduce of the counts",
+            parallelism=(f"{world} fields of {wl['n_patch']} patches, one per GPU (no patch links between fields), one NCCL "
+                         f"reduce of the count tensor" if weak else
+                         f"second-catalog patches dealt to {world} GPU(s) as compact equal-cost groups, each rank holds only "
+                         f"the rows of its patches and of the first-catalog patches linked to them, one NCCL reduce of the counts"),
         ),
         breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=t_kernel * 1e3,
                           per_count={tag: stats_last[tag]["kernel_ms"] for tag in COUNT_TYPES},
@@ -435,10 +466,9 @@ def run_gpu_arm(args):
             frac=achieved / peak_tests, traffic=None,
             note=f"pair-count kernels of rank 0; executed (non-pruned) tests / kernel time vs {sms} SMs x 128 lanes x "
                  f"{sm_max_mhz:.0f} MHz / {FP32_INSTR_PER_TEST} FP32 instr per test (MEASURED_PEAKS.json sm_max_mhz)",
-            executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(sum(
-                s["pair_tests_naive"] for s in stats_last.values()), 1),
+            executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(float(tot_stats[1]), 1.0),
             useful_fraction=sum(in_scale.values()) / max(executed, 1),
-            fp64_rechecks=int(sum(s["rechecks"] for s in stats_last.values())),
+            fp64_rechecks=int(tot_stats[2]),
         ),
         e2e=dict(value=total_naive / float(np.mean(e2e_s)) / 1e9, unit="Gpairs/s", ms_per_step=float(np.mean(e2e_s)) * 1e3,
                  h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
@@ -470,6 +500,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every catalog (development only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one C3-sized field per GPU (default), strong = the one field split over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,160 @@
+"""
+GPU parity at the BASELINE.json configurations (scaled where the FP64 all-pairs cross-check would take
+minutes): the production kernel (sky-cell pruning, FP32 test, FP64 recheck) against the unpruned FP64
+kernel through the public API.  Integer counts bit-exact, weighted sums rtol 1e-12.
+
+Size-independent properties checked alongside: DD == DR when the random catalog is the data catalog,
+auto counts are symmetric-consistent (pairs counted once), sums of weights equal plain numpy sums.
+"""
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+pytestmark = pytest.mark.gpu
+
+BOX = (0.0, 40.0, -12.5, 12.5)
+
+
+class ExactEngine:
+    """routes every count through the FP64 all-pairs kernel (validation flag of the C ABI)"""
+
+    def __init__(self, engine):
+        self._e = engine
+
+    def upload_catalog(self, *a, **k):
+        return self._e.upload_catalog(*a, **k)
+
+    def count(self, c1, c2, pi, pj, r2, **k):
+        return self._e.count(c1, c2, pi, pj, r2, exact=True)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from yet_another_wizz_b200 import Engine
+
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def grid_centers(nx, ny, box=BOX):
+    import yet_another_wizz_b200 as yb
+
+    ras = box[0] + (np.arange(nx) + 0.5) * (box[1] - box[0]) / nx
+    decs = box[2] + (np.arange(ny) + 0.5) * (box[3] - box[2]) / ny
+    return yb.AngularCoordinates(np.deg2rad([[r, d] for d in decs for r in ras]))
+
+
+def make(name, n, centers, *, zpool=None, wpool=None, seed=1, box=BOX):
+    import yet_another_wizz_b200 as yb
+
+    gen = yb.BoxRandoms(*box, redshifts=zpool, weights=wpool, seed=seed)
+    return yb.Catalog.from_random(name, gen, n, patch_centers=centers)
+
+
+def compare(fast, exact, kinds, exact_ints):
+    for cf, ce in zip(fast, exact):
+        for kind in kinds:
+            a, b = getattr(cf, kind), getattr(ce, kind)
+            if exact_ints:
+                assert_array_equal(a.counts.counts, b.counts.counts)
+            else:
+                assert_allclose(a.counts.counts, b.counts.counts, rtol=1e-12, atol=0)
+            assert b.counts.counts.sum() > 0
+            assert_allclose(a.sum_weights.sum_weights1, b.sum_weights.sum_weights1, rtol=1e-13)
+            assert_allclose(a.sum_weights.sum_weights2, b.sum_weights.sum_weights2, rtol=1e-13)
+
+
+def test_c1_full_size_crosscorrelate(engine):
+    """configs[0]: 1e5 ref x 1e5 unknown + 1e6 randoms per side, 16 patches, 100-1000 kpc, 10 z-bins"""
+    import yet_another_wizz_b200 as yb
+
+    centers = grid_centers(4, 4)
+    pool = np.random.default_rng(7).uniform(0.1, 1.0, 1_000_000)
+    ref = make("ref", 100_000, centers, zpool=pool, seed=1)
+    unk = make("unk", 100_000, centers, seed=2)
+    ref_rand = make("ref_rand", 1_000_000, centers, zpool=pool, seed=3)
+    unk_rand = make("unk_rand", 1_000_000, centers, seed=4)
+    config = yb.Configuration.create(rmin=100, rmax=1000, zmin=0.1, zmax=1.0, num_bins=10)
+    fast = yb.crosscorrelate(config, ref, unk, ref_rand=ref_rand, unk_rand=unk_rand, engine=engine)
+    exact = yb.crosscorrelate(config, ref, unk, ref_rand=ref_rand, unk_rand=unk_rand, engine=ExactEngine(engine))
+    compare(fast, exact, ("dd", "dr", "rd", "rr"), exact_ints=True)
+    # totals of SURVEY.md section 6 (reference probe of the same seeds): DD 9.65e4, RR 9.64e6
+    assert abs(fast[0].dd.counts.counts.sum() / 9.65e4 - 1) < 0.01
+    assert abs(fast[0].rr.counts.counts.sum() / 9.64e6 - 1) < 0.01
+    # sums of weights = row counts inside the binning
+    z = np.concatenate([ref[p].load_data()["redshifts"] for p in ref])
+    assert fast[0].dd.sum_weights.sum_weights1.sum() == ((z > 0.1) & (z <= 1.0)).sum()
+    assert fast[0].dd.sum_weights.sum_weights2.sum() == 10 * 100_000
+
+
+def test_c2_like_autocorrelate_rweight(engine):
+    """configs[1] scaled: autocorrelate with rweight=-1 and resolution=50 log sub-bins, 32 patches"""
+    import yet_another_wizz_b200 as yb
+
+    box = (0.0, 16.0, -4.0, 4.0)
+    centers = grid_centers(8, 4, box)
+    pool = np.random.default_rng(7).uniform(0.1, 1.0, 100_000)
+    wpool = np.random.default_rng(8).uniform(0.5, 1.5, 100_000)
+    data = make("data", 150_000, centers, zpool=pool, wpool=wpool, seed=1, box=box)
+    rand = make("rand", 150_000, centers, zpool=pool, seed=3, box=box)
+    config = yb.Configuration.create(rmin=100, rmax=1000, rweight=-1.0, resolution=50, zmin=0.1, zmax=1.0, num_bins=10)
+    fast = yb.autocorrelate(config, data, rand, engine=engine)
+    exact = yb.autocorrelate(config, data, rand, engine=ExactEngine(engine))
+    compare(fast, exact, ("dd", "dr", "rr"), exact_ints=False)
+    # RR is unweighted: r-weighted sums of integers must agree far below the 1e-12 bar
+    assert_allclose(fast[0].rr.counts.counts, exact[0].rr.counts.counts, rtol=1e-14, atol=0)
+    # auto counts: only the upper triangle is filled
+    assert np.all(np.tril(fast[0].dd.counts.counts.sum(axis=0), -1) == 0)
+
+
+def test_c4_like_multiscale_crosscorrelate(engine):
+    """configs[3] scaled: three (rmin, rmax) scale pairs counted in one pass, 30 z-bins"""
+    import yet_another_wizz_b200 as yb
+
+    box = (0.0, 10.0, -5.0, 5.0)
+    centers = grid_centers(4, 4, box)
+    pool = np.random.default_rng(7).uniform(0.07, 1.42, 100_000)
+    ref = make("ref", 60_000, centers, zpool=pool, seed=1, box=box)
+    unk = make("unk", 400_000, centers, seed=2, box=box)
+    config = yb.Configuration.create(rmin=[100, 300, 500], rmax=[1000, 1500, 2000], zmin=0.07, zmax=1.42, num_bins=30)
+    fast = yb.crosscorrelate(config, ref, unk, unk_rand=unk.__class__(dict(unk.items()), "unk_copy"), engine=engine)
+    exact = yb.crosscorrelate(config, ref, unk, unk_rand=unk.__class__(dict(unk.items()), "unk_copy"),
+                              engine=ExactEngine(engine))
+    assert len(fast) == 3
+    compare(fast, exact, ("dd", "dr"), exact_ints=True)
+    for cf in fast:  # the "random" catalog is the data catalog: DR must equal DD exactly
+        assert_array_equal(cf.dd.counts.counts, cf.dr.counts.counts)
+    # nested scales: 100-1000 kpc counts < 300-1500 < 500-2000 for a uniform field
+    sums = [cf.dd.counts.counts.sum() for cf in fast]
+    assert sums[0] < sums[1] < sums[2]
+
+
+def test_many_bins_and_empty_patches(engine):
+    """50 z-bins (configs[4] binning), patches with no rows and z-bins with no rows"""
+    import yet_another_wizz_b200 as yb
+
+    box = (0.0, 6.0, -3.0, 3.0)
+    centers = grid_centers(3, 3, box)
+    rng = np.random.default_rng(5)
+    n1, n2 = 40_000, 120_000
+    ra1 = rng.uniform(0.0, 4.0, n1)  # right third of the box stays empty in catalog 1
+    dec1 = np.rad2deg(np.arcsin(rng.uniform(np.sin(np.deg2rad(-3)), np.sin(np.deg2rad(3)), n1)))
+    z1 = rng.uniform(0.1, 0.6, n1)   # upper z-bins stay empty
+    ra2 = rng.uniform(0.0, 6.0, n2)
+    dec2 = np.rad2deg(np.arcsin(rng.uniform(np.sin(np.deg2rad(-3)), np.sin(np.deg2rad(3)), n2)))
+    # keep the patch count consistent: a handful of far-right points so every patch id exists
+    ra1[:9] = np.rad2deg(centers.ra)
+    dec1[:9] = np.rad2deg(centers.dec)
+    ref = yb.Catalog.from_arrays(ra1, dec1, patch_centers=centers, redshifts=z1)
+    unk = yb.Catalog.from_arrays(ra2, dec2, patch_centers=centers)
+    config = yb.Configuration.create(rmin=100, rmax=1000, zmin=0.07, zmax=1.42, num_bins=50)
+    kw = dict(unk_rand=yb.Catalog.from_arrays(ra2, dec2, patch_centers=centers))
+    try:
+        fast = yb.crosscorrelate(config, ref, unk, engine=engine, **kw)
+    except yb.InconsistentPatchesError:
+        pytest.skip("sparse patch centres drifted too far for the reference's consistency check")
+    exact = yb.crosscorrelate(config, ref, unk, engine=ExactEngine(engine), **kw)
+    compare(fast, exact, ("dd", "dr"), exact_ints=True)
+    assert fast[0].dd.counts.counts[30:].sum() == 0  # bins above z = 0.6 hold nothing

@@ -60,3 +60,24 @@ def test_two_rank_gloo_reduce_matches_golden(tmp_path):
     got = np.load(tmp_path / "rank0.npz")
     for kind in ("dd", "dr", "rd", "rr"):
         np.testing.assert_array_equal(got[kind], g[f"cross_{kind}_counts_s0"])
+
+
+def test_contiguous_patch_groups():
+    from yet_another_wizz_b200.sharding import assign_patches_contiguous
+
+    # 8 x 8 grid of patch centres on the equator, equal cost: groups are compact and balanced
+    ras, decs = np.meshgrid(np.deg2rad(np.arange(8) * 5.0 + 2.5), np.deg2rad(np.arange(8) * 3.0 - 10.5))
+    xyz = np.column_stack([np.cos(ras.ravel()) * np.cos(decs.ravel()), np.sin(ras.ravel()) * np.cos(decs.ravel()),
+                           np.sin(decs.ravel())])
+    for world in (1, 2, 4, 8):
+        groups = assign_patches_contiguous(np.ones(64), xyz, world)
+        assert sorted(np.concatenate(groups).tolist()) == list(range(64))
+        assert all(len(g) == 64 // world for g in groups)
+        for g in groups:  # compact: bounding box of a group covers at most twice its share of the grid
+            cols, rows = g % 8, g // 8
+            assert (np.ptp(cols) + 1) * (np.ptp(rows) + 1) <= 2 * len(g)
+    # unequal costs: loads within one patch of the mean
+    costs = np.random.default_rng(1).uniform(1, 3, 64)
+    groups = assign_patches_contiguous(costs, xyz, 4)
+    loads = np.array([costs[g].sum() for g in groups])
+    assert loads.max() - loads.min() <= 2 * costs.max()

@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Shard", "assign_pairs_lpt", "current_shard", "pair_costs"]
+__all__ = ["Shard", "assign_pairs_lpt", "assign_patches_contiguous", "current_shard", "pair_costs"]
 
 
 def pair_costs(pair_i, pair_j, n1_per_patch, n2_per_patch, centers_dist=None, reach=None) -> np.ndarray:
@@ -43,6 +43,36 @@ def assign_pairs_lpt(costs: np.ndarray, world_size: int) -> list[np.ndarray]:
         owned[r].append(int(k))
         heapq.heappush(heap, (load + float(costs[k]), r))
     return [np.array(sorted(o), dtype=np.int64) for o in owned]
+
+
+def assign_patches_contiguous(patch_costs: np.ndarray, centers_xyz: np.ndarray, world_size: int) -> list[np.ndarray]:
+    """Deal patches to ranks as spatially compact groups of about equal cost: patches are ordered along a
+    Morton curve of their centres (longitude, z) and the order is cut where the running cost crosses
+    k / world_size of the total.  A rank then needs few first-catalog patches beyond its own (only the
+    neighbours across the cut), which keeps per-rank uploads and index builds ~1/world_size."""
+    patch_costs = np.asarray(patch_costs, dtype=np.float64)
+    xyz = np.asarray(centers_xyz, dtype=np.float64)
+    lon = np.arctan2(xyz[:, 1], xyz[:, 0])
+    # unwrap around the mean direction so a field that straddles RA = 0 stays contiguous
+    mean_lon = np.arctan2(xyz[:, 1].sum(), xyz[:, 0].sum())
+    lon = (lon - mean_lon + np.pi) % (2 * np.pi)
+    def quant(v):
+        span = v.max() - v.min()
+        return np.zeros(len(v), dtype=np.uint64) if span <= 0 else ((v - v.min()) / span * 1023).astype(np.uint64)
+    qx, qy = quant(lon), quant(xyz[:, 2])
+    code = np.zeros(len(xyz), dtype=np.uint64)
+    for bit in range(10):
+        code |= ((qx >> np.uint64(bit)) & np.uint64(1)) << np.uint64(2 * bit)
+        code |= ((qy >> np.uint64(bit)) & np.uint64(1)) << np.uint64(2 * bit + 1)
+    order = np.argsort(code, kind="stable")
+    csum = np.cumsum(patch_costs[order])
+    total = csum[-1] if len(csum) else 0.0
+    bounds = [0]
+    for r in range(1, world_size):
+        bounds.append(min(len(order), int(np.searchsorted(csum, total * r / world_size * (1 - 1e-12), side="left")) + 1))
+    bounds.append(len(order))
+    bounds = np.maximum.accumulate(bounds)
+    return [np.sort(order[bounds[r]:bounds[r + 1]]) for r in range(world_size)]
 
 
 class Shard:
