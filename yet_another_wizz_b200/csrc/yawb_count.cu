@@ -88,13 +88,21 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// One staged candidate: (-2x, -2y, -2z, |s|^2 - mid), every component duplicated so that it can be
+// used directly as the broadcast operand of the packed f32x2 instructions (FFMA2 / FADD2).
+struct __align__(16) Cand {
+    float4 a;  // (-2x, -2x, -2y, -2y)
+    float4 b;  // (-2z, -2z, |s|^2 - mid, |s|^2 - mid)
+};
+constexpr int HPL = YAWB_RPL / 2;  // row pairs per lane
+
 // ---- per-warp shared memory -------------------------------------------------------------------
 constexpr int CCAP = 128;  // (z-bin, cell-row) combinations resolved per batch
 constexpr int GRAB = 4;    // work items taken per atomic
 
 template <bool WEIGHTED>
 struct WarpSmem {
-    float4 *list;             // [LCAP] staged candidates (-2x, -2y, -2z, |s|^2 - mid)
+    Cand *list;               // [LCAP] staged candidates
     double *lw;               // [LCAP] their weights (WEIGHTED)
     unsigned long long *acc;  // [n_bins * nsub] pair counts of the current patch pair
     double *accw;             // same, weighted sums (WEIGHTED)
@@ -143,32 +151,40 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
 // One candidate against the lane's YAWB_RPL rows:  u = (rn + s.w) + rx s.x + ry s.y + rz s.z = d2 - mid.
 //   predicated: |u| < h - eps, |u| < h + eps (2 FSETP) + 2 predicated FADD, also feeds the weighted sums;
 //   SAT: v = sat(C - K |u|) is a ramp through the uncertainty band: exactly 1 well inside the bin,
-//        exactly 0 well outside, in [0.375, 0.625] wherever FP32 cannot decide (K = 1 / (8 eps),
+//        exactly 0 well outside, in [0.1, 0.9] wherever FP32 cannot decide (K = 0.4 / eps,
 //        C = 1/2 + h K).  sum(v) and sum(v*v) are equal iff every v of the chunk was 0 or 1 (then
-//        sum(v) is the exact count); an undecidable test makes them differ by >= 0.23.
+//        sum(v) is the exact count); an undecidable test makes them differ by >= 0.09.
 // Two accumulator pairs (even / odd rows) halve the length of the dependent add chains.
 template <bool WEIGHTED, bool SAT>
-__device__ __forceinline__ void test_candidate(const float4 s, double swt, const float (&rx)[YAWB_RPL],
-                                               const float (&ry)[YAWB_RPL], const float (&rz)[YAWB_RPL],
-                                               const float (&rn)[YAWB_RPL], float ta, float tb,
-                                               float (&acc_a)[2], float (&acc_b)[2], double (&ws)[YAWB_RPL]) {
+__device__ __forceinline__ void test_candidate(const Cand c, double swt, const float2 (&rx)[HPL],
+                                               const float2 (&ry)[HPL], const float2 (&rz)[HPL],
+                                               const float2 (&rn)[HPL], float ta, float tb, float2 &acc_a,
+                                               float2 &acc_b, double (&ws)[YAWB_RPL]) {
+    // Blackwell packed FP32: one FFMA2 / FADD2 carries two pair tests (rows 2k and 2k+1 of the lane)
+    const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
+    const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
 #pragma unroll
-    for (int r = 0; r < YAWB_RPL; ++r) {
-        float u = rn[r] + s.w;
-        u = fmaf(rx[r], s.x, u);
-        u = fmaf(ry[r], s.y, u);
-        u = fmaf(rz[r], s.z, u);
+    for (int k = 0; k < HPL; ++k) {
+        float2 u = __fadd2_rn(rn[k], sw);
+        u = __ffma2_rn(rx[k], sx, u);
+        u = __ffma2_rn(ry[k], sy, u);
+        u = __ffma2_rn(rz[k], sz, u);
         if (SAT) {
-            const float v = __saturatef(fmaf(fabsf(u), ta, tb));  // ta = -K, tb = C
-            acc_a[r & 1] += v;
-            acc_b[r & 1] = fmaf(v, v, acc_b[r & 1]);
+            float2 v;
+            v.x = __saturatef(fmaf(fabsf(u.x), ta, tb));  // ta = -K, tb = C
+            v.y = __saturatef(fmaf(fabsf(u.y), ta, tb));
+            acc_a = __fadd2_rn(acc_a, v);
+            acc_b = __ffma2_rn(v, v, acc_b);
         } else {
-            const float au = fabsf(u);
-            const bool in = au < ta;  // ta = h - eps, tb = h + eps
-            if (in) acc_a[r & 1] += 1.f;
-            if (au < tb) acc_b[r & 1] += 1.f;
+            const float a0 = fabsf(u.x), a1 = fabsf(u.y);
+            const bool in0 = a0 < ta, in1 = a1 < ta;  // ta = h - eps, tb = h + eps
+            if (in0) acc_a.x += 1.f;
+            if (in1) acc_a.y += 1.f;
+            if (a0 < tb) acc_b.x += 1.f;
+            if (a1 < tb) acc_b.y += 1.f;
             if (WEIGHTED) {
-                if (in) ws[r] += swt;
+                if (in0) ws[2 * k] += swt;
+                if (in1) ws[2 * k + 1] += swt;
             }
         }
     }
@@ -177,14 +193,14 @@ __device__ __forceinline__ void test_candidate(const float4 s, double swt, const
 // entries [ea, eb) of the list belong to one z-bin
 template <bool WEIGHTED, bool SAT>
 __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
-                                              const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
-                                              const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
+                                              const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                              const float2 (&rz)[HPL], const float2 (&rn)[HPL],
                                               float ta, float tb, const Tile &tl, int lane, double lo,
                                               double hi, unsigned &cnt_total, double &w_total,
                                               unsigned &n_recheck) {
     for (int e0 = ea; e0 < eb; e0 += CHUNK) {
         const int e1 = min(e0 + CHUNK, eb);
-        float acc_a[2] = {0.f, 0.f}, acc_b[2] = {0.f, 0.f};
+        float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
         double ws[YAWB_RPL];
         if (WEIGHTED) {
 #pragma unroll
@@ -200,7 +216,7 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
                 test_candidate<WEIGHTED, SAT>(S.list[e], WEIGHTED ? S.lw[e] : 0.0, rx, ry, rz, rn, ta, tb, acc_a,
                                               acc_b, ws);
         }
-        const float sa = acc_a[0] + acc_a[1], sb = acc_b[0] + acc_b[1];
+        const float sa = acc_a.x + acc_a.y, sb = acc_b.x + acc_b.y;
         unsigned c = (unsigned)(sa + 0.5f);
         double wsum = 0.0;
         if (WEIGHTED) {
@@ -230,21 +246,24 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
 template <bool WEIGHTED>
 __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
-                                             const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
-                                             const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
+                                             const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL],
                                              float h_out, float eps, float mid, const Tile &tl, int lane, int b,
                                              unsigned &n_recheck) {
     const int ne = P.n_edges;
     const float *ef = P.r2f + (size_t)b * ne;
     const double *ed = P.r2 + (size_t)b * ne;
     for (int e = ea; e < eb; ++e) {
-        const float4 s = S.list[e];
+        const Cand c = S.list[e];
+        const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
+        const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
-            float u = rn[r] + s.w;
-            u = fmaf(rx[r], s.x, u);
-            u = fmaf(ry[r], s.y, u);
-            u = fmaf(rz[r], s.z, u);
+            float2 u2 = __fadd2_rn(rn[r >> 1], sw);
+            u2 = __ffma2_rn(rx[r >> 1], sx, u2);
+            u2 = __ffma2_rn(ry[r >> 1], sy, u2);
+            u2 = __ffma2_rn(rz[r >> 1], sz, u2);
+            const float u = (r & 1) ? u2.y : u2.x;  // the compiler merges the two halves of a row pair
             if (fabsf(u) < h_out) {  // possibly inside [lo, hi]
                 const float d2f = u + mid;
                 int lo = 0, hi = ne;  // edges strictly below d2f (float copy of the edges)

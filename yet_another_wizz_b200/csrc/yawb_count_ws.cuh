@@ -52,11 +52,11 @@ struct __align__(16) ChanCtl {
 template <bool WEIGHTED>
 struct Channel {
     ChanCtl *ctl;
-    float4 *list0;            // two buffers of WS_LB entries each, addressed arithmetically (no
+    Cand *list0;              // two buffers of WS_LB entries each, addressed arithmetically (no
     double *lw0;              // runtime-indexed pointer arrays: those would live in local memory)
     int *lidx0;
     unsigned short *lbin0;
-    __device__ __forceinline__ float4 *list(int buf) const { return list0 + buf * WS_LB; }
+    __device__ __forceinline__ Cand *list(int buf) const { return list0 + buf * WS_LB; }
     __device__ __forceinline__ double *lw(int buf) const { return lw0 ? lw0 + buf * WS_LB : nullptr; }
     __device__ __forceinline__ int *lidx(int buf) const { return lidx0 + buf * WS_LB; }
     __device__ __forceinline__ unsigned short *lbin(int buf) const { return lbin0 + buf * WS_LB; }
@@ -71,7 +71,7 @@ struct Channel {
 
 __host__ __device__ inline size_t ws_chan_bytes(bool weighted, bool multi, int n_bins, int nsub, int nbuf = 2) {
     size_t b = sizeof(ChanCtl);
-    b += (size_t)nbuf * WS_LB * sizeof(float4) + (size_t)n_bins * sizeof(float4);
+    b += (size_t)nbuf * WS_LB * sizeof(Cand) + (size_t)n_bins * sizeof(float4);
     if (weighted) b += (size_t)nbuf * WS_LB * sizeof(double);
     b += (size_t)n_bins * nsub * sizeof(unsigned long long);
     if (weighted) b += (size_t)n_bins * nsub * sizeof(double);
@@ -89,7 +89,7 @@ __device__ __forceinline__ void ws_carve(Channel<WEIGHTED> &C, unsigned char *p,
                                          int nbuf = 2) {
     const size_t nacc = (size_t)n_bins * nsub;
     C.ctl = (ChanCtl *)p; p += sizeof(ChanCtl);
-    C.list0 = (float4 *)p; p += (size_t)nbuf * WS_LB * sizeof(float4);
+    C.list0 = (Cand *)p; p += (size_t)nbuf * WS_LB * sizeof(Cand);
     C.binrec = (float4 *)p; p += (size_t)n_bins * sizeof(float4);
     C.lw0 = nullptr; C.accw = nullptr; C.histw = nullptr; C.hist = nullptr;
     if (WEIGHTED) { C.lw0 = (double *)p; p += (size_t)nbuf * WS_LB * sizeof(double); }
@@ -141,12 +141,14 @@ __device__ __forceinline__ void ws_begin_item(const FastParams &P, const Channel
                 const float hx = (float)(eu + bp.rmax) * 1.000001f, hy = (float)(ev + bp.rmax) * 1.000001f,
                             hz = (float)(et + bp.rmax) * 1.000001f;
                 const float m2 = hx * hx + hy * hy + hz * hz;
-                const float eps = 64.0f * EPS32 * (m2 + bp.mid) * 1.0001f;
+                // |u_fp32 - (d2_ref - mid)| <= 29 eps32 M^2 + 7 eps32 mid (coordinate rounding 8, |r|^2 3,
+                // |s|^2 - mid 4 + 1, first add 2 + 1, three FMAs 12 + 3, mid/h rounding 2)
+                const float eps = EPS32 * (32.0f * m2 + 8.0f * bp.mid) * 1.0001f;
                 C.binrec[b] = make_float4(hx, hy, hz, bp.mid);
                 if (MULTI) {
                     C.binthr[b] = make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi);
                 } else if (SAT) {
-                    const float K = 1.0f / (8.0f * eps);
+                    const float K = 0.4f / eps;  // undecidable tests land in v = [0.1, 0.9]: v (1 - v) >= 0.09
                     C.binthr[b] = make_float2(-K, 0.5f + bp.h * K);
                 } else {
                     C.binthr[b] = make_float2(bp.h - eps, bp.h + eps);
@@ -183,7 +185,7 @@ __device__ __forceinline__ int ws_fill(const FastParams &P, const Channel<WEIGHT
     int cb = ctl.st_cb, n_cand = ctl.st_ncand, t0 = ctl.st_t0;
     bool have_batch = ctl.st_have != 0;
     const int n_combo = ctl.st_ncombo;
-    float4 *list = C.list(buf);
+    Cand *list = C.list(buf);
     int *lidx = C.lidx(buf);
     unsigned short *lbin = C.lbin(buf);
     double *lwb = C.lw(buf);
@@ -295,7 +297,9 @@ __device__ __forceinline__ int ws_fill(const FastParams &P, const Channel<WEIGHT
             if (ok) {
                 const int pos = L + __popc(m & ((1u << lane) - 1u));
                 const float sn = fx * fx + fy * fy + fz * fz;
-                list[pos] = make_float4(-2.0f * fx, -2.0f * fy, -2.0f * fz, sn - mid);
+                const float ax = -2.0f * fx, ay = -2.0f * fy, az = -2.0f * fz, aw = sn - mid;
+                list[pos].a = make_float4(ax, ax, ay, ay);
+                list[pos].b = make_float4(az, az, aw, aw);
                 lidx[pos] = ci[h];
                 lbin[pos] = (unsigned short)cbn[h];
                 if (WEIGHTED) lwb[pos] = P.sw ? P.sw[ci[h]] : 1.0;
@@ -317,8 +321,8 @@ __device__ __forceinline__ int ws_fill(const FastParams &P, const Channel<WEIGHT
 // ---- run the pair tests on one staged list: one pass of phase 2 per z-bin segment ---------------------
 template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WEIGHTED> &C, int buf, int L,
-                                           const float (&rx)[YAWB_RPL], const float (&ry)[YAWB_RPL],
-                                           const float (&rz)[YAWB_RPL], const float (&rn)[YAWB_RPL],
+                                           const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                           const float2 (&rz)[HPL], const float2 (&rn)[HPL],
                                            const Tile &tl, int lane, int nsub, unsigned &n_recheck) {
     WarpSmem<WEIGHTED> S;  // view of the current buffer for the shared phase-2 code
     S.list = C.list(buf); S.lw = C.lw(buf); S.lidx = C.lidx(buf); S.lbin = C.lbin(buf);
@@ -530,21 +534,21 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 1) k_count_ws(const FastParams 
             __threadfence_block();
             st_flag(&ctl.seq, ++seq);
         }
-        float rx[YAWB_RPL], ry[YAWB_RPL], rz[YAWB_RPL], rn[YAWB_RPL];
+        float2 rx[HPL], ry[HPL], rz[HPL], rn[HPL];  // rows (2k, 2k+1) of the lane share one register pair
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
             const int k = lane + 32 * r;
+            float x = FAR, y = FAR, z = FAR, n = 3.0f * FAR * FAR;  // padding rows are never in range
             if (k < tl.count) {
                 const int j = tl.start + k;
                 const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                rx[r] = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
-                ry[r] = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
-                rz[r] = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
-                rn[r] = rx[r] * rx[r] + ry[r] * ry[r] + rz[r] * rz[r];
-            } else {
-                rx[r] = FAR; ry[r] = FAR; rz[r] = FAR;
-                rn[r] = 3.0f * FAR * FAR;
+                x = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
+                y = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
+                z = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
+                n = x * x + y * y + z * z;
             }
+            if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; rn[r >> 1].y = n; }
+            else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; rn[r >> 1].x = n; }
         }
 
         // ---- consume the lists of this item ----
@@ -670,21 +674,21 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_uni(co
             ctl.b_hi = tl.bin >= 0 ? tl.bin + 1 : P.n_bins;
         }
         __syncwarp();
-        float rx[YAWB_RPL], ry[YAWB_RPL], rz[YAWB_RPL], rn[YAWB_RPL];
+        float2 rx[HPL], ry[HPL], rz[HPL], rn[HPL];  // rows (2k, 2k+1) of the lane share one register pair
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
             const int k = lane + 32 * r;
+            float x = FAR, y = FAR, z = FAR, n = 3.0f * FAR * FAR;  // padding rows are never in range
             if (k < tl.count) {
                 const int j = tl.start + k;
                 const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                rx[r] = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
-                ry[r] = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
-                rz[r] = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
-                rn[r] = rx[r] * rx[r] + ry[r] * ry[r] + rz[r] * rz[r];
-            } else {
-                rx[r] = FAR; ry[r] = FAR; rz[r] = FAR;
-                rn[r] = 3.0f * FAR * FAR;
+                x = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
+                y = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
+                z = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
+                n = x * x + y * y + z * z;
             }
+            if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; rn[r >> 1].y = n; }
+            else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; rn[r >> 1].x = n; }
         }
         ws_begin_item<WEIGHTED, MULTI, SAT>(P, C, lane);
         bool done = false;
