@@ -14,7 +14,7 @@ import sys
 
 
 def disasm_lines(path, kernel):
-    out, cur_line, active = [], 0, False
+    out, cur_line, active = [], ("?", 0), False
     for raw in open(path):
         if raw.startswith("//---") and ".text." in raw:
             active = kernel in raw
@@ -23,7 +23,7 @@ def disasm_lines(path, kernel):
             continue
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', raw)
         if m:
-            cur_line = int(m.group(2)) if m.group(1).endswith("yawb_count.cu") else -int(m.group(2))
+            cur_line = (m.group(1), int(m.group(2)))
             continue
         if re.match(r"\s*/\*[0-9a-f]{4,}\*/", raw):
             out.append((cur_line, raw.split("*/", 1)[1].strip().rstrip(";").strip()))
@@ -50,12 +50,19 @@ def main():
         inst[line] += int(r[ix["Instructions Executed"]])
         samp[line] += int(r[ix["# Samples"]])
     ti, ts = sum(inst.values()), sum(samp.values())
-    src = open("/root/repo/yet_another_wizz_b200/csrc/yawb_count.cu").read().split("\n")
     print(f"total warp instructions {ti:.3e}, samples {ts}")
-    print("   line   inst%  samp%  source")
-    for line, c in samp.most_common(top):
-        text = src[line - 1].strip()[:100] if 0 < line <= len(src) else "<other file>"
-        print(f"{line:7d} {inst[line] / ti * 100:6.2f} {c / ts * 100:6.2f}  {text}")
+    print("file:line   inst%  samp%  source")
+    cache = {}
+    for (fname, line), c in samp.most_common(top):
+        if fname not in cache:
+            try:
+                cache[fname] = open(fname).read().split("\n")
+            except OSError:
+                cache[fname] = []
+        src = cache[fname]
+        text = src[line - 1].strip()[:90] if 0 < line <= len(src) else ""
+        short = fname.split("/")[-1][:18]
+        print(f"{short:>18s}:{line:<5d} {inst[(fname, line)] / ti * 100:6.2f} {c / ts * 100:6.2f}  {text}")
 
 
 if __name__ == "__main__":

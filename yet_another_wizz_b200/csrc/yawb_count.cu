@@ -29,7 +29,10 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float EPS32 = 5.9604645e-8f;  // 2^-24
-constexpr int CHUNK = 8;                // candidates between consistency checks
+#ifndef YAWB_CHUNK
+#define YAWB_CHUNK 8
+#endif
+constexpr int CHUNK = YAWB_CHUNK;       // candidates between consistency checks (power of two)
 constexpr float FAR = 1.0e15f;          // coordinates of padding points (never in range)
 
 struct FastParams {
@@ -98,7 +101,10 @@ constexpr int HPL = YAWB_RPL / 2;  // row pairs per lane
 
 // ---- per-warp shared memory -------------------------------------------------------------------
 constexpr int CCAP = 128;  // (z-bin, cell-row) combinations resolved per batch
-constexpr int GRAB = 4;    // work items taken per atomic
+#ifndef YAWB_GRAB
+#define YAWB_GRAB 1
+#endif
+constexpr int GRAB = YAWB_GRAB;  // work items taken per atomic
 
 template <bool WEIGHTED>
 struct WarpSmem {

@@ -20,7 +20,10 @@ constexpr int WS_PRODUCERS = 8;      // two warpgroups of gather warps
 constexpr int WS_PER_PRODUCER = 2;   // channels served by one gather warp
 constexpr int WS_CONSUMERS = WS_PRODUCERS * WS_PER_PRODUCER;
 constexpr int WS_WARPS = WS_PRODUCERS + WS_CONSUMERS;
-constexpr int WS_LB = 192;  // entries per list buffer
+#ifndef YAWB_WS_LB
+#define YAWB_WS_LB 192
+#endif
+constexpr int WS_LB = YAWB_WS_LB;  // entries per list buffer
 #ifndef YAWB_WS_SUB
 #define YAWB_WS_SUB 4
 #endif
@@ -109,6 +112,7 @@ __device__ __forceinline__ void ws_carve(Channel<WEIGHTED> &C, unsigned char *p,
     C.seg = (unsigned short *)p;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
 __device__ __forceinline__ void st_flag(int *p, int v) { *(volatile int *)p = v; }
 
@@ -227,6 +231,13 @@ __device__ __forceinline__ int ws_fill(const FastParams &P, const Channel<WEIGHT
                     const long long row = G.cell_base + ((long long)b * G.gv + iv) * G.gu;
                     s0 = P.cell_start[row + (iu & 0xffff)];
                     cnt = P.cell_start[row + (iu >> 16) + 1] - s0;
+                    // pull the run's coordinates towards the SM while the scan below and the previous
+                    // list are being worked on (runs are short: one or two 128-byte lines per array)
+                    for (int q = 0; q < cnt; q += 16) {
+                        prefetch_l2(P.su + s0 + q);
+                        prefetch_l2(P.sv + s0 + q);
+                        prefetch_l2(P.st + s0 + q);
+                    }
                 }
                 int incl = cnt;
 #pragma unroll
@@ -644,6 +655,14 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_uni(co
         const int p1 = P.pair_i[cur_pair];
         const Tile tl = P.tiles[rec.y];
         const PatchFrame &F = P.sframe[p1];
+        if (grab_lo < grab_hi) {  // next item of this grab: start pulling its rows into L2 now
+            const Tile nx = P.tiles[P.live[grab_lo].y];
+            for (int k = lane * 16; k < nx.count; k += 512) {
+                prefetch_l2(P.rx + nx.start + k);
+                prefetch_l2(P.ry + nx.start + k);
+                prefetch_l2(P.rz + nx.start + k);
+            }
+        }
         const double c0 = F.c[0], c1 = F.c[1], c2 = F.c[2];
         const double a0 = F.e1[0], a1 = F.e1[1], a2 = F.e1[2];
         const double g0 = F.e2[0], g1 = F.e2[1], g2 = F.e2[2];

@@ -24,7 +24,10 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr double kTargetPerCell = 8.0;
+#ifndef YAWB_TARGET_PER_CELL
+#define YAWB_TARGET_PER_CELL 5.5
+#endif
+constexpr double kTargetPerCell = YAWB_TARGET_PER_CELL;  // rows per sky cell and z-bin the grid is sized for
 constexpr long long kMaxCellsPerPatchBin = 1ll << 22;
 
 inline int blocks_for(int64_t n, int per_block = kThreads) {
