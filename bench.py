@@ -345,7 +345,10 @@ def run_gpu_arm(args):
 
     def count_all(dev):
         results, stats = {}, {}
-        for tag, (a, b) in COUNT_TYPES.items():
+        # order follows the uploads (ref, unk, ref_rand, unk_rand): DD and RD can start while the last
+        # catalog is still on its way through PCIe
+        for tag in ("DD", "RD", "DR", "RR"):
+            a, b = COUNT_TYPES[tag]
             ci, _, st = eng.count(dev[a], dev[b], opi, opj, plan.r2)
             results[tag], stats[tag] = ci, st
         return results, stats

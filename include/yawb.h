@@ -77,6 +77,10 @@ int yawb_destroy(yawb_ctx *ctx);
  *   patch_off  n_patch + 1 row offsets (patch ids are 0..n_patch-1,
  *              src/yaw/correlation/measurements.py:358-364)
  *   n_bins     number of z-bins (ignored when zbin == NULL)
+ *
+ * The call is asynchronous: copies are enqueued on a dedicated copy stream and overlap with kernels of
+ * earlier calls; the host buffers must stay valid until the first call that uses the catalog (or
+ * yawb_sync) has returned.
  */
 int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);

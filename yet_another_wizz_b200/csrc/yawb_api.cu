@@ -47,6 +47,8 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sms = prop.multiProcessorCount;
     YAWB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    YAWB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+
     YAWB_CUDA(cudaEventCreate(&ctx->ev0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev1));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
@@ -65,8 +67,10 @@ int yawb_create(int device, yawb_ctx **out) {
 int yawb_destroy(yawb_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_counters);
+    cudaStreamDestroy(ctx->copy_stream);
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -84,6 +88,7 @@ int yawb_device_sms(const yawb_ctx *ctx) { return ctx ? ctx->sms : 0; }
 
 int yawb_sync(yawb_ctx *ctx) {
     YAWB_REQUIRE(ctx != nullptr, "yawb_sync: ctx is NULL");
+    YAWB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     YAWB_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -150,6 +155,7 @@ int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const
 int yawb_free_catalog(yawb_cat *cat) {
     if (!cat) return 0;
     cudaSetDevice(cat->ctx->device);
+    cudaStreamSynchronize(cat->ctx->copy_stream);
     cudaStreamSynchronize(cat->ctx->stream);
     yawb_index_free(cat, true);
     delete cat;
@@ -175,6 +181,7 @@ int yawb_build_index(yawb_cat *cat, int role, double *ms) {
 int yawb_drop_index(yawb_cat *cat) {
     YAWB_REQUIRE(cat != nullptr, "yawb_drop_index: cat is NULL");
     YAWB_CUDA(cudaSetDevice(cat->ctx->device));
+    if (yawb_cat_finalize(cat)) return 1;
     YAWB_CUDA(cudaStreamSynchronize(cat->ctx->stream));
     yawb_index_free(cat, false);
     return 0;
@@ -182,6 +189,7 @@ int yawb_drop_index(yawb_cat *cat) {
 
 int yawb_catalog_info(const yawb_cat *cat, int64_t *n_rows, int64_t *device_bytes) {
     YAWB_REQUIRE(cat != nullptr, "yawb_catalog_info: cat is NULL");
+    if (yawb_cat_finalize(const_cast<yawb_cat *>(cat))) return 1;
     if (n_rows) *n_rows = cat->n;
     if (device_bytes) *device_bytes = cat->device_bytes;
     return 0;
@@ -189,6 +197,7 @@ int yawb_catalog_info(const yawb_cat *cat, int64_t *n_rows, int64_t *device_byte
 
 int yawb_sum_weights(const yawb_cat *cat, double *out) {
     YAWB_REQUIRE(cat && out, "yawb_sum_weights: NULL argument");
+    if (yawb_cat_finalize(const_cast<yawb_cat *>(cat))) return 1;
     std::memcpy(out, cat->h_sumw.data(), cat->h_sumw.size() * sizeof(double));
     return 0;
 }
@@ -219,6 +228,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     YAWB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     yawb_stats s{};
+    if (yawb_cat_finalize(cat1) || yawb_cat_finalize(cat2)) return 1;
 
     // indexes (lazy)
     float t_idx = 0.f;

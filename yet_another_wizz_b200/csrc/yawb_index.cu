@@ -38,10 +38,10 @@ inline int blocks_for(int64_t n, int per_block = kThreads) {
 // stream; the pool keeps freed blocks, see yawb_create), so building and dropping indexes costs no
 // device synchronisation and no driver round trips after the first use.
 template <typename T>
-int dev_alloc(yawb_cat *cat, T **ptr, size_t count) {
+int dev_alloc(yawb_cat *cat, T **ptr, size_t count, cudaStream_t stream = nullptr) {
     *ptr = nullptr;
     if (count == 0) count = 1;
-    YAWB_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), cat->ctx->stream));
+    YAWB_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), stream ? stream : cat->ctx->stream));
     cat->device_bytes += (int64_t)(count * sizeof(T));
     return 0;
 }
@@ -448,15 +448,18 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
                       const int32_t *zbin, const int64_t *patch_off) {
     const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
-    cudaStream_t st = ctx->stream;
+    // The whole upload (allocation, host-to-device copies, per-patch reductions, meta data to pinned
+    // staging) runs on the context's copy stream, so it overlaps with index builds and pair counts of
+    // catalogs that arrived earlier; the main stream joins through `ev_meta` when the catalog is first used.
+    cudaStream_t st = ctx->copy_stream;
     Scratch scr(st);
 
-    if (dev_alloc(cat, &cat->x, n) || dev_alloc(cat, &cat->y, n) || dev_alloc(cat, &cat->z, n) ||
-        dev_alloc(cat, &cat->patch, n))
+    if (dev_alloc(cat, &cat->x, n, st) || dev_alloc(cat, &cat->y, n, st) || dev_alloc(cat, &cat->z, n, st) ||
+        dev_alloc(cat, &cat->patch, n, st))
         return 1;
-    if (w && dev_alloc(cat, &cat->w, n)) return 1;
-    if (zbin && dev_alloc(cat, &cat->bin, n)) return 1;
-    if (dev_alloc(cat, &cat->d_frames, P) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1)) return 1;
+    if (w && dev_alloc(cat, &cat->w, n, st)) return 1;
+    if (zbin && dev_alloc(cat, &cat->bin, n, st)) return 1;
+    if (dev_alloc(cat, &cat->d_frames, P, st) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1, st)) return 1;
 
     double *d_xyz = scr.get<double>((size_t)n * 3);
     long long *d_poff = scr.get<long long>(P + 1);
@@ -490,24 +493,37 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
                                                          d_box);
     k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
 
-    // the one host round trip of an upload: frames, row counts and sums of weights
-    std::vector<unsigned long long> counts((size_t)B * P);
-    cat->h_sumw.assign((size_t)B * P, 0.0);
-    cat->h_frames.assign(P, PatchFrame{});
-    YAWB_CUDA(cudaMemcpyAsync(cat->h_frames.data(), cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (size_t)B * P * sizeof(unsigned long long),
+    // meta data (frames, row counts, sums of weights) travels to pinned staging; nobody waits here:
+    // yawb_cat_finalize() picks it up when the catalog is first used
+    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_frames, std::max<size_t>(P, 1) * sizeof(PatchFrame), cudaHostAllocDefault));
+    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_counts, (size_t)B * P * sizeof(unsigned long long), cudaHostAllocDefault));
+    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_sumw, (size_t)B * P * sizeof(double), cudaHostAllocDefault));
+    YAWB_CUDA(cudaEventCreateWithFlags(&cat->ev_meta, cudaEventDisableTiming));
+    YAWB_CUDA(cudaMemcpyAsync(cat->hp_frames, cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaMemcpyAsync(cat->hp_counts, d_counts, (size_t)B * P * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaMemcpyAsync(cat->h_sumw.data(), d_sumw, (size_t)B * P * sizeof(double),
-                              cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaStreamSynchronize(st));
+    YAWB_CUDA(cudaMemcpyAsync(cat->hp_sumw, d_sumw, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaEventRecord(cat->ev_meta, st));
     YAWB_CUDA(cudaGetLastError());
+    cat->finalized = false;
+    return 0;
+}
 
+// Host-side completion of an upload: wait for the meta data, derive the row tables.
+int yawb_cat_finalize(yawb_cat *cat) {
+    if (cat->finalized) return 0;
+    const int P = cat->n_patch, B = cat->n_bins;
+    YAWB_CUDA(cudaEventSynchronize(cat->ev_meta));
+    YAWB_CUDA(cudaStreamWaitEvent(cat->ctx->stream, cat->ev_meta, 0));  // the main stream may now touch the rows
+    YAWB_CUDA(cudaGetLastError());
+    cat->h_frames.assign(cat->hp_frames, cat->hp_frames + P);
+    cat->h_sumw.assign(cat->hp_sumw, cat->hp_sumw + (size_t)B * P);
     cat->h_counts.assign((size_t)B * P, 0);
     cat->n = 0;
-    for (size_t k = 0; k < counts.size(); ++k) {
-        cat->h_counts[k] = (long long)counts[k];
-        cat->n += (long long)counts[k];
-        if (!w) cat->h_sumw[k] = (double)counts[k];  // trees.py:225-227
+    for (size_t k = 0; k < cat->h_counts.size(); ++k) {
+        cat->h_counts[k] = (long long)cat->hp_counts[k];
+        cat->n += cat->h_counts[k];
+        if (!cat->weighted) cat->h_sumw[k] = (double)cat->hp_counts[k];  // trees.py:225-227
     }
     // rows of (patch p, bin b) in both sort orders: patch-major, bin-minor
     cat->h_seg_off.assign((size_t)P * B + 1, 0);
@@ -516,12 +532,14 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
             cat->h_seg_off[(size_t)p * B + b + 1] =
                 cat->h_seg_off[(size_t)p * B + b] + (int)cat->h_counts[(size_t)b * P + p];
     YAWB_CUDA(cudaMemcpyAsync(cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int),
-                              cudaMemcpyHostToDevice, st));
+                              cudaMemcpyHostToDevice, cat->ctx->stream));
+    cat->finalized = true;
     return 0;
 }
 
 // -------------------------------------------------------------------------------------------
 int yawb_index_build_first(yawb_cat *cat) {
+    if (yawb_cat_finalize(cat)) return 1;
     if (cat->has_sindex) return 0;
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
@@ -588,6 +606,7 @@ int yawb_index_build_first(yawb_cat *cat) {
 
 // -------------------------------------------------------------------------------------------
 int yawb_index_build_second(yawb_cat *cat) {
+    if (yawb_cat_finalize(cat)) return 1;
     if (cat->has_rtiles) return 0;
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
@@ -662,6 +681,11 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
         cat->has_rtiles = false;
     }
     if (everything) {
+        if (cat->hp_frames) cudaFreeHost(cat->hp_frames);
+        if (cat->hp_counts) cudaFreeHost(cat->hp_counts);
+        if (cat->hp_sumw) cudaFreeHost(cat->hp_sumw);
+        if (cat->ev_meta) cudaEventDestroy(cat->ev_meta);
+        cat->hp_frames = nullptr; cat->hp_counts = nullptr; cat->hp_sumw = nullptr; cat->ev_meta = nullptr;
         const size_t ni = (size_t)cat->n_in;
         dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
         dev_free(cat, cat->w, ni);

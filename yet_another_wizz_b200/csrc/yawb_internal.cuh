@@ -79,7 +79,8 @@ constexpr int YAWB_MAX_EDGES = 256;
 struct yawb_ctx {
     int device = 0;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // all kernels and result copies
+    cudaStream_t copy_stream = nullptr;  // host-to-device copies of catalog uploads (overlap with kernels)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user stopwatch
     unsigned long long *d_counters = nullptr;  // [8] work counter + statistics
@@ -94,6 +95,13 @@ struct yawb_cat {
     bool binned = false;
     bool weighted = false;
     int64_t device_bytes = 0;
+
+    // uploads are asynchronous: the host-side tables below are filled by yawb_cat_finalize() on first use
+    bool finalized = false;
+    cudaEvent_t ev_meta = nullptr;            // recorded after the meta data reached the pinned staging
+    unsigned long long *hp_counts = nullptr;  // pinned staging [n_bins][n_patch]
+    double *hp_sumw = nullptr;                // pinned staging [n_bins][n_patch]
+    PatchFrame *hp_frames = nullptr;          // pinned staging [n_patch]
 
     // raw rows in upload order (grouped by patch)
     double *x = nullptr, *y = nullptr, *z = nullptr, *w = nullptr;
@@ -131,6 +139,7 @@ struct yawb_cat {
 // index construction (yawb_index.cu)
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
                       const int32_t *zbin, const int64_t *patch_off);
+int yawb_cat_finalize(yawb_cat *cat);
 int yawb_index_build_first(yawb_cat *cat);
 int yawb_index_build_second(yawb_cat *cat);
 void yawb_index_free(yawb_cat *cat, bool everything);

@@ -109,6 +109,8 @@ class Engine:
         )
         cat = DeviceCatalog(self, h, len(patch_off) - 1, int(n_bins) if zbin is not None else 1,
                             zbin is not None, weights is not None)
+        # the upload is asynchronous: keep the host buffers alive as long as the handle
+        cat._keepalive = (xyz, weights, zbin, patch_off)
         return cat
 
     def count(
