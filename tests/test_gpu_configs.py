@@ -158,3 +158,22 @@ def test_many_bins_and_empty_patches(engine):
     exact = yb.crosscorrelate(config, ref, unk, engine=ExactEngine(engine), **kw)
     compare(fast, exact, ("dd", "dr"), exact_ints=True)
     assert fast[0].dd.counts.counts[30:].sum() == 0  # bins above z = 0.6 hold nothing
+
+
+def test_many_bins_times_many_subbins(engine):
+    """50 z-bins x 53 r-weight sub-bins (configs[4] binning with rweight): the per-warp accumulators no longer
+    fit four warps per CTA, the launcher falls back to smaller CTAs; weighted first catalog"""
+    import yet_another_wizz_b200 as yb
+
+    box = (0.0, 4.0, -2.0, 2.0)
+    centers = grid_centers(2, 2, box)
+    pool = np.random.default_rng(7).uniform(0.07, 1.42, 50_000)
+    wpool = np.random.default_rng(9).uniform(0.5, 1.5, 50_000)
+    ref = make("ref", 30_000, centers, zpool=pool, wpool=wpool, seed=1, box=box)
+    unk = make("unk", 120_000, centers, seed=2, box=box)
+    unk2 = make("unk2", 60_000, centers, seed=4, box=box)
+    config = yb.Configuration.create(rmin=[100, 200], rmax=[1000, 3000], rweight=-1.0, resolution=50,
+                                     zmin=0.07, zmax=1.42, num_bins=50)
+    fast = yb.crosscorrelate(config, ref, unk, unk_rand=unk2, engine=engine)
+    exact = yb.crosscorrelate(config, ref, unk, unk_rand=unk2, engine=ExactEngine(engine))
+    compare(fast, exact, ("dd", "dr"), exact_ints=False)

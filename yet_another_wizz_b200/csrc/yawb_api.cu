@@ -51,6 +51,8 @@ int yawb_create(int device, yawb_ctx **out) {
 
     YAWB_CUDA(cudaEventCreate(&ctx->ev0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev1));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_i0));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_i1));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t1));
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
@@ -77,6 +79,8 @@ int yawb_destroy(yawb_ctx *ctx) {
     }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_i0);
+    cudaEventDestroy(ctx->ev_i1);
     cudaEventDestroy(ctx->ev_t0);
     cudaEventDestroy(ctx->ev_t1);
     cudaStreamDestroy(ctx->stream);
@@ -230,17 +234,14 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     yawb_stats s{};
     if (yawb_cat_finalize(cat1) || yawb_cat_finalize(cat2)) return 1;
 
-    // indexes (lazy)
-    float t_idx = 0.f;
-    if (!cat1->has_sindex || !cat2->has_rtiles) {
-        YAWB_CUDA(cudaEventRecord(ctx->ev0, st));
+    // indexes (lazy); timed with events that are only read after the final synchronisation of this call
+    const bool build_idx = !cat1->has_sindex || !cat2->has_rtiles;
+    if (build_idx) {
+        YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
         if (yawb_index_build_first(cat1)) return 1;
         if (yawb_index_build_second(cat2)) return 1;
-        YAWB_CUDA(cudaEventRecord(ctx->ev1, st));
-        YAWB_CUDA(cudaEventSynchronize(ctx->ev1));
-        YAWB_CUDA(cudaEventElapsedTime(&t_idx, ctx->ev0, ctx->ev1));
+        YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
     }
-    s.index_ms = t_idx;
 
     const bool weighted = cat1->weighted || cat2->weighted;
     const size_t n_out = (size_t)n_pairs * B * nsub;
@@ -356,8 +357,10 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     TRY(cudaGetLastError());
-    float t_k = 0.f;
+    float t_k = 0.f, t_idx = 0.f;
     TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));
+    if (build_idx) TRY(cudaEventElapsedTime(&t_idx, ctx->ev_i0, ctx->ev_i1));
+    s.index_ms = t_idx;
 #undef TRY
     cleanup();
     s.kernel_ms = t_k;

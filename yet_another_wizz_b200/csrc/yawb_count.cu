@@ -474,15 +474,18 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         }
 #undef LAUNCH_WS
     } else {
-        const size_t smem = YAWB_WARPS * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1);
+        // fewer warps per CTA when many z-bins x sub-bins make the per-warp accumulators large
+        int warps = YAWB_WARPS;
+        while (warps > 1 && warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1) > 227 * 1024) warps /= 2;
+        const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1);
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
-        const int ctas = ctx->sms * YAWB_MIN_CTAS;
+        const int ctas = ctx->sms * YAWB_MIN_CTAS * (YAWB_WARPS / warps);
 #define LAUNCH(W, M, T)                                                                                   \
     do {                                                                                                  \
         YAWB_CUDA(cudaFuncSetAttribute(k_count_uni<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)smem));                                                       \
-        k_count_uni<W, M, T><<<ctas, YAWB_WARPS * 32, smem, ctx->stream>>>(P);                           \
+        k_count_uni<W, M, T><<<ctas, warps * 32, smem, ctx->stream>>>(P);                           \
     } while (0)
         if (a.weighted) {
             if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);

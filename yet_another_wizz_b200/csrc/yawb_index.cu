@@ -215,44 +215,57 @@ __global__ void k_finish_frames(const unsigned long long *__restrict__ box, int 
     frames[p].radius = sqrt(dec_double_dev(box[5 * p + 4])) * (1.0 + 1e-12) + 1e-15;
 }
 
-// per patch: (u, v) bounding box and max squared chord distance from the centre
-__global__ void k_patch_bbox(const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ z, const int *__restrict__ patch, long long n,
-                             const PatchFrame *__restrict__ frames,
-                             unsigned long long *__restrict__ box /*[n_patch][5]*/) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p = patch[i];
-    const PatchFrame &f = frames[p];
-    double dx = x[i] - f.c[0], dy = y[i] - f.c[1], dz = z[i] - f.c[2];
-    double u = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
-    double v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
-    double d2 = dx * dx + dy * dy + dz * dz;
-    const unsigned full = __activemask();
-    int p0 = __shfl_sync(full, p, __ffs(full) - 1);
-    unsigned long long eu = enc_double(u), ev = enc_double(v), ed = enc_double(d2);
-    if (full == 0xffffffffu && __all_sync(full, p == p0)) {
-        unsigned long long umin = eu, umax = eu, vmin = ev, vmax = ev, dmax = ed;
-        for (int o = 16; o; o >>= 1) {
-            umin = min(umin, __shfl_xor_sync(full, umin, o));
-            umax = max(umax, __shfl_xor_sync(full, umax, o));
-            vmin = min(vmin, __shfl_xor_sync(full, vmin, o));
-            vmax = max(vmax, __shfl_xor_sync(full, vmax, o));
-            dmax = max(dmax, __shfl_xor_sync(full, dmax, o));
+// per patch: (u, v) bounding box and max squared chord distance from the centre.  Same blocking as
+// k_patch_sums: a block owns kSumRows consecutive rows, reduces the rows of its first patch in
+// registers / shuffles / shared memory and issues five atomics; stragglers of the next patch go direct.
+__global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restrict__ x, const double *__restrict__ y,
+                                                         const double *__restrict__ z, const int *__restrict__ patch,
+                                                         long long n, const PatchFrame *__restrict__ frames,
+                                                         unsigned long long *__restrict__ box /*[n_patch][5]*/) {
+    __shared__ unsigned long long s_box[5][kThreads / 32];
+    const long long row0 = (long long)blockIdx.x * kSumRows;
+    const int p_blk = patch[row0];
+    const PatchFrame f = frames[p_blk];
+    unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull;
+    for (int k = threadIdx.x; k < kSumRows; k += blockDim.x) {
+        const long long i = row0 + k;
+        if (i >= n) break;
+        const int p = patch[i];
+        const PatchFrame &g = p == p_blk ? f : frames[p];
+        const double dx = x[i] - g.c[0], dy = y[i] - g.c[1], dz = z[i] - g.c[2];
+        const unsigned long long eu = enc_double(dx * g.e1[0] + dy * g.e1[1] + dz * g.e1[2]);
+        const unsigned long long ev = enc_double(dx * g.e2[0] + dy * g.e2[1] + dz * g.e2[2]);
+        const unsigned long long ed = enc_double(dx * dx + dy * dy + dz * dz);
+        if (p == p_blk) {
+            umin = min(umin, eu); umax = max(umax, eu);
+            vmin = min(vmin, ev); vmax = max(vmax, ev);
+            dmax = max(dmax, ed);
+        } else {
+            atomicMin(&box[5 * p], eu);
+            atomicMax(&box[5 * p + 1], eu);
+            atomicMin(&box[5 * p + 2], ev);
+            atomicMax(&box[5 * p + 3], ev);
+            atomicMax(&box[5 * p + 4], ed);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicMin(&box[5 * p0], umin);
-            atomicMax(&box[5 * p0 + 1], umax);
-            atomicMin(&box[5 * p0 + 2], vmin);
-            atomicMax(&box[5 * p0 + 3], vmax);
-            atomicMax(&box[5 * p0 + 4], dmax);
-        }
-    } else {
-        atomicMin(&box[5 * p], eu);
-        atomicMax(&box[5 * p + 1], eu);
-        atomicMin(&box[5 * p + 2], ev);
-        atomicMax(&box[5 * p + 3], ev);
-        atomicMax(&box[5 * p + 4], ed);
+    }
+    for (int o = 16; o; o >>= 1) {
+        umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_box[0][w] = umin; s_box[1][w] = umax; s_box[2][w] = vmin; s_box[3][w] = vmax; s_box[4][w] = dmax;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        unsigned long long v = s_box[threadIdx.x][0];
+        const bool is_min = threadIdx.x == 0 || threadIdx.x == 2;
+        for (int k = 1; k < kThreads / 32; ++k) v = is_min ? min(v, s_box[threadIdx.x][k]) : max(v, s_box[threadIdx.x][k]);
+        if (is_min) atomicMin(&box[5 * p_blk + threadIdx.x], v);  // ~0 / 0 are the neutral initial values
+        else atomicMax(&box[5 * p_blk + threadIdx.x], v);
     }
 }
 
@@ -489,8 +502,8 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     k_make_frames<<<pb, 128, 0, st>>>(d_sums, P, cat->d_frames);
     k_init_box<<<pb, 128, 0, st>>>(d_box, P);
     if (n > 0)
-        k_patch_bbox<<<blocks_for(n), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n, cat->d_frames,
-                                                         d_box);
+        k_patch_bbox<<<blocks_for(n, kSumRows), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n,
+                                                                   cat->d_frames, d_box);
     k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
 
     // meta data (frames, row counts, sums of weights) travels to pinned staging; nobody waits here:

@@ -349,16 +349,16 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
     _last_stats.clear()
     kw = dict(binned_second=False)
     try:
-        # uploads are asynchronous: enqueue every catalog first, then count in arrival order so that
-        # DD / RD run while the later catalogs are still crossing PCIe
+        # uploads are asynchronous: enqueue every catalog first (randoms, the big ones, in front), then
+        # count in arrival order so that RR / RD run while the later catalogs are still crossing PCIe
         binning = _as_binning(config)
-        for cat, bins in ((reference, binning), (unknown, None), (ref_rand, binning), (unk_rand, None)):
+        for cat, bins in ((ref_rand, binning), (unk_rand, None), (unknown, None), (reference, binning)):
             if cat is not None:
                 links._uploads.get(cat, bins)
-        DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
+        RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
         RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
         DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
-        RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
+        DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
     finally:
         links._uploads.free()
         links._uploads = None
