@@ -56,6 +56,8 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t1));
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+    ctx->pin_size = 8u << 20;
+    YAWB_CUDA(cudaHostAlloc((void **)&ctx->pin_base, ctx->pin_size, cudaHostAllocDefault));
     {   // keep freed blocks in the stream-ordered pool: index rebuilds then reuse them without driver calls
         cudaMemPool_t pool;
         YAWB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -72,6 +74,7 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_counters);
+    if (ctx->pin_base) cudaFreeHost(ctx->pin_base);
     cudaStreamDestroy(ctx->copy_stream);
     {
         cudaMemPool_t pool;

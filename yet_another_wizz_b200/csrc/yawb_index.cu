@@ -278,17 +278,18 @@ __device__ __forceinline__ void local_uv(const PatchFrame &f, double X, double Y
     v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
 }
 
+template <typename K>
 __global__ void k_keys_first(const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ z, const int *__restrict__ bin,
                              const int *__restrict__ patch, long long n, int n_bins,
                              const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
-                             unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+                             K *__restrict__ keys, unsigned *__restrict__ vals) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     vals[i] = (unsigned)i;
     int b = bin ? bin[i] : 0;
     if (b < 0 || b >= n_bins) {
-        keys[i] = ~0ull;
+        keys[i] = (K)~(K)0;
         return;
     }
     int p = patch[i];
@@ -298,7 +299,7 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
     // clamp in double first: the product can exceed the int range for degenerate patches
     int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_c), 0.0), (double)(g.gu - 1));
     int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_c), 0.0), (double)(g.gv - 1));
-    keys[i] = (unsigned long long)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
+    keys[i] = (K)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
 }
 
 // Hilbert index of a cell on a 65536 x 65536 grid.  Unlike the Morton (Z) curve the Hilbert curve has
@@ -324,17 +325,19 @@ __device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y) {
     return d;
 }
 
+// key = (patch * n_bins + bin) << hbits | top `hbits` bits of the Hilbert index
+template <typename K>
 __global__ void k_keys_second(const double *__restrict__ x, const double *__restrict__ y,
                               const double *__restrict__ z, const int *__restrict__ bin,
-                              const int *__restrict__ patch, long long n, int n_bins,
-                              const PatchFrame *__restrict__ frames,
-                              unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+                              const int *__restrict__ patch, long long n, int n_bins, int hbits,
+                              const PatchFrame *__restrict__ frames, K *__restrict__ keys,
+                              unsigned *__restrict__ vals) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     vals[i] = (unsigned)i;
     int b = bin ? bin[i] : 0;
     if (b < 0 || b >= n_bins) {
-        keys[i] = ~0ull;
+        keys[i] = (K)~(K)0;
         return;
     }
     int p = patch[i];
@@ -347,7 +350,8 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     double s = fmin(su > 0.0 ? su : sv, sv > 0.0 ? sv : su);
     int qu = min(max((int)((u - f.umin) * s), 0), 65535);
     int qv = min(max((int)((v - f.vmin) * s), 0), 65535);
-    keys[i] = ((unsigned long long)((long long)p * n_bins + b) << 32) | hilbert16((unsigned)qu, (unsigned)qv);
+    keys[i] = (K)(((unsigned long long)((long long)p * n_bins + b) << hbits) |
+                  (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv) >> (32 - hbits)));
 }
 
 __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
@@ -386,14 +390,15 @@ __global__ void k_gather_local(const unsigned *__restrict__ perm, long long n, c
 }
 
 // cell_start[g] = first sorted row whose key is >= g (one thread per cell, binary search)
-__global__ void k_cell_start(const unsigned long long *__restrict__ keys, long long n, long long n_cells,
+template <typename K>
+__global__ void k_cell_start(const K *__restrict__ keys, long long n, long long n_cells,
                              int *__restrict__ cell_start) {
     long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g > n_cells) return;
     long long lo = 0, hi = n;
     while (lo < hi) {
         long long mid = (lo + hi) >> 1;
-        if (keys[mid] < (unsigned long long)g) lo = mid + 1; else hi = mid;
+        if ((unsigned long long)keys[mid] < (unsigned long long)g) lo = mid + 1; else hi = mid;
     }
     cell_start[g] = (int)lo;
 }
@@ -436,8 +441,9 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     }
 }
 
-int sort_pairs(yawb_ctx *ctx, Scratch &scr, unsigned long long *keys_in, unsigned long long *keys_out,
-               unsigned *vals_in, unsigned *vals_out, long long n, int end_bit) {
+template <typename K>
+int sort_pairs(yawb_ctx *ctx, Scratch &scr, K *keys_in, K *keys_out, unsigned *vals_in, unsigned *vals_out,
+               long long n, int end_bit) {
     size_t temp_bytes = 0;
     YAWB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys_in, keys_out, vals_in, vals_out,
                                               (int)n, 0, end_bit, ctx->stream));
@@ -452,6 +458,55 @@ int bits_for(unsigned long long max_key) {
     int b = 1;
     while (b < 64 && (max_key >> b)) ++b;
     return b;
+}
+
+template <typename K>
+int build_first_sorted(yawb_cat *cat, long long base) {
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    const long long n_in = cat->n_in, n = cat->n;
+    Scratch scr(st);
+    const size_t nn = std::max<long long>(n_in, 1);
+    K *k0 = scr.get<K>(nn), *k1 = scr.get<K>(nn);
+    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
+    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
+    if (n_in > 0) {
+        k_keys_first<K><<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in,
+                                                               cat->n_bins, cat->d_frames, cat->d_sgrid, k0, v0);
+        // dropped rows carry the all-ones key: sort every bit only if something was dropped
+        const int end_bit = (n == n_in) ? bits_for((unsigned long long)std::max<long long>(base, 1)) : (int)(8 * sizeof(K));
+        if (sort_pairs<K>(ctx, scr, k0, k1, v0, v1, n_in, end_bit)) return 1;
+    }
+    if (n > 0)
+        k_gather_local<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->patch,
+                                                           cat->d_frames, cat->sx, cat->sy, cat->sz, cat->sw,
+                                                           cat->su, cat->sv, cat->st);
+    k_cell_start<K><<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, cat->cell_start);
+    return 0;
+}
+
+template <typename K>
+int build_second_sorted(yawb_cat *cat, int hbits) {
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    const long long n_in = cat->n_in, n = cat->n;
+    const int P = cat->n_patch, B = cat->n_bins;
+    Scratch scr(st);
+    const size_t nn = std::max<long long>(n_in, 1);
+    K *k0 = scr.get<K>(nn), *k1 = scr.get<K>(nn);
+    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
+    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
+    if (n_in > 0) {
+        k_keys_second<K><<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in, B,
+                                                                hbits, cat->d_frames, k0, v0);
+        const int end_bit = (n == n_in) ? hbits + bits_for((unsigned long long)std::max<long long>((long long)P * B, 1))
+                                        : (int)(8 * sizeof(K));
+        if (sort_pairs<K>(ctx, scr, k0, k1, v0, v1, n_in, std::min(end_bit, (int)(8 * sizeof(K))))) return 1;
+    }
+    if (n > 0)
+        k_gather<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->rx, cat->ry,
+                                                     cat->rz, cat->rw);
+    return 0;
 }
 
 }  // namespace
@@ -508,9 +563,25 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
 
     // meta data (frames, row counts, sums of weights) travels to pinned staging; nobody waits here:
     // yawb_cat_finalize() picks it up when the catalog is first used
-    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_frames, std::max<size_t>(P, 1) * sizeof(PatchFrame), cudaHostAllocDefault));
-    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_counts, (size_t)B * P * sizeof(unsigned long long), cudaHostAllocDefault));
-    YAWB_CUDA(cudaHostAlloc((void **)&cat->hp_sumw, (size_t)B * P * sizeof(double), cudaHostAllocDefault));
+    {
+        const size_t b_frames = (((size_t)std::max(P, 1) * sizeof(PatchFrame)) + 63) & ~(size_t)63;
+        const size_t b_counts = (((size_t)B * P * sizeof(unsigned long long)) + 63) & ~(size_t)63;
+        const size_t b_sumw = (((size_t)B * P * sizeof(double)) + 63) & ~(size_t)63;
+        const size_t need = b_frames + b_counts + b_sumw;
+        unsigned char *blk = nullptr;
+        if (ctx->pin_base && ctx->pin_used + need <= ctx->pin_size) {
+            blk = ctx->pin_base + ctx->pin_used;
+            ctx->pin_used += need;
+            ctx->pin_live += 1;
+            cat->staging_in_arena = true;
+        } else {
+            YAWB_CUDA(cudaHostAlloc((void **)&blk, need, cudaHostAllocDefault));
+            cat->hp_block = blk;
+        }
+        cat->hp_frames = (PatchFrame *)blk;
+        cat->hp_counts = (unsigned long long *)(blk + b_frames);
+        cat->hp_sumw = (double *)(blk + b_frames + b_counts);
+    }
     YAWB_CUDA(cudaEventCreateWithFlags(&cat->ev_meta, cudaEventDisableTiming));
     YAWB_CUDA(cudaMemcpyAsync(cat->hp_frames, cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
     YAWB_CUDA(cudaMemcpyAsync(cat->hp_counts, d_counts, (size_t)B * P * sizeof(unsigned long long),
@@ -520,6 +591,19 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     YAWB_CUDA(cudaGetLastError());
     cat->finalized = false;
     return 0;
+}
+
+static void release_staging(yawb_cat *cat) {
+    if (cat->staging_in_arena) {
+        yawb_ctx *ctx = cat->ctx;
+        if (--ctx->pin_live == 0) ctx->pin_used = 0;  // nothing pending: the arena starts over
+        cat->staging_in_arena = false;
+    }
+    if (cat->hp_block) cudaFreeHost(cat->hp_block);
+    cat->hp_block = nullptr;
+    cat->hp_frames = nullptr;
+    cat->hp_counts = nullptr;
+    cat->hp_sumw = nullptr;
 }
 
 // Host-side completion of an upload: wait for the meta data, derive the row tables.
@@ -546,6 +630,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
                 cat->h_seg_off[(size_t)p * B + b] + (int)cat->h_counts[(size_t)b * P + p];
     YAWB_CUDA(cudaMemcpyAsync(cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int),
                               cudaMemcpyHostToDevice, cat->ctx->stream));
+    release_staging(cat);
     cat->finalized = true;
     return 0;
 }
@@ -556,7 +641,7 @@ int yawb_index_build_first(yawb_cat *cat) {
     if (cat->has_sindex) return 0;
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
-    const long long n_in = cat->n_in, n = cat->n;
+    const long long n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
 
     // grid per patch: cell edge from the mean density of one z-bin of this patch
@@ -591,27 +676,16 @@ int yawb_index_build_first(yawb_cat *cat) {
     if (dev_alloc(cat, &cat->d_sgrid, P)) return 1;
     YAWB_CUDA(cudaMemcpyAsync(cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid), cudaMemcpyHostToDevice, st));
 
-    Scratch scr(st);
-    const size_t nn = std::max<long long>(n_in, 1);
-    unsigned long long *k0 = scr.get<unsigned long long>(nn), *k1 = scr.get<unsigned long long>(nn);
-    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
-    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
-    if (n_in > 0) {
-        k_keys_first<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in,
-                                                            B, cat->d_frames, cat->d_sgrid, k0, v0);
-        // dropped rows carry key ~0: sort all 64 bits only if something was dropped
-        int end_bit = (n == n_in) ? bits_for((unsigned long long)std::max<long long>(base, 1)) : 64;
-        if (sort_pairs(ctx, scr, k0, k1, v0, v1, n_in, end_bit)) return 1;
-    }
     if (dev_alloc(cat, &cat->sx, n) || dev_alloc(cat, &cat->sy, n) || dev_alloc(cat, &cat->sz, n)) return 1;
     if (dev_alloc(cat, &cat->su, n) || dev_alloc(cat, &cat->sv, n) || dev_alloc(cat, &cat->st, n)) return 1;
     if (cat->weighted && dev_alloc(cat, &cat->sw, n)) return 1;
     if (dev_alloc(cat, &cat->cell_start, base + 1)) return 1;
-    if (n > 0)
-        k_gather_local<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->patch,
-                                                           cat->d_frames, cat->sx, cat->sy, cat->sz, cat->sw,
-                                                           cat->su, cat->sv, cat->st);
-    k_cell_start<<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, cat->cell_start);
+    // 32-bit sort keys whenever the cell ids fit (they nearly always do): a third less radix-sort traffic
+    if (base < 0xffffffffll) {
+        if (build_first_sorted<unsigned>(cat, base)) return 1;
+    } else {
+        if (build_first_sorted<unsigned long long>(cat, base)) return 1;
+    }
     YAWB_CUDA(cudaGetLastError());
     cat->has_sindex = true;
     return 0;
@@ -623,25 +697,21 @@ int yawb_index_build_second(yawb_cat *cat) {
     if (cat->has_rtiles) return 0;
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
-    const long long n_in = cat->n_in, n = cat->n;
+    const long long n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
 
-    Scratch scr(st);
-    const size_t nn = std::max<long long>(n_in, 1);
-    unsigned long long *k0 = scr.get<unsigned long long>(nn), *k1 = scr.get<unsigned long long>(nn);
-    unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
-    YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
-    if (n_in > 0) {
-        k_keys_second<<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch,
-                                                             n_in, B, cat->d_frames, k0, v0);
-        int end_bit = (n == n_in) ? 32 + bits_for((unsigned long long)std::max<long long>((long long)P * B, 1)) : 64;
-        if (sort_pairs(ctx, scr, k0, k1, v0, v1, n_in, std::min(end_bit, 64))) return 1;
-    }
     if (dev_alloc(cat, &cat->rx, n) || dev_alloc(cat, &cat->ry, n) || dev_alloc(cat, &cat->rz, n)) return 1;
     if (cat->weighted && dev_alloc(cat, &cat->rw, n)) return 1;
-    if (n > 0)
-        k_gather<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->rx, cat->ry,
-                                                     cat->rz, cat->rw);
+    // 32-bit sort keys when (patch, bin) leaves at least 16 bits (an even number) for the Hilbert index
+    {
+        const int seg_bits = bits_for((unsigned long long)std::max<long long>((long long)P * B, 1));
+        const int hbits32 = ((31 - seg_bits) / 2) * 2;  // the all-ones key stays reserved for dropped rows
+        if (hbits32 >= 16) {
+            if (build_second_sorted<unsigned>(cat, hbits32)) return 1;
+        } else {
+            if (build_second_sorted<unsigned long long>(cat, 32)) return 1;
+        }
+    }
 
     // tiles: chunks of YAWB_TILE rows inside each (patch, bin) segment
     std::vector<Tile> &tiles = cat->h_tiles;
@@ -694,11 +764,9 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
         cat->has_rtiles = false;
     }
     if (everything) {
-        if (cat->hp_frames) cudaFreeHost(cat->hp_frames);
-        if (cat->hp_counts) cudaFreeHost(cat->hp_counts);
-        if (cat->hp_sumw) cudaFreeHost(cat->hp_sumw);
+        release_staging(cat);
         if (cat->ev_meta) cudaEventDestroy(cat->ev_meta);
-        cat->hp_frames = nullptr; cat->hp_counts = nullptr; cat->hp_sumw = nullptr; cat->ev_meta = nullptr;
+        cat->ev_meta = nullptr;
         const size_t ni = (size_t)cat->n_in;
         dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
         dev_free(cat, cat->w, ni);

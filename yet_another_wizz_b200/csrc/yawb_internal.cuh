@@ -85,6 +85,10 @@ struct yawb_ctx {
     cudaEvent_t ev_i0 = nullptr, ev_i1 = nullptr;  // lazy index builds inside yawb_count
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user stopwatch
     unsigned long long *d_counters = nullptr;  // [8] work counter + statistics
+    // pinned arena for the meta data of in-flight uploads (bump allocated, reset when none is pending)
+    unsigned char *pin_base = nullptr;
+    size_t pin_size = 0, pin_used = 0;
+    int pin_live = 0;
 };
 
 struct yawb_cat {
@@ -103,6 +107,8 @@ struct yawb_cat {
     unsigned long long *hp_counts = nullptr;  // pinned staging [n_bins][n_patch]
     double *hp_sumw = nullptr;                // pinned staging [n_bins][n_patch]
     PatchFrame *hp_frames = nullptr;          // pinned staging [n_patch]
+    bool staging_in_arena = false;            // staging lives in the context's pinned arena
+    void *hp_block = nullptr;                 // or in its own pinned block
 
     // raw rows in upload order (grouped by patch)
     double *x = nullptr, *y = nullptr, *z = nullptr, *w = nullptr;
