@@ -463,6 +463,8 @@ def run_gpu_arm(args):
         ),
         breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=t_kernel * 1e3,
                           per_count={tag: stats_last[tag]["kernel_ms"] for tag in COUNT_TYPES},
+                          work_items={tag: int(stats_last[tag]["work_items"]) for tag in COUNT_TYPES},
+                          executed_tests={tag: int(stats_last[tag]["pair_tests"]) for tag in COUNT_TYPES},
                           host_prep_s=wl["t_host_prep"], catalogs_s=wl["t_catalogs"]),
         roofline=dict(
             bound="fp32", achieved=achieved / 1e9, peak=peak_tests / 1e9, unit="Gtests/s",

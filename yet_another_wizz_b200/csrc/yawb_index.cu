@@ -346,10 +346,12 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     local_uv(f, x[i], y[i], z[i], u, v);
     double su = f.umax > f.umin ? 65535.0 / (f.umax - f.umin) : 0.0;
     double sv = f.vmax > f.vmin ? 65535.0 / (f.vmax - f.vmin) : 0.0;
-    // isotropic quantisation keeps the curve's blocks square in (u, v)
-    double s = fmin(su > 0.0 ? su : sv, sv > 0.0 ? sv : su);
-    int qu = min(max((int)((u - f.umin) * s), 0), 65535);
-    int qv = min(max((int)((v - f.vmin) * s), 0), 65535);
+    // The bounding box of the patch is stretched over the whole Hilbert square: an isotropic mapping
+    // would leave part of the square empty, and wherever the curve leaves the populated part and
+    // re-enters elsewhere, 256 consecutive rows straddle the gap (measured: a few tiles per patch with
+    // patch-sized boxes, each worth several average work items -> a 13 % straggler tail).
+    int qu = min(max((int)((u - f.umin) * su), 0), 65535);
+    int qv = min(max((int)((v - f.vmin) * sv), 0), 65535);
     keys[i] = (K)(((unsigned long long)((long long)p * n_bins + b) << hbits) |
                   (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv) >> (32 - hbits)));
 }
