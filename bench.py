@@ -399,7 +399,8 @@ def run_gpu_arm(args):
 
     # ---- e2e: host buffers through the C ABI ----
     e2e_s = []
-    for step in range(max(1, min(args.warmup, 1)) + args.steps):
+    e2e_warm = max(1, args.warmup)
+    for step in range(e2e_warm + args.steps):
         barrier()
         t0 = time.perf_counter()
         dev = upload_all()
@@ -411,7 +412,7 @@ def run_gpu_arm(args):
             d.free()
         if rank == 0:
             log(f"[bench] e2e step {step}: {dt * 1e3:.1f} ms")
-        if step >= 1:
+        if step >= e2e_warm:
             e2e_s.append(max_over_ranks(dt))
 
     # statistics of the last timed step, summed over ranks

@@ -443,6 +443,12 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     }
 }
 
+__global__ void k_count_oversized(const Tile *__restrict__ tiles, int n_tiles, const float *__restrict__ thr,
+                                  unsigned *__restrict__ n_big) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tiles && tiles[t].count > 32 && tiles[t].rad > thr[tiles[t].patch]) atomicAdd(n_big, 1u);
+}
+
 template <typename K>
 int sort_pairs(yawb_ctx *ctx, Scratch &scr, K *keys_in, K *keys_out, unsigned *vals_in, unsigned *vals_out,
                long long n, int end_bit) {
@@ -734,13 +740,70 @@ int yawb_index_build_second(yawb_cat *cat) {
         }
     }
     cat->h_ptile_off[P] = (int)tiles.size();
+
+    // Straggler guard: a chunk of consecutive rows can straddle a place where the Hilbert curve leaves the
+    // populated part of the patch box and re-enters elsewhere (irregular footprints, masks).  Such a tile
+    // has a bounding sphere several times the typical one and would be worth many average work items.
+    // Tiles whose radius exceeds 3x the radius expected from the patch's mean density are cut into
+    // sub-tiles of 32 rows (rare; they run the same kernel with most register rows padded).  The common
+    // case costs one 4-byte read-back.
+    if (!tiles.empty()) {
+        Scratch scr(st);
+        Tile *d_tmp = scr.get<Tile>(tiles.size());
+        float *d_thr = scr.get<float>(P);
+        unsigned *d_nbig = scr.get<unsigned>(1);
+        YAWB_REQUIRE(d_tmp && d_thr && d_nbig, "out of device memory (tile table)");
+        std::vector<float> thr(P, 3.0e38f);
+        for (int p = 0; p < P; ++p) {
+            const PatchFrame &f = cat->h_frames[p];
+            const long long np = cat->h_seg_off[(size_t)(p + 1) * B] - cat->h_seg_off[(size_t)p * B];
+            const double area = std::max(f.umax - f.umin, 0.0) * std::max(f.vmax - f.vmin, 0.0);
+            if (np >= 8 * YAWB_TILE && area > 0.0)  // radius of a disc holding YAWB_TILE rows of one z-bin
+                thr[p] = (float)(3.0 * std::sqrt((double)YAWB_TILE * B * area / (3.14159265358979 * (double)np)));
+        }
+        YAWB_CUDA(cudaMemcpyAsync(d_tmp, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
+        YAWB_CUDA(cudaMemcpyAsync(d_thr, thr.data(), P * sizeof(float), cudaMemcpyHostToDevice, st));
+        YAWB_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
+        k_tile_spheres<<<blocks_for((long long)tiles.size() * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, d_tmp,
+                                                                                      (int)tiles.size());
+        k_count_oversized<<<blocks_for((long long)tiles.size()), kThreads, 0, st>>>(d_tmp, (int)tiles.size(), d_thr, d_nbig);
+        unsigned n_big = 0;
+        YAWB_CUDA(cudaMemcpyAsync(&n_big, d_nbig, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        YAWB_CUDA(cudaStreamSynchronize(st));
+        if (n_big > 0) {
+            YAWB_CUDA(cudaMemcpyAsync(tiles.data(), d_tmp, tiles.size() * sizeof(Tile), cudaMemcpyDeviceToHost, st));
+            YAWB_CUDA(cudaStreamSynchronize(st));
+            std::vector<Tile> out;
+            out.reserve(tiles.size() + 8 * (size_t)n_big);
+            std::vector<int> new_off(P + 1, 0);
+            for (int p = 0; p < P; ++p) {
+                new_off[p] = (int)out.size();
+                for (int t = cat->h_ptile_off[p]; t < cat->h_ptile_off[p + 1]; ++t) {
+                    const Tile &tl = tiles[t];
+                    if (tl.rad > thr[p] && tl.count > 32) {
+                        for (int s0 = 0; s0 < tl.count; s0 += 32) {
+                            Tile sub = tl;
+                            sub.start = tl.start + s0;
+                            sub.count = std::min(32, tl.count - s0);
+                            out.push_back(sub);
+                        }
+                    } else {
+                        out.push_back(tl);
+                    }
+                }
+            }
+            new_off[P] = (int)out.size();
+            tiles.swap(out);
+            cat->h_ptile_off = new_off;
+        }
+    }
     cat->n_tiles = (int)tiles.size();
     if (dev_alloc(cat, &cat->d_tiles, tiles.size()) || dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
     if (!tiles.empty())
         YAWB_CUDA(cudaMemcpyAsync(cat->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
     YAWB_CUDA(cudaMemcpyAsync(cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int),
                               cudaMemcpyHostToDevice, st));
-    if (cat->n_tiles > 0)
+    if (cat->n_tiles > 0)  // spheres of the final table (the split tiles need their own)
         k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz,
                                                                                       cat->d_tiles, cat->n_tiles);
     YAWB_CUDA(cudaGetLastError());
