@@ -475,6 +475,8 @@ def run_gpu_arm(args):
             executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(float(tot_stats[1]), 1.0),
             useful_fraction=sum(in_scale.values()) / max(executed, 1),
             fp64_rechecks=int(tot_stats[2]),
+            per_launch_frac={tag: (stats_last[tag]["pair_tests"] / max(stats_last[tag]["kernel_ms"], 1e-9) * 1e3) / peak_tests
+                             for tag in COUNT_TYPES},
         ),
         e2e=dict(value=total_naive / float(np.mean(e2e_s)) / 1e9, unit="Gpairs/s", ms_per_step=float(np.mean(e2e_s)) * 1e3,
                  h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
