@@ -120,6 +120,10 @@ COUNT_TYPES = dict(DD=("ref", "unk"), DR=("ref", "unk_rand"), RD=("ref_rand", "u
 
 # ---- clocks ------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle-reason samples taken while the timed regions run.  In-process NVML
+    (a few microseconds per sample); one `nvidia-smi` query costs ~0.3 s and was seen to stall a
+    concurrently running 10 ms step, so it is only the fallback."""
+
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -127,8 +131,36 @@ class ClockSampler:
     def __init__(self, index: int = 0):
         self.rows, self._stop, self.index = [], threading.Event(), index
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.source = "nvml"
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+        idx = self.index
+        if visible and visible[0].strip().isdigit() and idx < len(visible):
+            idx = int(visible[idx])
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
     def _run(self):
+        try:
+            nv, h = self._nvml_handle()
+            sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            while not self._stop.is_set():
+                r = get_reasons(h)
+                row = [nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), sm_max, nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                       "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if (r & bit) else "Not Active"
+                self.rows.append([str(c) for c in row])
+                self._stop.wait(0.01)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
@@ -156,7 +188,7 @@ class ClockSampler:
             if any(r[col].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
-                    samples=len(self.rows), power_w_max=max(float(r[2]) for r in self.rows))
+                    samples=len(self.rows), power_w_max=max(float(r[2]) for r in self.rows), source=self.source)
 
 
 # ---- CPU arm (oracle port of the reference's dual-tree path) --------------------------------------------
@@ -374,26 +406,26 @@ def run_gpu_arm(args):
     step_ms, kernel_ms, index_ms, stats_last, launches = [], [], [], None, 0
     clocks = ClockSampler(local_rank)
     results = None
-    with clocks:
-        for step in range(args.warmup + args.steps):
-            for d in dev.values():
-                d.drop_index()
-            barrier()
-            eng.timer_start()
-            results, stats = count_all(dev)  # builds the dropped indexes on first use, inside the timed region
-            t_idx = sum(s["index_ms"] for s in stats.values())
-            ms = eng.timer_stop()
-            results = reduce_results(results)
-            barrier()
-            if rank == 0:
-                log(f"[bench] step {step}: {ms:.2f} ms (index {t_idx:.2f}, kernels "
-                    f"{sum(s['kernel_ms'] for s in stats.values()):.2f})")
-            if step >= args.warmup:
-                step_ms.append(max_over_ranks(ms))
-                kernel_ms.append(sum(s["kernel_ms"] for s in stats.values()))
-                index_ms.append(t_idx)
-                stats_last = stats
-                launches += sum(s["launches"] for s in stats.values())
+    clocks.__enter__()  # sampled over both timed regions (value and e2e)
+    for step in range(args.warmup + args.steps):
+        for d in dev.values():
+            d.drop_index()
+        barrier()
+        eng.timer_start()
+        results, stats = count_all(dev)  # builds the dropped indexes on first use, inside the timed region
+        t_idx = sum(s["index_ms"] for s in stats.values())
+        ms = eng.timer_stop()
+        results = reduce_results(results)
+        barrier()
+        if rank == 0:
+            log(f"[bench] step {step}: {ms:.2f} ms (index {t_idx:.2f}, kernels "
+                f"{sum(s['kernel_ms'] for s in stats.values()):.2f})")
+        if step >= args.warmup:
+            step_ms.append(max_over_ranks(ms))
+            kernel_ms.append(sum(s["kernel_ms"] for s in stats.values()))
+            index_ms.append(t_idx)
+            stats_last = stats
+            launches += sum(s["launches"] for s in stats.values())
     for d in dev.values():
         d.free()
 
@@ -414,6 +446,7 @@ def run_gpu_arm(args):
             log(f"[bench] e2e step {step}: {dt * 1e3:.1f} ms")
         if step >= e2e_warm:
             e2e_s.append(max_over_ranks(dt))
+    clocks.__exit__()
 
     # statistics of the last timed step, summed over ranks
     tot_stats = np.array([sum(s[k] for s in stats_last.values()) for k in ("pair_tests", "pair_tests_naive", "rechecks")],
@@ -501,7 +534,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=list(WORKLOADS))

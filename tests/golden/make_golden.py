@@ -52,9 +52,12 @@ def grid_centers(nx, ny, ra0, ra1, dec0, dec1):
     )
 
 
-def make_catalog(tmp, name, ra, dec, centers, *, z=None, w=None):
+def make_catalog(tmp, name, ra, dec, centers, *, z=None, w=None, kappa=None):
     cols = dict(ra=ra, dec=dec)
     kw = dict(ra_name="ra", dec_name="dec", degrees=False, patch_centers=centers)
+    if kappa is not None:
+        cols["kappa"] = kappa
+        kw["kappa_name"] = "kappa"
     if z is not None:
         cols["z"] = z
         kw["redshift_name"] = "z"
@@ -66,9 +69,11 @@ def make_catalog(tmp, name, ra, dec, centers, *, z=None, w=None):
 
 def dump_catalog(prefix, cat, out):
     """concatenate the reference's per-patch cache content, patch-id order"""
-    ras, decs, zs, ws, pids = [], [], [], [], []
+    ras, decs, zs, ws, ks, pids = [], [], [], [], [], []
     for pid in sorted(cat.keys()):
         data = cat[pid].load_data()
+        if "kappa" in data.dtype.names:
+            ks.append(np.asarray(data["kappa"]))
         ras.append(np.asarray(data["ra"]))
         decs.append(np.asarray(data["dec"]))
         if cat.has_redshifts:
@@ -83,6 +88,8 @@ def dump_catalog(prefix, cat, out):
         out[f"{prefix}_z"] = np.concatenate(zs)
     if ws:
         out[f"{prefix}_w"] = np.concatenate(ws)
+    if ks:
+        out[f"{prefix}_kappa"] = np.concatenate(ks)
     out[f"{prefix}_centers"] = cat.get_centers().data
     out[f"{prefix}_radii"] = cat.get_radii().data
 
@@ -187,6 +194,47 @@ def case_auto(tmp, name, *, box, nx, ny, n, seed, zbins, rweight, resolution, we
     print(name, "DD sum", corrs[0].dd.counts.counts.sum(), "RR sum", corrs[0].rr.counts.counts.sum())
 
 
+def dump_scalar_counts(tag, corrs, out):
+    for s, corr in enumerate(corrs):
+        for kind in ("dd", "dr"):
+            nc = getattr(corr, kind)
+            if nc is None:
+                continue
+            out[f"{tag}_{kind}_kappa_counts_s{s}"] = nc.kappa_counts.counts
+            out[f"{tag}_{kind}_number_counts_s{s}"] = nc.number_counts.counts
+
+
+def case_scalar(tmp, name, *, box, nx, ny, n, seed, zbins, weighted, closed="right"):
+    """`crosscorrelate_scalar` with and without unknown randoms and `autocorrelate_scalar` on the
+    same kappa-carrying reference sample (measurements.py:651-794)."""
+    rng = np.random.default_rng(seed)
+    centers = grid_centers(nx, ny, *box)
+    n_ref, n_unk, n_ur = n
+    zlo, zhi = 0.1, 1.0
+    cats = {}
+    for key, npts, has_z in (("ref", n_ref, True), ("unk", n_unk, False), ("unk_rand", n_ur, False)):
+        ra, dec = box_points(rng, npts, *box)
+        z = rng.uniform(zlo - 0.05, zhi + 0.05, npts) if has_z else None
+        w = rng.uniform(0.5, 1.5, npts) if (weighted and key in ("ref", "unk")) else None
+        kappa = rng.normal(0.02, 0.3, npts) if key == "ref" else None
+        cats[key] = make_catalog(tmp, f"{name}_{key}", ra, dec, centers, z=z, w=w, kappa=kappa)
+    cfg = Configuration.create(
+        rmin=[100, 300], rmax=[1000, 1500], rweight=-0.5 if weighted else None, resolution=10 if weighted else None,
+        zmin=zlo, zmax=zhi, num_bins=zbins, closed=closed,
+    )
+    out = {}
+    for key, cat in cats.items():
+        dump_catalog(key, cat, out)
+    dump_config(cfg, out)
+    dump_scalar_counts("crossr", yaw.crosscorrelate_scalar(cfg, cats["ref"], cats["unk"], unk_rand=cats["unk_rand"]), out)
+    dump_scalar_counts("cross", yaw.crosscorrelate_scalar(cfg, cats["ref"], cats["unk"]), out)
+    dump_scalar_counts("auto", yaw.autocorrelate_scalar(cfg, cats["ref"]), out)
+    dump_links(cfg, [cats["ref"], cats["unk"], cats["unk_rand"]], out)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, "kn sum", out["crossr_dd_kappa_counts_s0"].sum(), "nn sum", out["crossr_dd_number_counts_s0"].sum(),
+          "kk sum", out["auto_dd_kappa_counts_s0"].sum())
+
+
 def case_edge(name, n=1500, theta=3.7e-3, seed=11):
     """adversarial: every matched pair (A_i, B_i) sits within a few ulp of the
     bin edge r = 2 sin(theta/2)."""
@@ -220,6 +268,12 @@ def case_edge(name, n=1500, theta=3.7e-3, seed=11):
 def main():
     tmp = tempfile.mkdtemp(prefix="yaw_golden_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
+        case_scalar(tmp, "scalar_weighted", box=(10.0, 12.0, -1.0, 1.0), nx=3, ny=2, n=(2000, 3000, 4000),
+                    seed=5, zbins=4, weighted=True)
+        case_scalar(tmp, "scalar_unweighted", box=(200.0, 202.0, 39.0, 41.0), nx=2, ny=2, n=(1500, 2500, 3000),
+                    seed=6, zbins=3, weighted=False, closed="left")
+        if "--scalar-only" in sys.argv:
+            return
         case_cross(tmp, "cross_unweighted", weighted=False, multiscale=False,
                    box=(10.0, 12.0, -1.0, 1.0), nx=3, ny=2, n=(2000, 3000, 4000, 4000), seed=1, zbins=5)
         case_cross(tmp, "cross_weighted_multiscale", weighted=True, multiscale=True,

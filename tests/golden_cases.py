@@ -20,7 +20,7 @@ def catalog_from_golden(g: dict, prefix: str):
     c = golden_io.catalog_arrays(g, prefix)
     return Catalog.from_arrays(
         c["ra"], c["dec"], patch_ids=c["patch"], patch_centers=AngularCoordinates(c["centers"]),
-        weights=c["w"], redshifts=c["z"], degrees=False,
+        weights=c["w"], redshifts=c["z"], kappa=c["kappa"], degrees=False,
     )
 
 
@@ -67,3 +67,34 @@ def run_auto(g, engine):
     config = config_from_golden(g)
     data, rand = catalog_from_golden(g, "data"), catalog_from_golden(g, "rand")
     return yb.autocorrelate(config, data, rand, engine=engine)
+
+
+def run_scalar(g, engine):
+    """the three scalar-field measurements stored in a `scalar_*` golden"""
+    import yet_another_wizz_b200 as yb
+
+    config = config_from_golden(g)
+    cats = {k: catalog_from_golden(g, k) for k in ("ref", "unk", "unk_rand")}
+    return dict(
+        crossr=yb.crosscorrelate_scalar(config, cats["ref"], cats["unk"], unk_rand=cats["unk_rand"], engine=engine),
+        cross=yb.crosscorrelate_scalar(config, cats["ref"], cats["unk"], engine=engine),
+        auto=yb.autocorrelate_scalar(config, cats["ref"], engine=engine),
+    )
+
+
+def check_scalar(g: dict, results: dict, exact_numbers: bool):
+    """kappa-weighted sums cancel (signed field): absolute tolerance relative to the largest entry"""
+    for tag, corrs in results.items():
+        kinds = ("dd",) if tag == "auto" else ("dd", "dr")
+        for s, corr in enumerate(corrs):
+            for kind in kinds:
+                nc = getattr(corr, kind)
+                want_k = g[f"{tag}_{kind}_kappa_counts_s{s}"]
+                want_n = g[f"{tag}_{kind}_number_counts_s{s}"]
+                assert np.abs(want_k).max() > 0 and want_n.sum() > 0
+                assert_allclose(nc.kappa_counts.counts, want_k, rtol=RTOL_WEIGHTED,
+                                atol=RTOL_WEIGHTED * np.abs(want_k).max())
+                if exact_numbers:
+                    assert_array_equal(nc.number_counts.counts, want_n)
+                else:
+                    assert_allclose(nc.number_counts.counts, want_n, rtol=RTOL_WEIGHTED, atol=0)

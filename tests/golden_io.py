@@ -15,10 +15,10 @@ def load(name: str) -> dict:
 
 
 def catalog_arrays(g: dict, prefix: str) -> dict:
-    """per-catalog arrays: ra, dec, patch, optional z / w, centers, radii"""
+    """per-catalog arrays: ra, dec, patch, optional z / w / kappa, centers, radii"""
     out = dict(
         ra=g[f"{prefix}_ra"], dec=g[f"{prefix}_dec"], patch=g[f"{prefix}_patch"],
-        z=g.get(f"{prefix}_z"), w=g.get(f"{prefix}_w"),
+        z=g.get(f"{prefix}_z"), w=g.get(f"{prefix}_w"), kappa=g.get(f"{prefix}_kappa"),
         centers=g[f"{prefix}_centers"], radii=g[f"{prefix}_radii"],
     )
     return out

@@ -40,6 +40,13 @@ def test_autocorrelate_golden(engine, name):
     golden_cases.check_corrfunc(g, "auto", corrs, ("dd", "dr", "rr"), exact=name == "auto_unweighted")
 
 
+@pytest.mark.parametrize("name", ["scalar_weighted", "scalar_unweighted"])
+def test_scalar_modes_golden(engine, name):
+    g = golden_io.load(name)
+    results = golden_cases.run_scalar(g, engine)
+    golden_cases.check_scalar(g, results, exact_numbers=name == "scalar_unweighted")
+
+
 def test_default_engine_and_stats():
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import measurements

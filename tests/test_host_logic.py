@@ -68,6 +68,26 @@ def test_autocorrelate_host_logic(name):
     assert corrs[0].rd is None and corrs[0].auto
 
 
+@pytest.mark.parametrize("name", ["scalar_weighted", "scalar_unweighted"])
+def test_scalar_modes_host_logic(name):
+    """crosscorrelate_scalar (with / without unknown randoms) and autocorrelate_scalar against the
+    reference's goldens: kappa x weight on the "k" side, NN companion counts, mean-kappa DR."""
+    g = golden_io.load(name)
+    results = golden_cases.run_scalar(g, OracleEngine())
+    golden_cases.check_scalar(g, results, exact_numbers=name == "scalar_unweighted")
+    assert results["cross"][0].dr is not None and results["auto"][0].dr is None
+
+
+def test_scalar_modes_need_kappa():
+    g = golden_io.load("cross_unweighted")
+    config = golden_cases.config_from_golden(g)
+    ref, unk = golden_cases.catalog_from_golden(g, "ref"), golden_cases.catalog_from_golden(g, "unk")
+    with pytest.raises(ValueError, match="kappa"):
+        yb.crosscorrelate_scalar(config, ref, unk, engine=OracleEngine())
+    with pytest.raises(ValueError, match="kappa"):
+        yb.autocorrelate_scalar(config, ref, engine=OracleEngine())
+
+
 def test_error_behaviour():
     g = golden_io.load("cross_unweighted")
     config = golden_cases.config_from_golden(g)

@@ -45,7 +45,7 @@ def test_boxrandoms_identical(yaw):
         assert_array_equal(mine[key], np.asarray(ref[key]))
 
 
-def _make_ref_catalogs(yaw, tmpdir, tag, weighted):
+def _make_ref_catalogs(yaw, tmpdir, tag, weighted, kappa=False):
     import pandas as pd
     from yaw import AngularCoordinates, Catalog
 
@@ -61,6 +61,9 @@ def _make_ref_catalogs(yaw, tmpdir, tag, weighted):
         if weighted and key in ("ref", "unk"):
             cols["w"] = rng.uniform(0.5, 1.5, n)
             kw["weight_name"] = "w"
+        if kappa and key == "ref":
+            cols["kappa"] = rng.normal(0.0, 0.3, n)
+            kw["kappa_name"] = "kappa"
         cats[key] = Catalog.from_dataframe(os.path.join(tmpdir, f"{tag}_{key}"), pd.DataFrame(cols), **kw)
     return cats
 
@@ -104,6 +107,34 @@ def test_dropin_with_reference_objects(yaw, tmpdir, weighted):
             assert_allclose(a.counts.counts, b.counts.counts, rtol=1e-12, atol=0)
             assert_allclose(a.sum_weights.get_array(), b.sum_weights.get_array(), rtol=1e-12)
             assert_allclose(a.sample_patch_sum().samples, b.sample_patch_sum().samples, rtol=1e-10)
+
+
+def test_scalar_dropin_with_reference_objects(yaw, tmpdir):
+    """yaw.Catalog objects carrying `kappa` through crosscorrelate_scalar / autocorrelate_scalar"""
+    import yet_another_wizz_b200 as yb
+
+    cats = _make_ref_catalogs(yaw, tmpdir, "kappa", True, kappa=True)
+    config = yaw.Configuration.create(rmin=[100, 400], rmax=[1000, 2000], zmin=0.1, zmax=0.9, num_bins=4)
+    runs = [
+        (yaw.crosscorrelate_scalar(config, cats["ref"], cats["unk"], unk_rand=cats["unk_rand"]),
+         yb.crosscorrelate_scalar(config, cats["ref"], cats["unk"], unk_rand=cats["unk_rand"], engine=OracleEngine())),
+        (yaw.crosscorrelate_scalar(config, cats["ref"], cats["unk"]),
+         yb.crosscorrelate_scalar(config, cats["ref"], cats["unk"], engine=OracleEngine())),
+        (yaw.autocorrelate_scalar(config, cats["ref"]),
+         yb.autocorrelate_scalar(config, cats["ref"], engine=OracleEngine())),
+    ]
+    for want, got in runs:
+        assert len(want) == len(got) == 2
+        for w, g in zip(want, got):
+            for kind in ("dd", "dr"):
+                b, a = getattr(w, kind), getattr(g, kind)
+                assert (a is None) == (b is None)
+                if b is None:
+                    continue
+                scale = np.abs(b.kappa_counts.counts).max()
+                assert_allclose(a.kappa_counts.counts, b.kappa_counts.counts, rtol=1e-12, atol=1e-12 * scale)
+                assert_allclose(a.number_counts.counts, b.number_counts.counts, rtol=1e-12, atol=0)
+                assert_allclose(a.sample_patch_sum().data, b.sample_patch_sum().data, rtol=1e-9, atol=1e-12)
 
 
 def test_read_reference_cache(yaw, tmpdir):

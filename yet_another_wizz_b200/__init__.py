@@ -12,14 +12,15 @@ from .binning import Binning
 from .catalog import Catalog, InconsistentPatchesError
 from .config import Configuration
 from .coordinates import AngularCoordinates, AngularDistances
-from .corrfunc import CorrFunc
+from .corrfunc import CorrFunc, ScalarCorrFunc
 from .engine import DeviceCatalog, Engine
-from .measurements import PatchLinkage, autocorrelate, crosscorrelate
+from .measurements import (PatchLinkage, autocorrelate, autocorrelate_scalar, crosscorrelate,
+                           crosscorrelate_scalar)
 from .randoms import BoxRandoms
 
 __all__ = [
     "AngularCoordinates", "AngularDistances", "Binning", "BoxRandoms", "Catalog", "Configuration", "CorrFunc",
-    "DeviceCatalog", "Engine", "InconsistentPatchesError", "PatchLinkage", "YawbError", "autocorrelate",
-    "crosscorrelate",
+    "DeviceCatalog", "Engine", "InconsistentPatchesError", "PatchLinkage", "ScalarCorrFunc", "YawbError",
+    "autocorrelate", "autocorrelate_scalar", "crosscorrelate", "crosscorrelate_scalar",
 ]
 __version__ = "0.1.0"

@@ -65,12 +65,14 @@ class Metadata:
                 f"center={self.center.data[0]}, radius={self.radius.data[0]})")
 
 
-def _structured(ra, dec, weights, redshifts) -> np.ndarray:
+def _structured(ra, dec, weights, redshifts, kappa=None) -> np.ndarray:
     fields = [("ra", "f8"), ("dec", "f8")]
     if weights is not None:
         fields.append(("weights", "f8"))
     if redshifts is not None:
         fields.append(("redshifts", "f8"))
+    if kappa is not None:
+        fields.append(("kappa", "f8"))
     data = np.empty(len(ra), dtype=np.dtype(fields))
     data["ra"] = ra
     data["dec"] = dec
@@ -78,6 +80,8 @@ def _structured(ra, dec, weights, redshifts) -> np.ndarray:
         data["weights"] = weights
     if redshifts is not None:
         data["redshifts"] = redshifts
+    if kappa is not None:
+        data["kappa"] = kappa
     return data
 
 
@@ -108,6 +112,10 @@ class Patch:
     @property
     def has_redshifts(self) -> bool:
         return "redshifts" in self.load_data().dtype.names if self._data is not None else _cache_flags(self._path)[1]
+
+    @property
+    def has_kappa(self) -> bool:
+        return "kappa" in self.load_data().dtype.names
 
     @property
     def coords(self) -> AngularCoordinates:
@@ -163,13 +171,14 @@ class Catalog(Mapping):
     # ---- constructors -----------------------------------------------------------------------
     @classmethod
     def from_arrays(cls, ra, dec, *, patch_centers=None, patch_ids=None, weights=None, redshifts=None,
-                    degrees: bool = True, cache_directory=None) -> "Catalog":
+                    kappa=None, degrees: bool = True, cache_directory=None) -> "Catalog":
         ra = np.asarray(ra, dtype=np.float64)
         dec = np.asarray(dec, dtype=np.float64)
         if degrees:
             ra, dec = np.deg2rad(ra), np.deg2rad(dec)
         weights = None if weights is None else np.asarray(weights, dtype=np.float64)
         redshifts = None if redshifts is None else np.asarray(redshifts, dtype=np.float64)
+        kappa = None if kappa is None else np.asarray(kappa, dtype=np.float64)
         if patch_centers is None and patch_ids is None:
             raise ValueError("one of 'patch_centers' and 'patch_ids' must be provided")
         centers = None
@@ -190,7 +199,8 @@ class Catalog(Mapping):
         for pid, s, e in zip(uniq.tolist(), starts, ends):
             sel = order[s:e]
             data = _structured(ra[sel], dec[sel], None if weights is None else weights[sel],
-                               None if redshifts is None else redshifts[sel])
+                               None if redshifts is None else redshifts[sel],
+                               None if kappa is None else kappa[sel])
             center = None if centers is None else centers[int(pid)]
             patches[int(pid)] = Patch(data, center=center)
         return cls(patches, cache_directory)
@@ -198,7 +208,7 @@ class Catalog(Mapping):
     @classmethod
     def from_dataframe(cls, cache_directory, dataframe, *, ra_name, dec_name, weight_name=None,
                        redshift_name=None, patch_centers=None, patch_name=None, patch_num=None,
-                       degrees: bool = True, **_ignored) -> "Catalog":
+                       kappa_name=None, degrees: bool = True, **_ignored) -> "Catalog":
         """Signature of `yaw.Catalog.from_dataframe` (`src/yaw/catalog/catalog.py:980-1108`);
         `patch_num` (treecorr k-means) is not supported -- pass centres or a patch column."""
         if patch_num is not None and patch_centers is None and patch_name is None:
@@ -207,7 +217,7 @@ class Catalog(Mapping):
         return cls.from_arrays(
             get(ra_name), get(dec_name), patch_centers=patch_centers,
             patch_ids=None if patch_centers is not None else get(patch_name),
-            weights=get(weight_name), redshifts=get(redshift_name), degrees=degrees,
+            weights=get(weight_name), redshifts=get(redshift_name), kappa=get(kappa_name), degrees=degrees,
             cache_directory=cache_directory,
         )
 
@@ -266,6 +276,10 @@ class Catalog(Mapping):
     @property
     def has_redshifts(self) -> bool:
         return all(p.has_redshifts for p in self.values())
+
+    @property
+    def has_kappa(self) -> bool:
+        return all(p.has_kappa for p in self.values())
 
     def get_num_records(self) -> tuple[int, ...]:
         return tuple(p.meta.num_records for p in self.values())

@@ -9,9 +9,9 @@ Estimators, jackknife covariance and n(z) stay on the reference's host code: cal
 
 from __future__ import annotations
 
-from .paircounts import NormalisedCounts, write_version_tag
+from .paircounts import NormalisedCounts, NormalisedScalarCounts, write_version_tag
 
-__all__ = ["CorrFunc", "EstimatorError"]
+__all__ = ["CorrFunc", "EstimatorError", "ScalarCorrFunc"]
 
 _COUNTS_NAME = dict(dd="data_data", dr="data_random", rd="random_data", rr="random_random")
 
@@ -108,3 +108,39 @@ class CorrFunc:
             return ref_pc.NormalisedCounts(counts, sumw)
 
         return yaw.CorrFunc(**{kind: convert(nc) for kind, nc in self._counts_dict.items()})
+
+
+class ScalarCorrFunc:
+    """`ScalarCorrFunc(dd, dr)` returned by `crosscorrelate_scalar` / `autocorrelate_scalar` (mirrors
+    `yaw.ScalarCorrFunc`, reference `src/yaw/correlation/corrfunc.py:352-400`; HDF5 groups `data_data`,
+    `data_random`)."""
+
+    __slots__ = ("_counts_dict",)
+
+    def __init__(self, dd: NormalisedScalarCounts, dr: NormalisedScalarCounts | None = None) -> None:
+        if type(dd) is not NormalisedScalarCounts:
+            raise TypeError(f"pair counts must be of type {NormalisedScalarCounts}")
+        self._counts_dict = dict(dd=dd)
+        if dr is not None:
+            if dr.num_patches != dd.num_patches or dr.binning != dd.binning:
+                raise ValueError("pair counts 'dr' and 'dd' are not compatible")
+            self._counts_dict["dr"] = dr
+
+    dd = property(lambda self: self._counts_dict["dd"])
+    dr = property(lambda self: self._counts_dict.get("dr"))
+    binning = property(lambda self: self.dd.binning)
+    auto = property(lambda self: self.dd.auto)
+    num_patches = property(lambda self: self.dd.num_patches)
+
+    def __repr__(self) -> str:
+        return (f"ScalarCorrFunc(counts={'|'.join(self._counts_dict)}, auto={self.auto}, "
+                f"binning={self.binning}, num_patches={self.num_patches})")
+
+    def to_dict(self) -> dict:
+        return self._counts_dict.copy()
+
+    def to_hdf(self, dest) -> None:
+        write_version_tag(dest)
+        dest.create_dataset("kind", data="ScalarCorrFunc")
+        for kind, count in self._counts_dict.items():
+            count.to_hdf(dest.create_group(dict(dd="data_data", dr="data_random")[kind]))

@@ -29,11 +29,12 @@ from .angular import AngularBinPlan
 from .binning import Binning
 from .catalog import InconsistentPatchesError
 from .coordinates import AngularCoordinates, AngularDistances
-from .corrfunc import CorrFunc
-from .paircounts import NormalisedCounts, PatchedCounts, PatchedSumWeights
+from .corrfunc import CorrFunc, ScalarCorrFunc
+from .paircounts import NormalisedCounts, NormalisedScalarCounts, PatchedCounts, PatchedSumWeights
 from .sharding import Shard, assign_pairs_lpt, current_shard, pair_costs
 
-__all__ = ["PatchLinkage", "autocorrelate", "crosscorrelate", "get_default_engine", "last_stats"]
+__all__ = ["PatchLinkage", "autocorrelate", "autocorrelate_scalar", "compute_scalar_normalisation", "crosscorrelate",
+           "crosscorrelate_scalar", "get_default_engine", "last_stats"]
 
 logger = logging.getLogger("yaw_b200")
 
@@ -73,7 +74,8 @@ def _patch_rows(patch):
     dec = np.asarray(data["dec"], dtype=np.float64)
     weights = np.asarray(data["weights"], dtype=np.float64) if "weights" in names else None
     redshifts = np.asarray(data["redshifts"], dtype=np.float64) if "redshifts" in names else None
-    return ra, dec, weights, redshifts
+    kappa = np.asarray(data["kappa"], dtype=np.float64) if "kappa" in names else None
+    return ra, dec, weights, redshifts, kappa
 
 
 def _angles_per_bin(config) -> tuple[np.ndarray, np.ndarray]:
@@ -88,22 +90,29 @@ def _angles_per_bin(config) -> tuple[np.ndarray, np.ndarray]:
     return np.array(amin, dtype=np.float64), np.array(amax, dtype=np.float64)
 
 
-def prepare_catalog_arrays(catalog, binning: Binning | None) -> dict:
+def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = False) -> dict:
     """Host preparation of one catalog for the C ABI: load every patch once, convert to unit
     vectors with the reference's formula (`AngularCoordinates.to_3d`), digitise the redshifts
-    (`trees.py:408-414`).  Returns the keyword arguments of `Engine.upload_catalog`."""
+    (`trees.py:408-414`).  Returns the keyword arguments of `Engine.upload_catalog`.
+
+    `kappa=True` prepares the "k" side of a scalar-field count: the per-row pair weight is
+    kappa x weight (kappa alone without weights), `AngularTree.get_pair_weights`, `trees.py:270-301`."""
     xyz, ws, zb, sizes = [], [], [], []
-    has_w = bool(catalog.has_weights)
+    has_w = bool(catalog.has_weights) or kappa
     if binning is not None and not catalog.has_redshifts:
         raise ValueError("patch has no 'redshifts' attached")  # trees.py:397-398
     patch_ids = list(catalog.keys())
     if patch_ids != list(range(len(patch_ids))):
         raise InconsistentPatchesError("patch IDs must be 0..num_patches-1")
     for pid in patch_ids:
-        ra, dec, weights, redshifts = _patch_rows(catalog[pid])
+        ra, dec, weights, redshifts, kappa_vals = _patch_rows(catalog[pid])
         xyz.append(AngularCoordinates(np.column_stack([ra, dec])).to_3d())
         sizes.append(len(ra))
-        if has_w:
+        if kappa:
+            if kappa_vals is None:
+                raise ValueError("missing required 'kappa'")
+            ws.append(kappa_vals if weights is None else kappa_vals * weights)
+        elif has_w:
             ws.append(weights)
         if binning is not None:
             zb.append(binning.digitize(redshifts))
@@ -116,9 +125,9 @@ def prepare_catalog_arrays(catalog, binning: Binning | None) -> dict:
     )
 
 
-def upload_catalog(engine, catalog, binning: Binning | None):
+def upload_catalog(engine, catalog, binning: Binning | None, *, kappa: bool = False):
     """Replaces `Catalog.build_trees`: one upload, the index is built on the device."""
-    arrays = prepare_catalog_arrays(catalog, binning)
+    arrays = prepare_catalog_arrays(catalog, binning, kappa=kappa)
     return engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
 
 
@@ -127,12 +136,12 @@ class _Uploads:
 
     def __init__(self, engine) -> None:
         self.engine = engine
-        self._cache: dict[tuple[int, bool], object] = {}
+        self._cache: dict[tuple[int, bool, bool], object] = {}
 
-    def get(self, catalog, binning: Binning | None):
-        key = (id(catalog), binning is not None)
+    def get(self, catalog, binning: Binning | None, kappa: bool = False):
+        key = (id(catalog), binning is not None, kappa)
         if key not in self._cache:
-            self._cache[key] = upload_catalog(self.engine, catalog, binning)
+            self._cache[key] = upload_catalog(self.engine, catalog, binning, kappa=kappa)
         return self._cache[key]
 
     def free(self) -> None:
@@ -241,8 +250,9 @@ class PatchLinkage:
         """Pair counts between the patches of two catalogs; omit `optional_catalog` for an
         autocorrelation.  `binned_second` states whether the second catalog is paired bin by bin
         (autocorrelate DR) or as a whole with every z-bin (crosscorrelate's unknown sample)."""
-        if mode != "nn":
-            raise NotImplementedError("scalar-field modes (nk/kn/kk) are not part of the GPU path yet")
+        if mode not in ("nn", "nk", "kn", "kk"):
+            raise ValueError(f"invalid count mode '{mode}'")
+        kappa1, kappa2 = mode[0] == "k", mode[1] == "k"
         if count_type_info is not None:
             logger.info("counting %s from patch pairs", count_type_info)
         auto = len(optional_catalog) == 0
@@ -257,11 +267,22 @@ class PatchLinkage:
         num_bins, num_patches = len(binning), len(main_catalog)
         plan = self._get_plan()
         pair_i, pair_j = self.get_patch_id_pairs(auto=auto)
+        # the "k" side of a scalar-field count carries kappa x weight per row (trees.py:270-301)
+        has1, has2 = _has_kappa(main_catalog), _has_kappa(second)
+        if kappa1 and kappa2 and not (has1 and has2):
+            raise ValueError("missing required 'kappa' for both tree.")
+        if kappa1 and not has1:
+            raise ValueError("missing required 'kappa' for first tree.")
+        if kappa2 and not has2:
+            raise ValueError("missing required 'kappa' for second tree.")
 
         try:
-            dev1 = uploads.get(main_catalog, binning)
-            dev2 = dev1 if auto else uploads.get(second, binning if binned_second else None)
-            sw1_all, sw2_all = dev1.sum_weights(), dev2.sum_weights()
+            bins2 = binning if binned_second else None
+            dev1 = uploads.get(main_catalog, binning, kappa1)
+            dev2 = dev1 if (auto and kappa1 == kappa2) else uploads.get(second, bins2, kappa2)
+            # the reported sums are always the plain sum of weights (`AngularTree.sum_weights`)
+            sw1_all = (uploads.get(main_catalog, binning) if kappa1 else dev1).sum_weights()
+            sw2_all = (uploads.get(second, bins2) if kappa2 else dev2).sum_weights()
 
             own = np.arange(len(pair_i))
             if shard.active:
@@ -303,6 +324,34 @@ class PatchLinkage:
         if any(cat is None for cat in (main_catalog, *optional_catalog)):
             return [None for _ in range(self.config.scales.num_scales)]
         return self.count_pairs(main_catalog, *optional_catalog, **kwargs)
+
+
+    def count_scalar_pairs(self, main_catalog, *optional_catalog, progress: bool = False, max_workers=None,
+                           mode: str = "nn", count_type_info: str | None = None,
+                           binned_second: bool | None = None) -> list[NormalisedScalarCounts]:
+        """Scalar-field pair counts: one pass in `mode` ("kn" / "kk"), one in "nn" over the same patch
+        pairs, combined per scale (`PatchLinkage.count_scalar_pairs`, `measurements.py:394-429`)."""
+        own_uploads = self._uploads is None
+        if own_uploads:
+            self._uploads = _Uploads(self.engine or get_default_engine())
+        try:
+            counts = {
+                m: self.count_pairs(main_catalog, *optional_catalog, mode=m, count_type_info=count_type_info,
+                                    binned_second=binned_second)
+                for m in (mode, "nn")
+            }
+        finally:
+            if own_uploads:
+                self._uploads.free()
+                self._uploads = None
+        return [NormalisedScalarCounts(kk.counts, nn.counts) for kk, nn in zip(counts[mode], counts["nn"])]
+
+
+def _has_kappa(catalog) -> bool:
+    has = getattr(catalog, "has_kappa", None)
+    if has is not None:
+        return bool(has)
+    return all(p.has_kappa for p in catalog.values())
 
 
 # ---- public API -----------------------------------------------------------------------------------------
@@ -363,3 +412,64 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
         links._uploads.free()
         links._uploads = None
     return [CorrFunc(dd, dr, rd, rr) for dd, dr, rd, rr in zip(DD, DR, RD, RR)]
+
+
+# ---- scalar-field correlations (NK / KK) ----------------------------------------------------------------
+def compute_scalar_normalisation(catalog, binning: Binning, *, engine=None, uploads: "_Uploads | None" = None
+                                 ) -> NormalisedScalarCounts:
+    """Mean-kappa correction per patch and z-bin: sum(kappa x w) and sum(w) on the diagonal of two
+    `PatchedCounts` (`compute_scalar_normalisation`, `measurements.py:634-648`).  Both sums are the
+    per-(bin, patch) weight sums the device already computes for its catalogs."""
+    own = uploads is None
+    uploads = uploads or _Uploads(engine or get_default_engine())
+    try:
+        num_bins, num_patches = len(binning), len(catalog)
+        sum_kappa = np.zeros((num_bins, num_patches, num_patches))
+        sum_weights = np.zeros_like(sum_kappa)
+        diag = np.arange(num_patches)
+        sum_kappa[:, diag, diag] = uploads.get(catalog, binning, True).sum_weights()
+        sum_weights[:, diag, diag] = uploads.get(catalog, binning).sum_weights()
+    finally:
+        if own:
+            uploads.free()
+    return NormalisedScalarCounts(PatchedCounts(binning, sum_kappa, auto=False),
+                                  PatchedCounts(binning, sum_weights, auto=False))
+
+
+def autocorrelate_scalar(config, data, *, progress: bool = False, max_workers=None, engine=None,
+                         shard: Shard | None = None) -> list[ScalarCorrFunc]:
+    """Angular autocorrelation of a scalar field in z-bins: KK and NN counts of the data sample.
+    Signature and result layout of `yaw.autocorrelate_scalar` (`measurements.py:651-705`)."""
+    links = PatchLinkage.from_catalogs(config, data, engine=engine, shard=shard)
+    links._uploads = _Uploads(engine or get_default_engine())
+    _last_stats.clear()
+    try:
+        DD = links.count_scalar_pairs(data, mode="kk", count_type_info="DD")
+    finally:
+        links._uploads.free()
+        links._uploads = None
+    return [ScalarCorrFunc(dd) for dd in DD]
+
+
+def crosscorrelate_scalar(config, reference, unknown, *, unk_rand=None, progress: bool = False,
+                          max_workers=None, engine=None, shard: Shard | None = None) -> list[ScalarCorrFunc]:
+    """Angular cross-correlation between a z-binned scalar-field sample (`reference`, carries
+    `kappa`) and the unbinned `unknown` sample: KN and NN counts for DD and, with `unk_rand`,
+    for DR; without it DR is the per-patch mean-kappa normalisation.  Signature and result layout
+    of `yaw.crosscorrelate_scalar` (`measurements.py:708-794`)."""
+    _ensure_unique_catalogs(reference, unknown, unk_rand)
+    randoms = [unk_rand] if unk_rand is not None else []
+    links = PatchLinkage.from_catalogs(config, reference, unknown, *randoms, engine=engine, shard=shard)
+    links._uploads = _Uploads(engine or get_default_engine())
+    _last_stats.clear()
+    kw = dict(binned_second=False, mode="kn")
+    try:
+        DD = links.count_scalar_pairs(reference, unknown, count_type_info="DD", **kw)
+        if unk_rand is None:
+            DR = [compute_scalar_normalisation(reference, _as_binning(config), uploads=links._uploads)] * len(DD)
+        else:
+            DR = links.count_scalar_pairs(reference, unk_rand, count_type_info="DR", **kw)
+    finally:
+        links._uploads.free()
+        links._uploads = None
+    return [ScalarCorrFunc(dd, dr) for dd, dr in zip(DD, DR)]

@@ -18,7 +18,7 @@ import numpy as np
 
 from .binning import Binning
 
-__all__ = ["NormalisedCounts", "PatchedCounts", "PatchedSumWeights", "SampledPatchSum"]
+__all__ = ["NormalisedCounts", "NormalisedScalarCounts", "PatchedCounts", "PatchedSumWeights", "SampledPatchSum"]
 
 HDF_COMPRESSION = dict(fletcher32=True, compression="gzip", shuffle=True)  # src/yaw/utils/misc.py:36
 FORMAT_VERSION = "3.1.1"  # version tag of the reference whose layout is written
@@ -214,3 +214,44 @@ class NormalisedCounts:
     @classmethod
     def from_hdf(cls, source) -> "NormalisedCounts":
         return cls(PatchedCounts.from_hdf(source["counts"]), PatchedSumWeights.from_hdf(source["sum_weights"]))
+
+
+class NormalisedScalarCounts:
+    """Pair counts weighted by a scalar field, normalised by the plain pair counts of the same patch pairs
+    (mirrors `yaw.correlation.paircounts.NormalisedScalarCounts`, reference `paircounts.py:619-666`;
+    HDF5 groups `kappa_counts` / `number_counts`)."""
+
+    __slots__ = ("_counts", "_weights")
+
+    def __init__(self, kappa_counts: PatchedCounts, number_counts: PatchedCounts) -> None:
+        if kappa_counts.num_patches != number_counts.num_patches:
+            raise ValueError("number of patches of counts- and weights-container does not match")
+        if kappa_counts.num_bins != number_counts.num_bins:
+            raise ValueError("number of bins of counts- and weights-container does not match")
+        self._counts = kappa_counts
+        self._weights = number_counts
+
+    kappa_counts = property(lambda self: self._counts)
+    number_counts = property(lambda self: self._weights)
+    binning = property(lambda self: self._counts.binning)
+    auto = property(lambda self: self._counts.auto)
+    num_bins = property(lambda self: self._counts.num_bins)
+    num_patches = property(lambda self: self._counts.num_patches)
+
+    def __eq__(self, other) -> bool:
+        if type(self) is not type(other):
+            return NotImplemented
+        return self._counts == other._counts and self._weights == other._weights
+
+    def sample_patch_sum(self) -> SampledPatchSum:
+        c, w = self._counts.sample_patch_sum(), self._weights.sample_patch_sum()
+        return SampledPatchSum(self.binning, c.data / w.data, c.samples / w.samples)
+
+    def to_hdf(self, dest) -> None:
+        write_version_tag(dest)
+        self._counts.to_hdf(dest.create_group("kappa_counts"))
+        self._weights.to_hdf(dest.create_group("number_counts"))
+
+    @classmethod
+    def from_hdf(cls, source) -> "NormalisedScalarCounts":
+        return cls(PatchedCounts.from_hdf(source["kappa_counts"]), PatchedCounts.from_hdf(source["number_counts"]))
