@@ -235,6 +235,45 @@ def case_scalar(tmp, name, *, box, nx, ny, n, seed, zbins, weighted, closed="rig
           "kk sum", out["auto_dd_kappa_counts_s0"].sum())
 
 
+def case_example(tmp, name="example_2dflens"):
+    """The reference's bundled 2dFLenS example (SURVEY.md section 8c ii): recipe of the reference's
+    `create_example_data.py`, with the catalogs read from the bundled parquet files.  The generator
+    itself checks that the reference, run here, reproduces its own golden `examples/estimate.{dat,smp,cov}`
+    to the 7 decimals those files carry, then stores inputs, per-patch-pair counts and the n(z)."""
+    from yaw import RedshiftData
+
+    exdir = os.path.join(os.path.dirname(yaw.__file__), "examples")
+    kw = dict(ra_name="RA", dec_name="Dec", redshift_name="redshift", weight_name="wei", patch_name="patch")
+    data = Catalog.from_file(os.path.join(tmp, f"{name}_ref"), os.path.join(exdir, "2dflens_kidss_data.pqt"), **kw)
+    unk = Catalog.from_file(os.path.join(tmp, f"{name}_unk"), os.path.join(exdir, "2dflens_kidss_data.pqt"), **kw)
+    rand = Catalog.from_file(os.path.join(tmp, f"{name}_rand"), os.path.join(exdir, "2dflens_kidss_rand_5x.pqt"), **kw)
+    cfg = Configuration.create(rmin=100, rmax=1000, zmin=0.15, zmax=0.7, num_bins=11)  # examples/__init__.py:271
+    cross = yaw.crosscorrelate(cfg, data, unk, ref_rand=rand)
+    auto = yaw.autocorrelate(cfg, data, rand)
+    nz = RedshiftData.from_corrfuncs(cross[0], auto[0])
+
+    want = np.loadtxt(os.path.join(exdir, "estimate.dat"))
+    want_smp = np.loadtxt(os.path.join(exdir, "estimate.smp"))[:, 2:].T
+    want_cov = np.loadtxt(os.path.join(exdir, "estimate.cov"))
+    for got, ref, what in ((nz.data, want[:, 2], "dat"), (nz.error, want[:, 3], "err"),
+                           (nz.samples, want_smp, "smp"), (nz.covariance, want_cov, "cov")):
+        diff = np.nanmax(np.abs(np.asarray(got) - ref))
+        print(name, what, "max abs difference to the bundled golden:", diff)
+        assert diff < 2e-7, what
+
+    out = {}
+    dump_catalog("ref", data, out)
+    dump_catalog("rand", rand, out)
+    dump_config(cfg, out)
+    dump_counts("cross", cross, out)
+    dump_counts("auto", auto, out)
+    dump_links(cfg, [data, unk, rand], out)
+    out["nz_data"], out["nz_error"], out["nz_samples"] = nz.data, nz.error, nz.samples
+    out["bundled_nz_data"], out["bundled_nz_error"], out["bundled_nz_samples"] = want[:, 2], want[:, 3], want_smp
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(name, "cross DD sum", cross[0].dd.counts.counts.sum(), "auto DD sum", auto[0].dd.counts.counts.sum())
+
+
 def case_edge(name, n=1500, theta=3.7e-3, seed=11):
     """adversarial: every matched pair (A_i, B_i) sits within a few ulp of the
     bin edge r = 2 sin(theta/2)."""
@@ -268,11 +307,17 @@ def case_edge(name, n=1500, theta=3.7e-3, seed=11):
 def main():
     tmp = tempfile.mkdtemp(prefix="yaw_golden_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
+        if "--example-only" in sys.argv:
+            case_example(tmp)
+            return
         case_scalar(tmp, "scalar_weighted", box=(10.0, 12.0, -1.0, 1.0), nx=3, ny=2, n=(2000, 3000, 4000),
                     seed=5, zbins=4, weighted=True)
         case_scalar(tmp, "scalar_unweighted", box=(200.0, 202.0, 39.0, 41.0), nx=2, ny=2, n=(1500, 2500, 3000),
                     seed=6, zbins=3, weighted=False, closed="left")
         if "--scalar-only" in sys.argv:
+            return
+        case_example(tmp)
+        if "--example-only" in sys.argv:
             return
         case_cross(tmp, "cross_unweighted", weighted=False, multiscale=False,
                    box=(10.0, 12.0, -1.0, 1.0), nx=3, ny=2, n=(2000, 3000, 4000, 4000), seed=1, zbins=5)

@@ -98,3 +98,25 @@ def check_scalar(g: dict, results: dict, exact_numbers: bool):
                     assert_array_equal(nc.number_counts.counts, want_n)
                 else:
                     assert_allclose(nc.number_counts.counts, want_n, rtol=RTOL_WEIGHTED, atol=0)
+
+
+def run_example(g, engine):
+    """the reference's bundled 2dFLenS example: the data sample is both reference and unknown sample"""
+    import yet_another_wizz_b200 as yb
+
+    config = config_from_golden(g)
+    ref, rand = catalog_from_golden(g, "ref"), catalog_from_golden(g, "rand")
+    unk = catalog_from_golden(g, "ref")
+    cross = yb.crosscorrelate(config, ref, unk, ref_rand=rand, engine=engine)
+    auto = yb.autocorrelate(config, ref, rand, engine=engine)
+    return cross, auto
+
+
+def check_example(g, cross, auto):
+    assert len(cross) == len(auto) == 1
+    check_corrfunc(g, "cross", cross, ("dd", "rd"), exact=False)
+    check_corrfunc(g, "auto", auto, ("dd", "dr", "rr"), exact=False)
+    assert cross[0].dr is None and cross[0].rr is None
+    # totals quoted in SURVEY.md section 8c (ii)
+    assert abs(cross[0].dd.counts.counts.sum() - 1203.77777951) < 1e-7
+    assert abs(auto[0].dd.counts.counts.sum() - 154.771866) < 1e-7

@@ -47,6 +47,14 @@ def test_scalar_modes_golden(engine, name):
     golden_cases.check_scalar(g, results, exact_numbers=name == "scalar_unweighted")
 
 
+def test_bundled_example_golden(engine):
+    """the reference's own example data set (SURVEY.md section 8c ii): counts that reproduce its
+    golden n(z) files, see tests/golden/make_golden.py::case_example"""
+    g = golden_io.load("example_2dflens")
+    cross, auto = golden_cases.run_example(g, engine)
+    golden_cases.check_example(g, cross, auto)
+
+
 def test_default_engine_and_stats():
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import measurements

@@ -78,6 +78,13 @@ def test_scalar_modes_host_logic(name):
     assert results["cross"][0].dr is not None and results["auto"][0].dr is None
 
 
+def test_bundled_example_host_logic():
+    """per-patch-pair counts of the reference's bundled 2dFLenS example (11 patches, weighted)"""
+    g = golden_io.load("example_2dflens")
+    cross, auto = golden_cases.run_example(g, OracleEngine())
+    golden_cases.check_example(g, cross, auto)
+
+
 def test_scalar_modes_need_kappa():
     g = golden_io.load("cross_unweighted")
     config = golden_cases.config_from_golden(g)

@@ -137,6 +137,22 @@ def test_scalar_dropin_with_reference_objects(yaw, tmpdir):
                 assert_allclose(a.sample_patch_sum().data, b.sample_patch_sum().data, rtol=1e-9, atol=1e-12)
 
 
+def test_bundled_example_reproduces_golden_nz(yaw):
+    """counts of this package -> the reference's own estimator and jackknife -> the golden n(z) the
+    reference ships in `examples/estimate.{dat,smp}` (7 decimals), `tests/test_setups.py:149-168`"""
+    import golden_cases
+    import golden_io
+    from yaw import RedshiftData
+
+    g = golden_io.load("example_2dflens")
+    cross, auto = golden_cases.run_example(g, OracleEngine())
+    nz = RedshiftData.from_corrfuncs(cross[0].to_reference(), auto[0].to_reference())
+    assert_allclose(nz.data, g["bundled_nz_data"], rtol=0, atol=2e-7)
+    assert_allclose(nz.error, g["bundled_nz_error"], rtol=0, atol=2e-7)
+    assert_allclose(nz.samples, g["bundled_nz_samples"], rtol=0, atol=2e-7)
+    assert_allclose(nz.data, g["nz_data"], rtol=1e-9)
+
+
 def test_read_reference_cache(yaw, tmpdir):
     """`Catalog.from_cache` opens the reference's on-disk patch cache byte-compatibly"""
     import yet_another_wizz_b200 as yb
