@@ -285,6 +285,7 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import _lib
+    from yet_another_wizz_b200.pipeline import count_cross_pipelined
     from yet_another_wizz_b200.sharding import assign_patches_contiguous, pair_costs
 
     rank = int(os.environ.get("RANK", "0"))
@@ -435,8 +436,10 @@ def run_gpu_arm(args):
     for step in range(e2e_warm + args.steps):
         barrier()
         t0 = time.perf_counter()
-        dev = upload_all()
-        results_e2e, _ = count_all(dev)
+        # the package's schedule for host-resident inputs: every copy enqueued up front, counts issued in
+        # arrival order; with --e2e-groups > 1 the unbinned catalogs travel and are counted in patch slices
+        results_e2e, _, _, devs = count_cross_pipelined(eng, host, opi, opj, plan.r2, groups=args.e2e_groups)
+        dev = {f"{k}{n}": d for k, lst in devs.items() for n, (d, _, _) in enumerate(lst)}
         results_e2e = reduce_results(results_e2e)
         barrier()
         dt = time.perf_counter() - t0
@@ -444,9 +447,24 @@ def run_gpu_arm(args):
             d.free()
         if rank == 0:
             log(f"[bench] e2e step {step}: {dt * 1e3:.1f} ms")
+            if step == 0:
+                for tag in COUNT_TYPES:
+                    assert np.array_equal(results_e2e[tag], results[tag]), f"e2e result of {tag} differs"
         if step >= e2e_warm:
             e2e_s.append(max_over_ranks(dt))
     clocks.__exit__()
+
+    # how much of an e2e step is the PCIe copy alone (uploads without any count, synchronised)
+    h2d_only = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        dev = upload_all()
+        eng.sync()
+        h2d_only.append(time.perf_counter() - t0)
+        for d in dev.values():
+            d.free()
+    h2d_only_ms = 1e3 * min(h2d_only)
 
     # statistics of the last timed step, summed over ranks
     tot_stats = np.array([sum(s[k] for s in stats_last.values()) for k in ("pair_tests", "pair_tests_naive", "rechecks")],
@@ -512,7 +530,8 @@ def run_gpu_arm(args):
                              for tag in COUNT_TYPES},
         ),
         e2e=dict(value=total_naive / float(np.mean(e2e_s)) / 1e9, unit="Gpairs/s", ms_per_step=float(np.mean(e2e_s)) * 1e3,
-                 h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes)),
+                 h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes),
+                 h2d_only_ms=h2d_only_ms, h2d_only_gb_per_s=h2d_bytes / h2d_only_ms / 1e6),
         gpu_launches=int(launches),
         clocks=clk,
     )
@@ -541,6 +560,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every catalog (development only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=1,
+                    help="patch slices per unbinned catalog in the end-to-end schedule (1 = whole catalogs)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one C3-sized field per GPU (default), strong = the one field split over the GPUs")
     args = ap.parse_args()

@@ -55,6 +55,30 @@ def test_bundled_example_golden(engine):
     golden_cases.check_example(g, cross, auto)
 
 
+def test_pipelined_schedule_gpu(engine):
+    """asynchronous uploads in patch slices + counts in arrival order: same integers as whole catalogs"""
+    from yet_another_wizz_b200 import pipeline
+    from yet_another_wizz_b200.measurements import PatchLinkage, _as_binning, prepare_catalog_arrays
+
+    g = golden_io.load("cross_unweighted")
+    config = golden_cases.config_from_golden(g)
+    cats = {k: golden_cases.catalog_from_golden(g, k) for k in ("ref", "unk", "ref_rand", "unk_rand")}
+    binning = _as_binning(config)
+    host = {k: prepare_catalog_arrays(c, binning if k in ("ref", "ref_rand") else None) for k, c in cats.items()}
+    links = PatchLinkage.from_catalogs(config, *cats.values(), engine=engine)
+    pair_i, pair_j = links.get_patch_id_pairs(auto=False)
+    plan = links._get_plan()
+    for groups in (1, 2, 6):
+        counts, _, stats, devs = pipeline.count_cross_pipelined(engine, host, pair_i, pair_j, plan.r2, groups=groups)
+        for tag, kind in (("DD", "dd"), ("DR", "dr"), ("RD", "rd"), ("RR", "rr")):
+            got = plan.finish(counts[tag])[0]
+            assert np.array_equal(got, g[f"cross_{kind}_counts_s0"][:, pair_i, pair_j].T), (groups, tag)
+            assert stats[tag]["pair_tests"] > 0
+        for lst in devs.values():
+            for dev, _, _ in lst:
+                dev.free()
+
+
 def test_default_engine_and_stats():
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import measurements

@@ -156,3 +156,39 @@ def test_boxrandoms_and_catalog_assignment():
     a = yb.BoxRandoms(0, 40, -12.5, 12.5, seed=5)(100)
     b = yb.BoxRandoms(0, 40, -12.5, 12.5, seed=5)(100)
     assert_array_equal(a["ra"], b["ra"])
+
+
+def test_pipelined_schedule_matches_whole_catalog_counts():
+    """`pipeline.count_cross_pipelined`: slicing the unbinned catalogs by patch groups changes the schedule,
+    never the result; the slices cover every patch, also with empty patches"""
+    from yet_another_wizz_b200 import pipeline
+    from yet_another_wizz_b200.measurements import _as_binning, prepare_catalog_arrays
+
+    g = golden_io.load("cross_unweighted")
+    config = golden_cases.config_from_golden(g)
+    cats = {k: golden_cases.catalog_from_golden(g, k) for k in ("ref", "unk", "ref_rand", "unk_rand")}
+    binning = _as_binning(config)
+    host = {k: prepare_catalog_arrays(c, binning if k in ("ref", "ref_rand") else None) for k, c in cats.items()}
+    links = PatchLinkage.from_catalogs(config, *cats.values(), engine=OracleEngine())
+    pair_i, pair_j = links.get_patch_id_pairs(auto=False)
+    r2 = links._get_plan().r2
+
+    whole = pipeline.count_cross_pipelined(OracleEngine(), host, pair_i, pair_j, r2, groups=1)
+    sliced = pipeline.count_cross_pipelined(OracleEngine(), host, pair_i, pair_j, r2, groups=3)
+    assert set(whole[0]) == {"DD", "DR", "RD", "RR"}
+    assert len(sliced[3]["unk"]) == 3 and len(whole[3]["unk"]) == 1
+    for tag in whole[0]:
+        assert_array_equal(sliced[0][tag], whole[0][tag])
+        assert whole[0][tag].sum() > 0
+    # the DD counts are the golden ones
+    plan = links._get_plan()
+    dd = plan.finish(whole[0]["DD"])[0]
+    want = g["cross_dd_counts_s0"][:, pair_i, pair_j].T
+    assert_array_equal(dd, want)
+
+    for off, n, expect in (([0, 0, 0, 5, 5], 3, [(0, 4)]), ([0, 4, 4, 4, 9, 9, 12], 3, [(0, 1), (1, 4), (4, 6)]),
+                           ([0, 0, 0], 4, [(0, 2)])):
+        ranges = pipeline.split_patch_groups(np.array(off), n)
+        assert ranges == expect
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(off) - 1
+        assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))

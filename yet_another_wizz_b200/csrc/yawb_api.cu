@@ -22,6 +22,36 @@ void yawb_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+// 16 bytes per thread from mapped pinned host memory to device memory
+__global__ void k_pull_host(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+int yawb_h2d_small(yawb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    // device buffers come from cudaMallocAsync (256-byte aligned, sizes rounded up), so writing the
+    // padding is safe; tables too large for the arena take the ordinary copy path
+    if (!ctx->h2d_base || padded > ctx->h2d_size / 2 || ((uintptr_t)dst & 15)) {
+        YAWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    if (ctx->h2d_used + padded > ctx->h2d_size) {  // arena full: everything staged so far must have been pulled
+        YAWB_CUDA(cudaStreamSynchronize(st));
+        ctx->h2d_used = 0;
+    }
+    unsigned char *stage = ctx->h2d_base + ctx->h2d_used;
+    ctx->h2d_used += padded;
+    memcpy(stage, src, bytes);
+    const size_t n16 = padded / 16;
+    const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 296);
+    k_pull_host<<<blocks, 256, 0, st>>>((uint4 *)dst, (const uint4 *)stage, n16);
+    YAWB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" {
 
 const char *yawb_last_error(void) { return g_err; }
@@ -58,11 +88,17 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
     ctx->pin_size = 8u << 20;
     YAWB_CUDA(cudaHostAlloc((void **)&ctx->pin_base, ctx->pin_size, cudaHostAllocDefault));
+    ctx->h2d_size = 32u << 20;
+    YAWB_CUDA(cudaHostAlloc((void **)&ctx->h2d_base, ctx->h2d_size, cudaHostAllocMapped));
     {   // keep freed blocks in the stream-ordered pool: index rebuilds then reuse them without driver calls
         cudaMemPool_t pool;
         YAWB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = UINT64_MAX;
         YAWB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // blocks move between the copy stream (allocated at upload) and the main stream (freed there);
+        // never let the allocator make the copy stream wait for compute to get a block back
+        int off = 0;
+        YAWB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
     }
     *out = ctx;
     return 0;
@@ -75,6 +111,7 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_counters);
     if (ctx->pin_base) cudaFreeHost(ctx->pin_base);
+    if (ctx->h2d_base) cudaFreeHost(ctx->h2d_base);
     cudaStreamDestroy(ctx->copy_stream);
     {
         cudaMemPool_t pool;
@@ -235,13 +272,24 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     YAWB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     yawb_stats s{};
-    if (yawb_cat_finalize(cat1) || yawb_cat_finalize(cat2)) return 1;
-
-    // indexes (lazy); timed with events that are only read after the final synchronisation of this call
-    const bool build_idx = !cat1->has_sindex || !cat2->has_rtiles;
-    if (build_idx) {
+    // Indexes are built lazily.  The first catalog is completed and indexed BEFORE the host waits for the
+    // copies of the second one: with asynchronous uploads that work overlaps with the transfer.  Timed with
+    // events that are only read after the final synchronisation of this call (waiting for copies excluded).
+    if (yawb_cat_finalize(cat1)) return 1;
+    float t_idx = 0.f;
+    if (!cat1->has_sindex) {
+        float t = 0.f;
         YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
         if (yawb_index_build_first(cat1)) return 1;
+        YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
+        YAWB_CUDA(cudaEventSynchronize(ctx->ev_i1));
+        YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
+        t_idx += t;
+    }
+    if (yawb_cat_finalize(cat2)) return 1;
+    const bool second_built = !cat2->has_rtiles;
+    if (second_built) {
+        YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
         if (yawb_index_build_second(cat2)) return 1;
         YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
     }
@@ -310,14 +358,22 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     TRY(cudaMallocAsync(&d_bp, B * sizeof(BinPar), st));
     TRY(cudaMallocAsync(&d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
     if (weighted) TRY(cudaMallocAsync(&d_w, std::max<size_t>(n_out, 1) * sizeof(double), st));
+#define H2D_SMALL(dst, src, bytes)                          \
+    do {                                                    \
+        if (yawb_h2d_small(ctx, (dst), (src), (bytes))) {   \
+            cleanup();                                      \
+            return 1;                                       \
+        }                                                   \
+    } while (0)
     if (n_pairs) {
-        TRY(cudaMemcpyAsync(d_pi, pair_i, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
-        TRY(cudaMemcpyAsync(d_pj, pair_j, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st));
+        H2D_SMALL(d_pi, pair_i, n_pairs * sizeof(int));
+        H2D_SMALL(d_pj, pair_j, n_pairs * sizeof(int));
     }
-    TRY(cudaMemcpyAsync(d_base, item_base.data(), (n_pairs + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_r2, r2_edges, (size_t)B * n_edges * sizeof(double), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_r2f, r2f.data(), (size_t)B * n_edges * sizeof(float), cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(d_bp, binpar.data(), B * sizeof(BinPar), cudaMemcpyHostToDevice, st));
+    H2D_SMALL(d_base, item_base.data(), (n_pairs + 1) * sizeof(long long));
+    H2D_SMALL(d_r2, r2_edges, (size_t)B * n_edges * sizeof(double));
+    H2D_SMALL(d_r2f, r2f.data(), (size_t)B * n_edges * sizeof(float));
+    H2D_SMALL(d_bp, binpar.data(), B * sizeof(BinPar));
+#undef H2D_SMALL
     TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
     if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
     TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
@@ -360,9 +416,13 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     TRY(cudaGetLastError());
-    float t_k = 0.f, t_idx = 0.f;
+    float t_k = 0.f;
     TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));
-    if (build_idx) TRY(cudaEventElapsedTime(&t_idx, ctx->ev_i0, ctx->ev_i1));
+    if (second_built) {
+        float t = 0.f;
+        TRY(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
+        t_idx += t;
+    }
     s.index_ms = t_idx;
 #undef TRY
     cleanup();

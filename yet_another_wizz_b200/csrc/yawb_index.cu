@@ -520,81 +520,44 @@ int build_second_sorted(yawb_cat *cat, int hbits) {
 }  // namespace
 
 // -------------------------------------------------------------------------------------------
+#ifndef YAWB_COPY_CHUNK_MB
+#define YAWB_COPY_CHUNK_MB 64
+#endif
+static constexpr size_t kCopyChunk = (size_t)YAWB_COPY_CHUNK_MB << 20;
+
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
                       const int32_t *zbin, const int64_t *patch_off) {
     const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
-    // The whole upload (allocation, host-to-device copies, per-patch reductions, meta data to pinned
-    // staging) runs on the context's copy stream, so it overlaps with index builds and pair counts of
-    // catalogs that arrived earlier; the main stream joins through `ev_meta` when the catalog is first used.
+    // Only allocations and host-to-device copies are issued here, all on the context's copy stream, which
+    // never carries a kernel: the copies of later catalogs keep the bus busy while pair counts of earlier
+    // ones occupy every SM (a kernel queued on the copy stream would wait for those SMs and hold the
+    // copies behind it).  The per-patch reductions run on the main stream when the catalog is first used
+    // (yawb_cat_finalize), which joins the copies through `ev_meta`.
     cudaStream_t st = ctx->copy_stream;
-    Scratch scr(st);
-
     if (dev_alloc(cat, &cat->x, n, st) || dev_alloc(cat, &cat->y, n, st) || dev_alloc(cat, &cat->z, n, st) ||
         dev_alloc(cat, &cat->patch, n, st))
         return 1;
     if (w && dev_alloc(cat, &cat->w, n, st)) return 1;
     if (zbin && dev_alloc(cat, &cat->bin, n, st)) return 1;
     if (dev_alloc(cat, &cat->d_frames, P, st) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1, st)) return 1;
+    if (dev_alloc(cat, &cat->d_stage_xyz, (size_t)n * 3, st) || dev_alloc(cat, &cat->d_stage_poff, P + 1, st)) return 1;
 
-    double *d_xyz = scr.get<double>((size_t)n * 3);
-    long long *d_poff = scr.get<long long>(P + 1);
-    double *d_sums = scr.get<double>((size_t)P * 3);
-    double *d_sumw = scr.get<double>((size_t)B * P);
-    unsigned long long *d_counts = scr.get<unsigned long long>((size_t)B * P);
-    unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
-    YAWB_REQUIRE(d_xyz && d_poff && d_sums && d_sumw && d_counts && d_box, "out of device memory (upload scratch)");
-
-    if (n > 0) YAWB_CUDA(cudaMemcpyAsync(d_xyz, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    YAWB_CUDA(cudaMemcpyAsync(d_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    if (w && n > 0) YAWB_CUDA(cudaMemcpyAsync(cat->w, w, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (zbin && n > 0) YAWB_CUDA(cudaMemcpyAsync(cat->bin, zbin, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    YAWB_CUDA(cudaMemsetAsync(d_sums, 0, P * 3 * sizeof(double), st));
-    YAWB_CUDA(cudaMemsetAsync(d_sumw, 0, (size_t)B * P * sizeof(double), st));
-    YAWB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)B * P * sizeof(unsigned long long), st));
-
-    const int pb = (P + 127) / 128;
-    if (n > 0) {
-        k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(d_xyz, d_poff, P, n, cat->x, cat->y, cat->z,
-                                                           cat->patch);
-        const bool use_smem = B <= kSumMaxBins;
-        const size_t smem = 4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (w ? sizeof(double) : 0)) : 0);
-        k_patch_sums<<<blocks_for(n, kSumRows), kThreads, smem, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin,
-                                                                       cat->patch, n, P, B, d_sums, d_counts, d_sumw);
-    }
-    k_make_frames<<<pb, 128, 0, st>>>(d_sums, P, cat->d_frames);
-    k_init_box<<<pb, 128, 0, st>>>(d_box, P);
-    if (n > 0)
-        k_patch_bbox<<<blocks_for(n, kSumRows), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n,
-                                                                   cat->d_frames, d_box);
-    k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
-
-    // meta data (frames, row counts, sums of weights) travels to pinned staging; nobody waits here:
-    // yawb_cat_finalize() picks it up when the catalog is first used
-    {
-        const size_t b_frames = (((size_t)std::max(P, 1) * sizeof(PatchFrame)) + 63) & ~(size_t)63;
-        const size_t b_counts = (((size_t)B * P * sizeof(unsigned long long)) + 63) & ~(size_t)63;
-        const size_t b_sumw = (((size_t)B * P * sizeof(double)) + 63) & ~(size_t)63;
-        const size_t need = b_frames + b_counts + b_sumw;
-        unsigned char *blk = nullptr;
-        if (ctx->pin_base && ctx->pin_used + need <= ctx->pin_size) {
-            blk = ctx->pin_base + ctx->pin_used;
-            ctx->pin_used += need;
-            ctx->pin_live += 1;
-            cat->staging_in_arena = true;
-        } else {
-            YAWB_CUDA(cudaHostAlloc((void **)&blk, need, cudaHostAllocDefault));
-            cat->hp_block = blk;
+    // Bulk copies go out in pieces so that other users of the copy engine never wait behind a whole
+    // catalog (the small tables of a concurrent pair count avoid the engine altogether: yawb_h2d_small).
+    auto h2d = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        for (size_t o = 0; o < bytes; o += kCopyChunk) {
+            cudaError_t e = cudaMemcpyAsync((char *)dst + o, (const char *)src + o, std::min(kCopyChunk, bytes - o),
+                                            cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
         }
-        cat->hp_frames = (PatchFrame *)blk;
-        cat->hp_counts = (unsigned long long *)(blk + b_frames);
-        cat->hp_sumw = (double *)(blk + b_frames + b_counts);
-    }
+        return cudaSuccess;
+    };
+    if (n > 0) YAWB_CUDA(h2d(cat->d_stage_xyz, xyz, n * 3 * sizeof(double)));
+    YAWB_CUDA(cudaMemcpyAsync(cat->d_stage_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (w && n > 0) YAWB_CUDA(h2d(cat->w, w, n * sizeof(double)));
+    if (zbin && n > 0) YAWB_CUDA(h2d(cat->bin, zbin, n * sizeof(int32_t)));
     YAWB_CUDA(cudaEventCreateWithFlags(&cat->ev_meta, cudaEventDisableTiming));
-    YAWB_CUDA(cudaMemcpyAsync(cat->hp_frames, cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaMemcpyAsync(cat->hp_counts, d_counts, (size_t)B * P * sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaMemcpyAsync(cat->hp_sumw, d_sumw, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
     YAWB_CUDA(cudaEventRecord(cat->ev_meta, st));
     YAWB_CUDA(cudaGetLastError());
     cat->finalized = false;
@@ -614,12 +577,68 @@ static void release_staging(yawb_cat *cat) {
     cat->hp_sumw = nullptr;
 }
 
-// Host-side completion of an upload: wait for the meta data, derive the row tables.
+// Completion of an upload at first use: SoA split, per-patch reductions and frames on the main stream,
+// their results to pinned staging, then the host-side row tables.
 int yawb_cat_finalize(yawb_cat *cat) {
     if (cat->finalized) return 0;
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
-    YAWB_CUDA(cudaEventSynchronize(cat->ev_meta));
-    YAWB_CUDA(cudaStreamWaitEvent(cat->ctx->stream, cat->ev_meta, 0));  // the main stream may now touch the rows
+    YAWB_CUDA(cudaStreamWaitEvent(st, cat->ev_meta, 0));  // the copies of this catalog have landed
+    {
+        Scratch scr(st);
+        double *d_sums = scr.get<double>((size_t)P * 3);
+        double *d_sumw = scr.get<double>((size_t)B * P);
+        unsigned long long *d_counts = scr.get<unsigned long long>((size_t)B * P);
+        unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
+        YAWB_REQUIRE(d_sums && d_sumw && d_counts && d_box, "out of device memory (upload scratch)");
+        YAWB_CUDA(cudaMemsetAsync(d_sums, 0, P * 3 * sizeof(double), st));
+        YAWB_CUDA(cudaMemsetAsync(d_sumw, 0, (size_t)B * P * sizeof(double), st));
+        YAWB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)B * P * sizeof(unsigned long long), st));
+        const int pb = (P + 127) / 128;
+        if (n > 0) {
+            k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_xyz, cat->d_stage_poff, P, n, cat->x, cat->y,
+                                                               cat->z, cat->patch);
+            const bool use_smem = B <= kSumMaxBins;
+            const size_t smem =
+                4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (cat->w ? sizeof(double) : 0)) : 0);
+            k_patch_sums<<<blocks_for(n, kSumRows), kThreads, smem, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin,
+                                                                           cat->patch, n, P, B, d_sums, d_counts, d_sumw);
+        }
+        k_make_frames<<<pb, 128, 0, st>>>(d_sums, P, cat->d_frames);
+        k_init_box<<<pb, 128, 0, st>>>(d_box, P);
+        if (n > 0)
+            k_patch_bbox<<<blocks_for(n, kSumRows), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n,
+                                                                       cat->d_frames, d_box);
+        k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
+        dev_free(cat, cat->d_stage_xyz, (size_t)n * 3);
+        dev_free(cat, cat->d_stage_poff, P + 1);
+
+        // meta data (frames, row counts, sums of weights) through pinned staging
+        const size_t b_frames = (((size_t)std::max(P, 1) * sizeof(PatchFrame)) + 63) & ~(size_t)63;
+        const size_t b_counts = (((size_t)B * P * sizeof(unsigned long long)) + 63) & ~(size_t)63;
+        const size_t b_sumw = (((size_t)B * P * sizeof(double)) + 63) & ~(size_t)63;
+        const size_t need = b_frames + b_counts + b_sumw;
+        unsigned char *blk = nullptr;
+        if (ctx->pin_base && ctx->pin_used + need <= ctx->pin_size) {
+            blk = ctx->pin_base + ctx->pin_used;
+            ctx->pin_used += need;
+            ctx->pin_live += 1;
+            cat->staging_in_arena = true;
+        } else {
+            YAWB_CUDA(cudaHostAlloc((void **)&blk, need, cudaHostAllocDefault));
+            cat->hp_block = blk;
+        }
+        cat->hp_frames = (PatchFrame *)blk;
+        cat->hp_counts = (unsigned long long *)(blk + b_frames);
+        cat->hp_sumw = (double *)(blk + b_frames + b_counts);
+        YAWB_CUDA(cudaMemcpyAsync(cat->hp_frames, cat->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
+        YAWB_CUDA(cudaMemcpyAsync(cat->hp_counts, d_counts, (size_t)B * P * sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, st));
+        YAWB_CUDA(cudaMemcpyAsync(cat->hp_sumw, d_sumw, (size_t)B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    YAWB_CUDA(cudaStreamSynchronize(st));
     YAWB_CUDA(cudaGetLastError());
     cat->h_frames.assign(cat->hp_frames, cat->hp_frames + P);
     cat->h_sumw.assign(cat->hp_sumw, cat->hp_sumw + (size_t)B * P);
@@ -636,8 +655,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         for (int b = 0; b < B; ++b)
             cat->h_seg_off[(size_t)p * B + b + 1] =
                 cat->h_seg_off[(size_t)p * B + b] + (int)cat->h_counts[(size_t)b * P + p];
-    YAWB_CUDA(cudaMemcpyAsync(cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int),
-                              cudaMemcpyHostToDevice, cat->ctx->stream));
+    if (yawb_h2d_small(cat->ctx, cat->d_seg_off, cat->h_seg_off.data(), ((size_t)P * B + 1) * sizeof(int))) return 1;
     release_staging(cat);
     cat->finalized = true;
     return 0;
@@ -682,7 +700,7 @@ int yawb_index_build_first(yawb_cat *cat) {
     cat->n_cells = base;
     YAWB_REQUIRE(base < (1ll << 40), "sky-cell index too large (%lld cells)", base);
     if (dev_alloc(cat, &cat->d_sgrid, P)) return 1;
-    YAWB_CUDA(cudaMemcpyAsync(cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid), cudaMemcpyHostToDevice, st));
+    if (yawb_h2d_small(ctx, cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid))) return 1;
 
     if (dev_alloc(cat, &cat->sx, n) || dev_alloc(cat, &cat->sy, n) || dev_alloc(cat, &cat->sz, n)) return 1;
     if (dev_alloc(cat, &cat->su, n) || dev_alloc(cat, &cat->sv, n) || dev_alloc(cat, &cat->st, n)) return 1;
@@ -747,12 +765,15 @@ int yawb_index_build_second(yawb_cat *cat) {
     // Tiles whose radius exceeds 3x the radius expected from the patch's mean density are cut into
     // sub-tiles of 32 rows (rare; they run the same kernel with most register rows padded).  The common
     // case costs one 4-byte read-back.
+    bool table_on_device = false;
     if (!tiles.empty()) {
         Scratch scr(st);
-        Tile *d_tmp = scr.get<Tile>(tiles.size());
+        if (dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;  // becomes the final table unless tiles are split
+        Tile *d_tmp = cat->d_tiles;
+        const size_t n_tmp = tiles.size();
         float *d_thr = scr.get<float>(P);
         unsigned *d_nbig = scr.get<unsigned>(1);
-        YAWB_REQUIRE(d_tmp && d_thr && d_nbig, "out of device memory (tile table)");
+        YAWB_REQUIRE(d_thr && d_nbig, "out of device memory (tile table)");
         std::vector<float> thr(P, 3.0e38f);
         for (int p = 0; p < P; ++p) {
             const PatchFrame &f = cat->h_frames[p];
@@ -761,8 +782,8 @@ int yawb_index_build_second(yawb_cat *cat) {
             if (np >= 8 * YAWB_TILE && area > 0.0)  // radius of a disc holding YAWB_TILE rows of one z-bin
                 thr[p] = (float)(3.0 * std::sqrt((double)YAWB_TILE * B * area / (3.14159265358979 * (double)np)));
         }
-        YAWB_CUDA(cudaMemcpyAsync(d_tmp, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
-        YAWB_CUDA(cudaMemcpyAsync(d_thr, thr.data(), P * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (yawb_h2d_small(ctx, d_tmp, tiles.data(), tiles.size() * sizeof(Tile))) return 1;
+        if (yawb_h2d_small(ctx, d_thr, thr.data(), P * sizeof(float))) return 1;
         YAWB_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
         k_tile_spheres<<<blocks_for((long long)tiles.size() * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, d_tmp,
                                                                                       (int)tiles.size());
@@ -770,9 +791,11 @@ int yawb_index_build_second(yawb_cat *cat) {
         unsigned n_big = 0;
         YAWB_CUDA(cudaMemcpyAsync(&n_big, d_nbig, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         YAWB_CUDA(cudaStreamSynchronize(st));
+        table_on_device = n_big == 0;
         if (n_big > 0) {
             YAWB_CUDA(cudaMemcpyAsync(tiles.data(), d_tmp, tiles.size() * sizeof(Tile), cudaMemcpyDeviceToHost, st));
             YAWB_CUDA(cudaStreamSynchronize(st));
+            dev_free(cat, cat->d_tiles, n_tmp);
             std::vector<Tile> out;
             out.reserve(tiles.size() + 8 * (size_t)n_big);
             std::vector<int> new_off(P + 1, 0);
@@ -798,14 +821,14 @@ int yawb_index_build_second(yawb_cat *cat) {
         }
     }
     cat->n_tiles = (int)tiles.size();
-    if (dev_alloc(cat, &cat->d_tiles, tiles.size()) || dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
-    if (!tiles.empty())
-        YAWB_CUDA(cudaMemcpyAsync(cat->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st));
-    YAWB_CUDA(cudaMemcpyAsync(cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int),
-                              cudaMemcpyHostToDevice, st));
-    if (cat->n_tiles > 0)  // spheres of the final table (the split tiles need their own)
+    if (!table_on_device && dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;
+    if (dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
+    if (yawb_h2d_small(ctx, cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int))) return 1;
+    if (!table_on_device && !tiles.empty()) {  // the split tiles need their own spheres
+        if (yawb_h2d_small(ctx, cat->d_tiles, tiles.data(), tiles.size() * sizeof(Tile))) return 1;
         k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz,
                                                                                       cat->d_tiles, cat->n_tiles);
+    }
     YAWB_CUDA(cudaGetLastError());
     cat->has_rtiles = true;
     return 0;
@@ -830,9 +853,13 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
     }
     if (everything) {
         release_staging(cat);
+        // a catalog that was never used may still have copies in flight: frees are ordered behind them
+        if (cat->ev_meta && !cat->finalized) cudaStreamWaitEvent(cat->ctx->stream, cat->ev_meta, 0);
         if (cat->ev_meta) cudaEventDestroy(cat->ev_meta);
         cat->ev_meta = nullptr;
         const size_t ni = (size_t)cat->n_in;
+        dev_free(cat, cat->d_stage_xyz, ni * 3);
+        dev_free(cat, cat->d_stage_poff, P + 1);
         dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
         dev_free(cat, cat->w, ni);
         dev_free(cat, cat->bin, ni);

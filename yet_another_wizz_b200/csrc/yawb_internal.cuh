@@ -89,6 +89,9 @@ struct yawb_ctx {
     unsigned char *pin_base = nullptr;
     size_t pin_size = 0, pin_used = 0;
     int pin_live = 0;
+    // pinned arena that small host tables pass through on their way to the device (yawb_h2d_small)
+    unsigned char *h2d_base = nullptr;
+    size_t h2d_size = 0, h2d_used = 0;
 };
 
 struct yawb_cat {
@@ -103,7 +106,9 @@ struct yawb_cat {
 
     // uploads are asynchronous: the host-side tables below are filled by yawb_cat_finalize() on first use
     bool finalized = false;
-    cudaEvent_t ev_meta = nullptr;            // recorded after the meta data reached the pinned staging
+    cudaEvent_t ev_meta = nullptr;            // recorded on the copy stream after the last host-to-device copy
+    double *d_stage_xyz = nullptr;            // interleaved rows as uploaded, until yawb_cat_finalize()
+    long long *d_stage_poff = nullptr;        // row offsets of the patches, until yawb_cat_finalize()
     unsigned long long *hp_counts = nullptr;  // pinned staging [n_bins][n_patch]
     double *hp_sumw = nullptr;                // pinned staging [n_bins][n_patch]
     PatchFrame *hp_frames = nullptr;          // pinned staging [n_patch]
@@ -147,6 +152,9 @@ struct yawb_cat {
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
                       const int32_t *zbin, const int64_t *patch_off);
 int yawb_cat_finalize(yawb_cat *cat);
+// Small host table -> device on the main stream WITHOUT the copy engine: staged in pinned memory and
+// pulled over by a kernel, so it never queues behind the bulk uploads of later catalogs.
+int yawb_h2d_small(yawb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int yawb_index_build_first(yawb_cat *cat);
 int yawb_index_build_second(yawb_cat *cat);
 void yawb_index_free(yawb_cat *cat, bool everything);

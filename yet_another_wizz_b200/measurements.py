@@ -398,15 +398,16 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
     _last_stats.clear()
     kw = dict(binned_second=False)
     try:
-        # uploads are asynchronous: enqueue every catalog first (randoms, the big ones, in front), then
-        # count in arrival order so that RR / RD run while the later catalogs are still crossing PCIe
+        # uploads are asynchronous: enqueue every catalog first -- the z-binned ones, then the unbinned ones,
+        # randoms in front -- and count in arrival order, so that RR / DR run while the unknown sample is
+        # still crossing PCIe (same schedule as `pipeline.count_cross_pipelined`)
         binning = _as_binning(config)
-        for cat, bins in ((ref_rand, binning), (unk_rand, None), (unknown, None), (reference, binning)):
+        for cat, bins in ((ref_rand, binning), (reference, binning), (unk_rand, None), (unknown, None)):
             if cat is not None:
                 links._uploads.get(cat, bins)
         RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
-        RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
         DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
+        RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
         DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
     finally:
         links._uploads.free()

@@ -1,0 +1,107 @@
+"""
+Pipelined schedule of the four pair counts of a cross-correlation for HOST-resident inputs.
+
+With the rows resident in HBM a C3 pass takes ~10 ms, but pushing its 788 MB through PCIe takes ~16 ms,
+so an end-to-end call is bound by the copy and by whatever is left to do once the last byte has arrived.
+The schedule keeps that tail short:
+
+* the z-binned catalogs (reference sample, its randoms; "first role", sky-cell index) go first, whole;
+* the unbinned catalogs (unknown sample, its randoms; "second role", register tiles) follow in `groups`
+  slices of whole patches, each an independent device catalog; a patch pair (i, j) only ever needs the
+  slice that holds patch j, so the counts against a slice are issued as soon as it has arrived and run
+  while the next slice is still on the bus.  After the last slice only 1/groups of two counts remain.
+
+Every upload is enqueued before the first count (`yawb_upload_catalog` is asynchronous), the slices are
+views of the caller's buffers (rows of a patch are contiguous), and the per-slice results are scattered
+into the full `(n_pairs, n_bins, n_sub)` arrays -- the result is identical to four whole-catalog calls.
+This replaces the reference's task farm over patch pairs (`measurements.py:344-350`) on this path.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["COUNT_TYPES", "count_cross_pipelined", "split_patch_groups", "upload_patch_slices"]
+
+# count type -> (first-role catalog, second-role catalog), `crosscorrelate` naming (measurements.py:623-626)
+COUNT_TYPES = dict(DD=("ref", "unk"), DR=("ref", "unk_rand"), RD=("ref_rand", "unk"), RR=("ref_rand", "unk_rand"))
+
+
+def split_patch_groups(patch_off: np.ndarray, n_groups: int) -> list[tuple[int, int]]:
+    """Contiguous patch-id ranges `[lo, hi)` holding about the same number of rows each."""
+    patch_off = np.asarray(patch_off, dtype=np.int64)
+    n_patch, n_rows = len(patch_off) - 1, int(patch_off[-1])
+    n_groups = max(1, min(int(n_groups), n_patch))
+    if n_rows == 0 or n_groups == 1:
+        return [(0, n_patch)]
+    cuts = np.searchsorted(patch_off, n_rows * np.arange(1, n_groups) / n_groups, side="left")
+    bounds = np.unique(np.concatenate([[0], np.clip(cuts, 0, n_patch), [n_patch]]))
+    # drop empty ranges by merging them into their neighbour; the ranges always cover every patch
+    keep = [int(bounds[0])]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if patch_off[b] > patch_off[keep[-1]]:
+            keep.append(int(b))
+    keep[-1] = n_patch
+    return list(zip(keep[:-1], keep[1:]))
+
+
+def upload_patch_slices(engine, arrays: dict, n_groups: int) -> list[tuple[object, int, int]]:
+    """Upload one catalog as independent device catalogs of whole patches.  `arrays` holds the keyword
+    arguments of `Engine.upload_catalog` (xyz, patch_off, weights, zbin, n_bins); returns
+    `(device catalog, first patch, one past the last patch)` per slice.  Patches outside a slice are
+    empty in its device catalog, so patch ids keep their meaning."""
+    off = np.asarray(arrays["patch_off"], dtype=np.int64)
+    out = []
+    for lo, hi in split_patch_groups(off, n_groups):
+        a, b = int(off[lo]), int(off[hi])
+        sub_off = np.clip(off, a, b) - a
+        dev = engine.upload_catalog(
+            arrays["xyz"][a:b], sub_off,
+            weights=None if arrays.get("weights") is None else arrays["weights"][a:b],
+            zbin=None if arrays.get("zbin") is None else arrays["zbin"][a:b],
+            n_bins=arrays.get("n_bins", 1),
+        )
+        out.append((dev, lo, hi))
+    return out
+
+
+def count_cross_pipelined(engine, host: dict, pair_i: np.ndarray, pair_j: np.ndarray, r2: np.ndarray, *,
+                          groups: int = 4):
+    """DD / DR / RD / RR (as far as the catalogs in `host` allow) between the patches listed in
+    `(pair_i, pair_j)`.  `host[name]` = upload arguments of catalog `name` in ("ref", "ref_rand", "unk",
+    "unk_rand") or None.  Returns `(counts_i64, sums_f64, stats, devices)`: per count type the
+    `(n_pairs, n_bins, n_sub)` arrays, the merged kernel statistics, and the device catalogs (whole
+    first-role catalogs and the slices of the second-role ones) for the caller to query and free."""
+    pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+    pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+    first = [k for k in ("ref_rand", "ref") if host.get(k) is not None]
+    second = [k for k in ("unk_rand", "unk") if host.get(k) is not None]
+    # enqueue every copy up front, in the order the counts will want them: first-role catalogs, then the
+    # slices of the second-role catalogs, randoms (usually the larger ones) in front
+    devices: dict[str, list] = {}
+    for k in first:
+        h = host[k]
+        devices[k] = [(engine.upload_catalog(h["xyz"], h["patch_off"], weights=h.get("weights"), zbin=h.get("zbin"),
+                                             n_bins=h.get("n_bins", 1)), 0, len(h["patch_off"]) - 1)]
+    for k in second:
+        devices[k] = upload_patch_slices(engine, host[k], groups)
+
+    n_bins = max(host[k].get("n_bins", 1) for k in first) if first else 1
+    shape = (len(pair_i), n_bins, r2.shape[1] - 1)
+    counts, sums, stats = {}, {}, {}
+    for k2 in second:
+        for dev2, lo, hi in devices[k2]:
+            sel = np.flatnonzero((pair_j >= lo) & (pair_j < hi))
+            for k1 in first:
+                tag = next(t for t, (a, b) in COUNT_TYPES.items() if (a, b) == (k1, k2))
+                if tag not in counts:
+                    counts[tag] = np.zeros(shape, dtype=np.int64)
+                    sums[tag] = np.zeros(shape, dtype=np.float64)
+                    stats[tag] = {}
+                if len(sel) == 0:
+                    continue
+                ci, cf, st = engine.count(devices[k1][0][0], dev2, pair_i[sel], pair_j[sel], r2)
+                counts[tag][sel], sums[tag][sel] = ci, cf
+                for key, val in st.items():
+                    stats[tag][key] = stats[tag].get(key, 0) + val
+    return counts, sums, stats, devices
