@@ -520,7 +520,11 @@ def run_gpu_arm(args):
                           host_prep_s=wl["t_host_prep"], catalogs_s=wl["t_catalogs"]),
         roofline=dict(
             bound="fp32", achieved=achieved / 1e9, peak=peak_tests / 1e9, unit="Gtests/s",
-            frac=achieved / peak_tests, traffic=None,
+            frac=achieved / peak_tests,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant (RR) launch, one `ncu --set full`
+            # capture of this workload (profiles/r01_h_ncu_full_k_count_uni.txt); not an HBM-bound kernel
+            traffic=1.0075e9 if (args.workload == "C3" and args.scale == 1.0 and (world == 1 or weak)) else None,
+            traffic_unit="bytes per RR launch (algorithmic minimum 4.8e8: 1e7 tile rows + 1e7 candidate rows, 24 B each)",
             note=f"pair-count kernels of rank 0; executed (non-pruned) tests / kernel time vs {sms} SMs x 128 lanes x "
                  f"{sm_max_mhz:.0f} MHz / {FP32_INSTR_PER_TEST} FP32 instr per test (MEASURED_PEAKS.json sm_max_mhz)",
             executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(float(tot_stats[1]), 1.0),
