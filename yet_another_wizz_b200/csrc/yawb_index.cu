@@ -305,10 +305,11 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
 // Hilbert index of a cell on a 65536 x 65536 grid.  Unlike the Morton (Z) curve the Hilbert curve has
 // no jumps: consecutive cells are always neighbours, so every run of YAWB_TILE consecutive rows is a
 // compact clump and no register tile straddles a quadrant boundary with a patch-sized bounding box.
-__device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y) {
+// Only the top `levels` levels are resolved (the top 2 * levels bits of the index; the rest stays zero).
+__device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y, int levels = 16) {
     unsigned d = 0;
-#pragma unroll
-    for (unsigned s = 1u << 15; s > 0; s >>= 1) {
+    const unsigned stop = levels >= 16 ? 0u : (1u << (15 - levels));
+    for (unsigned s = 1u << 15; s > stop; s >>= 1) {
         const unsigned rx = (x & s) ? 1u : 0u;
         const unsigned ry = (y & s) ? 1u : 0u;
         d += s * s * ((3u * rx) ^ ry);
@@ -353,7 +354,7 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     int qu = min(max((int)((u - f.umin) * su), 0), 65535);
     int qv = min(max((int)((v - f.vmin) * sv), 0), 65535);
     keys[i] = (K)(((unsigned long long)((long long)p * n_bins + b) << hbits) |
-                  (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv) >> (32 - hbits)));
+                  (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv, (hbits + 1) / 2) >> (32 - hbits)));
 }
 
 __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
@@ -732,8 +733,15 @@ int yawb_index_build_second(yawb_cat *cat) {
     {
         const int seg_bits = bits_for((unsigned long long)std::max<long long>((long long)P * B, 1));
         const int hbits32 = ((31 - seg_bits) / 2) * 2;  // the all-ones key stays reserved for dropped rows
+        // The curve only has to order the rows down to about one row per Hilbert cell: with m rows in the
+        // largest (patch, bin) segment, 2^k x 2^k >= 1.5 m cells are enough.  Fewer key bits = fewer radix passes.
+        long long m = 1;
+        for (size_t sgm = 0; sgm + 1 < cat->h_seg_off.size(); ++sgm)
+            m = std::max<long long>(m, cat->h_seg_off[sgm + 1] - cat->h_seg_off[sgm]);
+        int k = 4;
+        while (k < 16 && (1ll << (2 * k)) < m + m / 2) ++k;
         if (hbits32 >= 16) {
-            if (build_second_sorted<unsigned>(cat, hbits32)) return 1;
+            if (build_second_sorted<unsigned>(cat, std::min(hbits32, 2 * k))) return 1;
         } else {
             if (build_second_sorted<unsigned long long>(cat, 32)) return 1;
         }
