@@ -52,6 +52,11 @@ for rep in range(3):
     for lst in devs.values():
         for d, _, _ in lst:
             d.free()
+    if rep == 0:
+        print("cold pass total", total)
+        for name, t, dt, st in events:
+            extra = "" if st is None else f" kernel {st['kernel_ms']:.2f} index {st['index_ms']:.2f} items {st['work_items']}"
+            print(f"{t:8.2f} +{dt:6.2f}  {name}{extra}")
 print("total", total)
 for name, t, dt, st in events:
     extra = "" if st is None else f" kernel {st['kernel_ms']:.2f} index {st['index_ms']:.2f} items {st['work_items']}"

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <cstdlib>
+
 #include "yawb_internal.cuh"
 
 namespace {
@@ -32,8 +34,8 @@ int yawb_h2d_small(yawb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     if (bytes == 0) return 0;
     cudaStream_t st = ctx->stream;
     const size_t padded = (bytes + 15) & ~(size_t)15;
-    // device buffers come from cudaMallocAsync (256-byte aligned, sizes rounded up), so writing the
-    // padding is safe; tables too large for the arena take the ordinary copy path
+    // device buffers come from the caching allocator (256-byte aligned, sizes rounded up to 512 B), so
+    // writing the padding is safe; tables too large for the arena take the ordinary copy path
     if (!ctx->h2d_base || padded > ctx->h2d_size / 2 || ((uintptr_t)dst & 15)) {
         YAWB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return 0;
@@ -90,16 +92,6 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaHostAlloc((void **)&ctx->pin_base, ctx->pin_size, cudaHostAllocDefault));
     ctx->h2d_size = 32u << 20;
     YAWB_CUDA(cudaHostAlloc((void **)&ctx->h2d_base, ctx->h2d_size, cudaHostAllocMapped));
-    {   // keep freed blocks in the stream-ordered pool: index rebuilds then reuse them without driver calls
-        cudaMemPool_t pool;
-        YAWB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = UINT64_MAX;
-        YAWB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        // blocks move between the copy stream (allocated at upload) and the main stream (freed there);
-        // never let the allocator make the copy stream wait for compute to get a block back
-        int off = 0;
-        YAWB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
-    }
     *out = ctx;
     return 0;
 }
@@ -113,10 +105,7 @@ int yawb_destroy(yawb_ctx *ctx) {
     if (ctx->pin_base) cudaFreeHost(ctx->pin_base);
     if (ctx->h2d_base) cudaFreeHost(ctx->h2d_base);
     cudaStreamDestroy(ctx->copy_stream);
-    {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
+    yawb_dcache_destroy(ctx);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_i0);
@@ -338,7 +327,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     auto cleanup = [&]() {
         for (void *p : {(void *)d_pi, (void *)d_pj, (void *)d_base, (void *)d_r2, (void *)d_r2f, (void *)d_bp,
                         (void *)d_cnt, (void *)d_w})
-            if (p) cudaFreeAsync(p, st);
+            if (p) yawb_dfree(ctx, p, st);
     };
 #define TRY(call)                                                                        \
     do {                                                                                 \
@@ -349,15 +338,22 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
             return 1;                                                                    \
         }                                                                                \
     } while (0)
+#define DALLOC(ptr, bytes)                                           \
+    do {                                                             \
+        if (yawb_dalloc(ctx, (void **)&(ptr), (bytes), st)) {        \
+            cleanup();                                               \
+            return 1;                                                \
+        }                                                            \
+    } while (0)
     const size_t np1 = std::max(n_pairs, 1);
-    TRY(cudaMallocAsync(&d_pi, np1 * sizeof(int), st));
-    TRY(cudaMallocAsync(&d_pj, np1 * sizeof(int), st));
-    TRY(cudaMallocAsync(&d_base, (np1 + 1) * sizeof(long long), st));
-    TRY(cudaMallocAsync(&d_r2, (size_t)B * n_edges * sizeof(double), st));
-    TRY(cudaMallocAsync(&d_r2f, (size_t)B * n_edges * sizeof(float), st));
-    TRY(cudaMallocAsync(&d_bp, B * sizeof(BinPar), st));
-    TRY(cudaMallocAsync(&d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
-    if (weighted) TRY(cudaMallocAsync(&d_w, std::max<size_t>(n_out, 1) * sizeof(double), st));
+    DALLOC(d_pi, np1 * sizeof(int));
+    DALLOC(d_pj, np1 * sizeof(int));
+    DALLOC(d_base, (np1 + 1) * sizeof(long long));
+    DALLOC(d_r2, (size_t)B * n_edges * sizeof(double));
+    DALLOC(d_r2f, (size_t)B * n_edges * sizeof(float));
+    DALLOC(d_bp, B * sizeof(BinPar));
+    DALLOC(d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long));
+    if (weighted) DALLOC(d_w, std::max<size_t>(n_out, 1) * sizeof(double));
 #define H2D_SMALL(dst, src, bytes)                          \
     do {                                                    \
         if (yawb_h2d_small(ctx, (dst), (src), (bytes))) {   \
@@ -404,11 +400,11 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
             launches += 1;
         } else {
             double *d_tmp = nullptr;
-            TRY(cudaMallocAsync(&d_tmp, n_out * sizeof(double), st));
+            DALLOC(d_tmp, n_out * sizeof(double));
             k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, d_tmp, (long long)n_out);
             launches += 1;
             cudaError_t e = cudaMemcpyAsync(out_f64, d_tmp, n_out * sizeof(double), kind, st);
-            cudaFreeAsync(d_tmp, st);
+            yawb_dfree(ctx, d_tmp, st);
             TRY(e);
         }
     }

@@ -430,7 +430,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
 
     // planner: compact list of the (patch pair, tile) items that can hold pairs
     int2 *d_live = nullptr;
-    YAWB_CUDA(cudaMallocAsync((void **)&d_live, (size_t)a.n_items * sizeof(int2), ctx->stream));
+    if (yawb_dalloc(ctx, (void **)&d_live, (size_t)a.n_items * sizeof(int2), ctx->stream)) return 1;
     P.live = d_live;
     int max_tiles = 1;
     for (size_t p = 0; p + 1 < a.c2->h_ptile_off.size(); ++p)
@@ -496,7 +496,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         }
 #undef LAUNCH
     }
-    cudaFreeAsync(d_live, ctx->stream);
+    yawb_dfree(ctx, d_live, ctx->stream);
     YAWB_CUDA(cudaGetLastError());
     *launches += 1;
     return 0;

@@ -34,14 +34,13 @@ inline int blocks_for(int64_t n, int per_block = kThreads) {
     return (int)std::min<int64_t>((n + per_block - 1) / per_block, 1 << 30);
 }
 
-// Catalog buffers come from the device's stream-ordered memory pool (cudaMallocAsync on the context's
-// stream; the pool keeps freed blocks, see yawb_create), so building and dropping indexes costs no
-// device synchronisation and no driver round trips after the first use.
+// Catalog buffers come from the context's caching allocator (yawb_alloc.cu): building and dropping
+// indexes costs no device synchronisation and no driver round trips after the first use.
 template <typename T>
 int dev_alloc(yawb_cat *cat, T **ptr, size_t count, cudaStream_t stream = nullptr) {
     *ptr = nullptr;
     if (count == 0) count = 1;
-    YAWB_CUDA(cudaMallocAsync((void **)ptr, count * sizeof(T), stream ? stream : cat->ctx->stream));
+    if (yawb_dalloc(cat->ctx, (void **)ptr, count * sizeof(T), stream ? stream : cat->ctx->stream)) return 1;
     cat->device_bytes += (int64_t)(count * sizeof(T));
     return 0;
 }
@@ -49,7 +48,7 @@ int dev_alloc(yawb_cat *cat, T **ptr, size_t count, cudaStream_t stream = nullpt
 template <typename T>
 void dev_free(yawb_cat *cat, T *&ptr, size_t count) {
     if (ptr) {
-        cudaFreeAsync(ptr, cat->ctx->stream);
+        yawb_dfree(cat->ctx, ptr, cat->ctx->stream);
         cat->device_bytes -= (int64_t)(std::max<size_t>(count, 1) * sizeof(T));
         ptr = nullptr;
     }
@@ -57,18 +56,19 @@ void dev_free(yawb_cat *cat, T *&ptr, size_t count) {
 
 // scratch that lives for one call
 struct Scratch {
+    yawb_ctx *ctx;
     cudaStream_t st;
     std::vector<void *> ptrs;
-    explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(yawb_ctx *c, cudaStream_t s) : ctx(c), st(s) {}
     template <typename T>
     T *get(size_t count) {
         void *p = nullptr;
-        if (cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), st) != cudaSuccess) return nullptr;
+        if (yawb_dalloc(ctx, &p, std::max<size_t>(count, 1) * sizeof(T), st)) return nullptr;
         ptrs.push_back(p);
         return (T *)p;
     }
     ~Scratch() {
-        for (void *p : ptrs) cudaFreeAsync(p, st);
+        for (void *p : ptrs) yawb_dfree(ctx, p, st);
     }
 };
 
@@ -474,7 +474,7 @@ int build_first_sorted(yawb_cat *cat, long long base) {
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
     const long long n_in = cat->n_in, n = cat->n;
-    Scratch scr(st);
+    Scratch scr(ctx, st);
     const size_t nn = std::max<long long>(n_in, 1);
     K *k0 = scr.get<K>(nn), *k1 = scr.get<K>(nn);
     unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
@@ -500,7 +500,7 @@ int build_second_sorted(yawb_cat *cat, int hbits) {
     cudaStream_t st = ctx->stream;
     const long long n_in = cat->n_in, n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
-    Scratch scr(st);
+    Scratch scr(ctx, st);
     const size_t nn = std::max<long long>(n_in, 1);
     K *k0 = scr.get<K>(nn), *k1 = scr.get<K>(nn);
     unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
@@ -588,7 +588,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
     const int P = cat->n_patch, B = cat->n_bins;
     YAWB_CUDA(cudaStreamWaitEvent(st, cat->ev_meta, 0));  // the copies of this catalog have landed
     {
-        Scratch scr(st);
+        Scratch scr(ctx, st);
         double *d_sums = scr.get<double>((size_t)P * 3);
         double *d_sumw = scr.get<double>((size_t)B * P);
         unsigned long long *d_counts = scr.get<unsigned long long>((size_t)B * P);
@@ -667,7 +667,6 @@ int yawb_index_build_first(yawb_cat *cat) {
     if (yawb_cat_finalize(cat)) return 1;
     if (cat->has_sindex) return 0;
     yawb_ctx *ctx = cat->ctx;
-    cudaStream_t st = ctx->stream;
     const long long n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
 
@@ -775,7 +774,7 @@ int yawb_index_build_second(yawb_cat *cat) {
     // case costs one 4-byte read-back.
     bool table_on_device = false;
     if (!tiles.empty()) {
-        Scratch scr(st);
+        Scratch scr(ctx, st);
         if (dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;  // becomes the final table unless tiles are split
         Tile *d_tmp = cat->d_tiles;
         const size_t n_tmp = tiles.size();

@@ -89,6 +89,7 @@ struct yawb_ctx {
     unsigned char *pin_base = nullptr;
     size_t pin_size = 0, pin_used = 0;
     int pin_live = 0;
+    struct yawb_devcache *cache = nullptr;  // device blocks, recycled (yawb_alloc.cu)
     // pinned arena that small host tables pass through on their way to the device (yawb_h2d_small)
     unsigned char *h2d_base = nullptr;
     size_t h2d_size = 0, h2d_used = 0;
@@ -151,6 +152,12 @@ struct yawb_cat {
 // index construction (yawb_index.cu)
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
                       const int32_t *zbin, const int64_t *patch_off);
+// device memory (yawb_alloc.cu): stream-aware caching allocator on top of cudaMalloc
+int yawb_dalloc(yawb_ctx *ctx, void **out, size_t bytes, cudaStream_t st);
+void yawb_dfree(yawb_ctx *ctx, void *ptr, cudaStream_t st);
+void yawb_dcache_destroy(yawb_ctx *ctx);
+size_t yawb_dcache_bytes(const yawb_ctx *ctx);
+
 int yawb_cat_finalize(yawb_cat *cat);
 // Small host table -> device on the main stream WITHOUT the copy engine: staged in pinned memory and
 // pulled over by a kernel, so it never queues behind the bulk uploads of later catalogs.
