@@ -78,9 +78,11 @@ int yawb_destroy(yawb_ctx *ctx);
  *              src/yaw/correlation/measurements.py:358-364)
  *   n_bins     number of z-bins (ignored when zbin == NULL)
  *
- * The call is asynchronous: copies are enqueued on a dedicated copy stream and overlap with kernels of
- * earlier calls; the host buffers must stay valid until the first call that uses the catalog (or
- * yawb_sync) has returned.
+ * The call is asynchronous: it only allocates and enqueues the host-to-device copies on a dedicated copy
+ * stream (which never carries a kernel, so copies of later catalogs proceed while pair counts of earlier
+ * ones occupy the GPU); the per-patch reductions run when the catalog is first used.  The host buffers
+ * must stay valid until the first call that uses the catalog (or yawb_sync) has returned.  Enqueue every
+ * catalog first and count in arrival order to overlap PCIe with the counts.
  */
 int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);
