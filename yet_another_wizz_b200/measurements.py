@@ -398,17 +398,18 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
     _last_stats.clear()
     kw = dict(binned_second=False)
     try:
-        # uploads are asynchronous: enqueue every catalog first -- the z-binned ones, then the unbinned ones,
-        # randoms in front -- and count in arrival order, so that RR / DR run while the unknown sample is
-        # still crossing PCIe (same schedule as `pipeline.count_cross_pipelined`)
+        # uploads are asynchronous: enqueue every catalog first, the data samples before the randoms, and
+        # count in the order in which the inputs become complete -- DD gets the GPU going a few ms into the
+        # transfer, RD / DR follow, and only RR waits for the last catalog (same schedule as
+        # `pipeline.count_cross_pipelined`)
         binning = _as_binning(config)
-        for cat, bins in ((ref_rand, binning), (reference, binning), (unk_rand, None), (unknown, None)):
+        for cat, bins in ((reference, binning), (unknown, None), (ref_rand, binning), (unk_rand, None)):
             if cat is not None:
                 links._uploads.get(cat, bins)
-        RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
-        DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
-        RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
         DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
+        RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
+        DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
+        RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
     finally:
         links._uploads.free()
         links._uploads = None

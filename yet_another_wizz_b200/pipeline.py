@@ -5,11 +5,15 @@ With the rows resident in HBM a C3 pass takes ~10 ms, but pushing its 788 MB thr
 so an end-to-end call is bound by the copy and by whatever is left to do once the last byte has arrived.
 The schedule keeps that tail short:
 
-* the z-binned catalogs (reference sample, its randoms; "first role", sky-cell index) go first, whole;
-* the unbinned catalogs (unknown sample, its randoms; "second role", register tiles) follow in `groups`
-  slices of whole patches, each an independent device catalog; a patch pair (i, j) only ever needs the
-  slice that holds patch j, so the counts against a slice are issued as soon as it has arrived and run
-  while the next slice is still on the bus.  After the last slice only 1/groups of two counts remain.
+* every copy is enqueued before the first count, smaller catalogs first (reference sample, unknown sample,
+  then the randoms): the cheap DD count gets the GPU going a few ms into the transfer, and every count
+  that does not need the last catalog has finished when it arrives;
+* counts are issued in the order in which their inputs become complete; each builds the indexes it needs
+  on first use (the first catalog's before the host waits for the copies of the second one);
+* optionally (`groups` > 1) the unbinned catalogs (unknown sample, its randoms; "second role", register
+  tiles) travel in slices of whole patches, each an independent device catalog; a patch pair (i, j) only
+  ever needs the slice that holds patch j, so the counts against a slice can run while the next slice is
+  still on the bus.  Pays only when a slice's work dwarfs its fixed costs (not at C3: DESIGN.md section 7).
 
 Every upload is enqueued before the first count (`yawb_upload_catalog` is asynchronous), the slices are
 views of the caller's buffers (rows of a patch are contiguous), and the per-slice results are scattered
@@ -74,34 +78,50 @@ def count_cross_pipelined(engine, host: dict, pair_i: np.ndarray, pair_j: np.nda
     first-role catalogs and the slices of the second-role ones) for the caller to query and free."""
     pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
     pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
-    first = [k for k in ("ref_rand", "ref") if host.get(k) is not None]
-    second = [k for k in ("unk_rand", "unk") if host.get(k) is not None]
-    # enqueue every copy up front, in the order the counts will want them: first-role catalogs, then the
-    # slices of the second-role catalogs, randoms (usually the larger ones) in front
+    def rows(k):
+        return int(host[k]["patch_off"][-1])
+
+    # smaller catalogs first (ties: data before randoms): the cheap pair (reference x unknown) gets the GPU
+    # going a few ms into the transfer, and every count that does not need the last catalog is done by the
+    # time it arrives; what is left then is its index and the counts against it
+    first = sorted((k for k in ("ref", "ref_rand") if host.get(k) is not None), key=rows)
+    second = sorted((k for k in ("unk", "unk_rand") if host.get(k) is not None), key=rows)
+    order = []  # upload order: F0, S0, F1, S1
+    for f, s2 in zip(first, second):
+        order += [f, s2]
+    order += first[len(second):] + second[len(first):]
+
+    # enqueue every copy up front
     devices: dict[str, list] = {}
-    for k in first:
+    arrival: dict[tuple[str, int], int] = {}
+    for k in order:
         h = host[k]
-        devices[k] = [(engine.upload_catalog(h["xyz"], h["patch_off"], weights=h.get("weights"), zbin=h.get("zbin"),
-                                             n_bins=h.get("n_bins", 1)), 0, len(h["patch_off"]) - 1)]
-    for k in second:
-        devices[k] = upload_patch_slices(engine, host[k], groups)
+        if k in first:
+            devices[k] = [(engine.upload_catalog(h["xyz"], h["patch_off"], weights=h.get("weights"), zbin=h.get("zbin"),
+                                                 n_bins=h.get("n_bins", 1)), 0, len(h["patch_off"]) - 1)]
+        else:
+            devices[k] = upload_patch_slices(engine, h, groups)
+        for n in range(len(devices[k])):
+            arrival[(k, n)] = len(arrival)
 
     n_bins = max(host[k].get("n_bins", 1) for k in first) if first else 1
     shape = (len(pair_i), n_bins, r2.shape[1] - 1)
     counts, sums, stats = {}, {}, {}
-    for k2 in second:
-        for dev2, lo, hi in devices[k2]:
-            sel = np.flatnonzero((pair_j >= lo) & (pair_j < hi))
-            for k1 in first:
-                tag = next(t for t, (a, b) in COUNT_TYPES.items() if (a, b) == (k1, k2))
-                if tag not in counts:
-                    counts[tag] = np.zeros(shape, dtype=np.int64)
-                    sums[tag] = np.zeros(shape, dtype=np.float64)
-                    stats[tag] = {}
-                if len(sel) == 0:
-                    continue
-                ci, cf, st = engine.count(devices[k1][0][0], dev2, pair_i[sel], pair_j[sel], r2)
-                counts[tag][sel], sums[tag][sel] = ci, cf
-                for key, val in st.items():
-                    stats[tag][key] = stats[tag].get(key, 0) + val
+    # counts in the order in which their inputs are complete
+    jobs = sorted(((max(arrival[(k1, 0)], arrival[(k2, n)]), arrival[(k2, n)], k1, k2, n)
+                   for k1 in first for k2 in second for n in range(len(devices[k2]))))
+    for _, _, k1, k2, n in jobs:
+        tag = next(t for t, (a, b) in COUNT_TYPES.items() if (a, b) == (k1, k2))
+        if tag not in counts:
+            counts[tag] = np.zeros(shape, dtype=np.int64)
+            sums[tag] = np.zeros(shape, dtype=np.float64)
+            stats[tag] = {}
+        dev2, lo, hi = devices[k2][n]
+        sel = np.flatnonzero((pair_j >= lo) & (pair_j < hi))
+        if len(sel) == 0:
+            continue
+        ci, cf, st = engine.count(devices[k1][0][0], dev2, pair_i[sel], pair_j[sel], r2)
+        counts[tag][sel], sums[tag][sel] = ci, cf
+        for key, val in st.items():
+            stats[tag][key] = stats[tag].get(key, 0) + val
     return counts, sums, stats, devices
