@@ -41,6 +41,11 @@ WORKLOADS = {
     "C1": dict(n=(100_000, 100_000, 1_000_000, 1_000_000), grid=(4, 4), zmin=0.1, zmax=1.0, bins=10),
     "C3": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30),
     "C5": dict(n=(10_000_000, 100_000_000, 100_000_000, 100_000_000), grid=(16, 16), zmin=0.07, zmax=1.42, bins=50),
+    # C3 with three scales (sub-bin histogram path of the kernel) / with r-weights (resolution 50)
+    "C4": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30,
+               scales=dict(rmin=[100, 300, 500], rmax=[1000, 1500, 2000])),
+    "C3w": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30,
+                scales=dict(rmin=100, rmax=1000, rweight=-1.0, resolution=50)),
 }
 BOX = (0.0, 40.0, -12.5, 12.5)
 SEEDS = dict(ref=1, unk=2, ref_rand=3, unk_rand=4)
@@ -66,7 +71,8 @@ def make_workload(name: str, scale: float = 1.0, field: int = 0):
     decs = BOX[2] + (np.arange(ny) + 0.5) * (BOX[3] - BOX[2]) / ny
     centers = yb.AngularCoordinates(np.deg2rad([[r, d] for d in decs for r in ras]))
     pool = np.random.default_rng(7).uniform(spec["zmin"], spec["zmax"], 1_000_000)
-    config = yb.Configuration.create(rmin=100, rmax=1000, zmin=spec["zmin"], zmax=spec["zmax"], num_bins=spec["bins"])
+    config = yb.Configuration.create(**spec.get("scales", dict(rmin=100, rmax=1000)), zmin=spec["zmin"], zmax=spec["zmax"],
+                                     num_bins=spec["bins"])
     binning = config.binning.binning
 
     t0 = time.perf_counter()
@@ -503,7 +509,7 @@ def run_gpu_arm(args):
         scaling="weak" if (weak or world == 1) else "strong", vs_baseline=None, dtype="f32+f64", data="synthetic",
         config=dict(
             workload=f"{wl['name']} crosscorrelate DD+DR+RD+RR: {wl['spec']['n']} rows x scale {args.scale}, "
-                     f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, 100-1000 kpc, BoxRandoms {BOX}"
+                     f"{wl['n_patch']} patches, {wl['spec']['bins']} z-bins, {wl['spec'].get('scales', '100-1000 kpc')}, BoxRandoms {BOX}"
                      + (f"; x {world} independent fields (sky area and rows grow with the GPU count, one field per GPU)"
                         if weak else ""),
             linked_patch_pairs=int(len(pi)), naive_pair_tests=wl["naive"], pairs_in_scale=in_scale,

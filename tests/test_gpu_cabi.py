@@ -260,3 +260,32 @@ def test_pair_test_variants_exact(engine, variant, monkeypatch):
     ei, _, _ = single_patch_hist(engine, xyz[: n // 2], None, xyz[n // 2 :], None, r2, True)
     assert_array_equal(fi, ei)
     assert ei[0] > 1e6 and fs["rechecks"] > 0
+
+
+def test_device_memory_is_recycled(engine):
+    """upload / count / free cycles of varying size: the context's caching allocator reuses its blocks, the
+    footprint on the device stops growing after the first cycles"""
+    import torch
+
+    rng = np.random.default_rng(5)
+    r2 = np.array([[1e-8, 4e-6]])
+
+    def cycle(n):
+        a = oracle.radec_to_xyz(rng.uniform(0.0, 0.05, n), rng.uniform(-0.02, 0.02, n))
+        off = np.array([0, n // 2, n], dtype=np.int64)
+        cat = engine.upload_catalog(a, off)
+        ci, _, _ = engine.count(cat, cat, np.array([0, 1], dtype=np.int32), np.array([0, 1], dtype=np.int32), r2)
+        cat.free()
+        return int(ci.sum())
+
+    sizes = [200_000, 50_000, 120_000, 200_000, 80_000]
+    first = [cycle(n) for n in sizes]
+    engine.sync()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(4):
+        for n in sizes:
+            cycle(n)
+    engine.sync()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 32 << 20, f"device footprint grew by {(free0 - free1) >> 20} MiB"
+    assert all(c > 0 for c in first)
