@@ -91,7 +91,7 @@ def make_workload(name: str, scale: float = 1.0, field: int = 0):
     links = PatchLinkage.from_catalogs(config, cats["ref"], cats["unk"], cats["ref_rand"], cats["unk_rand"])
     pair_i, pair_j = links.get_patch_id_pairs(auto=False)
     amin, amax = _angles_per_bin(config)
-    plan = AngularBinPlan(amin, amax, None, None)
+    plan = AngularBinPlan(amin, amax, config.scales.rweight, config.scales.resolution)
 
     # naive linked pair tests per count type
     naive = {}
