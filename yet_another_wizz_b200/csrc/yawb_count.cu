@@ -125,6 +125,8 @@ struct WarpSmem {
     unsigned *hist;           // [nsub] (MULTI)
     unsigned short *lbin;     // [LCAP] z-bin of the candidate
     unsigned short *seg;      // [LCAP] first entry of every z-bin segment of the staged list
+    float *cum;               // [n_bins][CUM_EDGES] ramp offsets K (e_k - mid) + 1/2 of the item (MULTI && SAT)
+    unsigned *cumtot;         // [CUM_EDGES] cumulative counts of one z-bin segment (MULTI && SAT)
 };
 
 // ---- exact re-evaluation of one lane's share of a chunk, done by the whole warp ----------------
@@ -247,6 +249,117 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
         cnt_total += c;
         if (WEIGHTED) w_total += wsum;
     }
+}
+
+// ---- phase 2, a few sub-bins (multi-scale without r-weights), unweighted: cumulative counts --------
+// For up to CUM_EDGES edges the sub-bin histogram is obtained without classifying anything: for every edge
+// e_k the pairs with d2 <= e_k are COUNTED with the same saturating ramp as in the single-bin test,
+//     v_k = sat(K (e_k - mid - u) + 1/2),     sum(v_k) == sum(v_k^2)  <=>  every test was decided,
+// CUM_GROUP edges per pass over the chunk (the distance is recomputed per pass: 2 + 2 CUM_GROUP FP32
+// lane-operations per test and pass), and the histogram is the difference of neighbouring cumulative
+// counts.  Undecided chunks are recounted exactly per lane as in the single-bin path.
+#ifndef YAWB_CUM_GROUP
+#define YAWB_CUM_GROUP 3
+#endif
+constexpr int CUM_GROUP = YAWB_CUM_GROUP;
+constexpr int CUM_MAX_EDGES = 8;  // n_edges up to this selects the path
+constexpr int CUM_EDGES = ((CUM_MAX_EDGES + CUM_GROUP - 1) / CUM_GROUP) * CUM_GROUP;  // table stride (padded)
+constexpr int CUM_CHUNK = 8;
+
+template <int G>
+__device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *lidx, int e0, int e1, const Tile &tl,
+                                              int lane, int src, const double *ed, int k0, int ne,
+                                              unsigned (&cnt_out)[G], unsigned &n_recheck) {
+    unsigned cnt[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) cnt[g] = 0;
+    for (int t = lane; t < CUM_CHUNK * YAWB_RPL; t += 32) {
+        const int e = e0 + (t & (CUM_CHUNK - 1));
+        const int k = src + 32 * (t / CUM_CHUNK);
+        if (e < e1 && k < tl.count) {
+            const int i = lidx[e], j = tl.start + k;
+            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (k0 + g < ne && d2 <= ed[k0 + g]) cnt[g] += 1;
+            n_recheck += 1;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) cnt_out[g] = __reduce_add_sync(FULL, cnt[g]);
+}
+
+// entries [ea, eb) of the list belong to z-bin b; adds the sub-bin counts of the segment to S.acc
+__device__ __forceinline__ void phase2_cumul(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
+                                             const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL], float nk,
+                                             const Tile &tl, int lane, int b, unsigned &n_recheck) {
+    const int ne = P.n_edges;
+    const double *ed = P.r2 + (size_t)b * ne;
+    for (int k0 = 0; k0 < ne; k0 += CUM_GROUP) {
+        float off[CUM_GROUP];
+#pragma unroll
+        for (int g = 0; g < CUM_GROUP; ++g) off[g] = S.cum[b * CUM_EDGES + k0 + g];
+        unsigned cnt[CUM_GROUP];
+#pragma unroll
+        for (int g = 0; g < CUM_GROUP; ++g) cnt[g] = 0;
+        for (int e0 = ea; e0 < eb; e0 += CUM_CHUNK) {
+            const int e1 = min(e0 + CUM_CHUNK, eb);
+            float2 acc_a[CUM_GROUP], acc_b[CUM_GROUP];
+#pragma unroll
+            for (int g = 0; g < CUM_GROUP; ++g) acc_a[g] = acc_b[g] = make_float2(0.f, 0.f);
+            for (int e = e0; e < e1; ++e) {
+                const Cand c = S.list[e];
+                const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
+                const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
+#pragma unroll
+                for (int k = 0; k < HPL; ++k) {
+                    float2 u = __fadd2_rn(rn[k], sw);
+                    u = __ffma2_rn(rx[k], sx, u);
+                    u = __ffma2_rn(ry[k], sy, u);
+                    u = __ffma2_rn(rz[k], sz, u);
+#pragma unroll
+                    for (int g = 0; g < CUM_GROUP; ++g) {
+                        float2 v;
+                        v.x = __saturatef(fmaf(u.x, nk, off[g]));  // nk = -K
+                        v.y = __saturatef(fmaf(u.y, nk, off[g]));
+                        acc_a[g] = __fadd2_rn(acc_a[g], v);
+                        acc_b[g] = __ffma2_rn(v, v, acc_b[g]);
+                    }
+                }
+            }
+            unsigned c[CUM_GROUP];
+            bool bad = false;
+#pragma unroll
+            for (int g = 0; g < CUM_GROUP; ++g) {
+                const float sa = acc_a[g].x + acc_a[g].y, sb = acc_b[g].x + acc_b[g].y;
+                c[g] = (unsigned)(sa + 0.5f);
+                bad = bad || sa != sb;
+            }
+            unsigned flagged = __ballot_sync(FULL, bad);
+            while (flagged) {  // warp-uniform: some lane met the uncertainty band of an edge
+                const int src = __ffs(flagged) - 1;
+                flagged &= flagged - 1;
+                unsigned cx[CUM_GROUP];
+                recheck_cumul<CUM_GROUP>(P, S.lidx, e0, e1, tl, lane, src, ed, k0, ne, cx, n_recheck);
+                if (lane == src) {
+#pragma unroll
+                    for (int g = 0; g < CUM_GROUP; ++g) c[g] = cx[g];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < CUM_GROUP; ++g) cnt[g] += c[g];
+        }
+#pragma unroll
+        for (int g = 0; g < CUM_GROUP; ++g) {
+            const unsigned tot = __reduce_add_sync(FULL, cnt[g]);
+            if (lane == 0) S.cumtot[k0 + g] = tot;
+        }
+    }
+    __syncwarp();
+    // pairs with r2[s] < d2 <= r2[s + 1]: difference of the cumulative counts
+    if (lane < ne - 1) S.acc[(size_t)b * (ne - 1) + lane] += (unsigned long long)(S.cumtot[lane + 1] - S.cumtot[lane]);
+    __syncwarp();
 }
 
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
@@ -490,7 +603,9 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         if (a.weighted) {
             if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
         } else {
-            if (multi) LAUNCH(false, true, false);
+            // few sub-bins (multi-scale without r-weights): cumulative counts with the saturating test
+            if (multi && sat && a.n_edges <= CUM_MAX_EDGES) LAUNCH(false, true, true);
+            else if (multi) LAUNCH(false, true, false);
             else if (sat) LAUNCH(false, false, true);
             else LAUNCH(false, false, false);
         }

@@ -69,6 +69,8 @@ struct Channel {
     double *accw, *histw;
     int *bin_iv0, *bin_iu, *cstart, *rs0, *rpre, *cbin;
     unsigned *hist;
+    float *cum;        // MULTI && SAT: ramp offsets of the current item, [n_bins][CUM_EDGES]
+    unsigned *cumtot;  // MULTI && SAT: cumulative counts of one segment, [CUM_EDGES]
     unsigned short *seg;
 };
 
@@ -82,7 +84,7 @@ __host__ __device__ inline size_t ws_chan_bytes(bool weighted, bool multi, int n
     b += (size_t)n_bins * sizeof(float2);
     b += (size_t)nbuf * WS_LB * sizeof(int);
     b += (size_t)(3 * n_bins + 1) * sizeof(int) + 3 * CCAP * sizeof(int);
-    if (multi) b += (size_t)nsub * sizeof(unsigned);
+    if (multi) b += (size_t)nsub * sizeof(unsigned) + ((size_t)n_bins + 1) * CUM_EDGES * sizeof(float);
     b += (size_t)(nbuf + 1) * WS_LB * sizeof(unsigned short);
     return (b + 15) & ~(size_t)15;
 }
@@ -107,7 +109,12 @@ __device__ __forceinline__ void ws_carve(Channel<WEIGHTED> &C, unsigned char *p,
     C.rs0 = (int *)p; p += CCAP * sizeof(int);
     C.rpre = (int *)p; p += CCAP * sizeof(int);
     C.cbin = (int *)p; p += CCAP * sizeof(int);
-    if (multi) { C.hist = (unsigned *)p; p += (size_t)nsub * sizeof(unsigned); }
+    C.cum = nullptr; C.cumtot = nullptr;
+    if (multi) {
+        C.hist = (unsigned *)p; p += (size_t)nsub * sizeof(unsigned);
+        C.cum = (float *)p; p += (size_t)n_bins * CUM_EDGES * sizeof(float);
+        C.cumtot = (unsigned *)p; p += (size_t)CUM_EDGES * sizeof(unsigned);
+    }
     C.lbin0 = (unsigned short *)p; p += (size_t)nbuf * WS_LB * sizeof(unsigned short);
     C.seg = (unsigned short *)p;
 }
@@ -149,7 +156,16 @@ __device__ __forceinline__ void ws_begin_item(const FastParams &P, const Channel
                 // |s|^2 - mid 4 + 1, first add 2 + 1, three FMAs 12 + 3, mid/h rounding 2)
                 const float eps = EPS32 * (32.0f * m2 + 8.0f * bp.mid) * 1.0001f;
                 C.binrec[b] = make_float4(hx, hy, hz, bp.mid);
-                if (MULTI) {
+                if (MULTI && SAT) {
+                    // cumulative counts per edge: v_k = sat(K (e_k - mid - u) + 1/2); the float copy of
+                    // e_k - mid adds at most eps32 |e_k - mid| to the error of u
+                    const float K = 0.4f / (eps + 4.0f * EPS32 * (float)bp.hi);
+                    C.binthr[b] = make_float2(-K, 0.f);
+                    const int ne = P.n_edges;
+                    for (int k = 0; k < CUM_EDGES; ++k)
+                        C.cum[b * CUM_EDGES + k] =
+                            k < ne ? fmaf(K, (float)(P.r2[(size_t)b * ne + k] - (double)bp.mid), 0.5f) : -1.0e30f;
+                } else if (MULTI) {
                     C.binthr[b] = make_float2(bp.h + eps, eps + 4.0f * EPS32 * (float)bp.hi);
                 } else if (SAT) {
                     const float K = 0.4f / eps;  // undecidable tests land in v = [0.1, 0.9]: v (1 - v) >= 0.09
@@ -338,6 +354,7 @@ __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WE
     WarpSmem<WEIGHTED> S;  // view of the current buffer for the shared phase-2 code
     S.list = C.list(buf); S.lw = C.lw(buf); S.lidx = C.lidx(buf); S.lbin = C.lbin(buf);
     S.hist = C.hist; S.histw = C.histw; S.acc = C.acc; S.accw = C.accw;
+    S.cum = C.cum; S.cumtot = C.cumtot;
     // segment table: positions where the z-bin changes (entries arrive sorted by z-bin)
     int n_seg = 0;
     for (int base = 0; base < L; base += 32) {
@@ -353,7 +370,10 @@ __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WE
         const int eb = sg + 1 < n_seg ? (int)C.seg[sg + 1] : L;
         const int b = S.lbin[ea];
         const float2 thr = C.binthr[b];
-        if (MULTI) {
+        if (MULTI && SAT && !WEIGHTED) {
+            if constexpr (!WEIGHTED)
+                phase2_cumul(P, S, ea, eb, rx, ry, rz, rn, thr.x, tl, lane, b, n_recheck);
+        } else if (MULTI) {
             for (int k = lane; k < nsub; k += 32) {
                 S.hist[k] = 0u;
                 if (WEIGHTED) S.histw[k] = 0.0;
