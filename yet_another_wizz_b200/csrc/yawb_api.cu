@@ -288,7 +288,12 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
 
     // host-side preparation of thresholds and the item table
     std::vector<BinPar> binpar(B);
-    std::vector<float> r2f((size_t)B * n_edges);
+    // float copy of the edges, followed (sub-bin paths only) by the arithmetic bin lookup of every z-bin:
+    // (scale, offset) with cell = lg2(d2) * scale + offset, and a table [n_cells] of the number of edges
+    // strictly below the start of each cell (a lower bound of the answer that the kernel fixes up)
+    const int lg_cells = n_edges > 2 ? 2 * n_edges : 0;
+    const size_t r2f_words = (size_t)B * n_edges + 2 * (size_t)B + ((size_t)B * lg_cells + 1) / 2;
+    std::vector<float> r2f(r2f_words, 0.f);
     for (int b = 0; b < B; ++b) {
         const double lo = r2_edges[(size_t)b * n_edges], hi = r2_edges[(size_t)b * n_edges + nsub];
         BinPar &bp = binpar[b];
@@ -300,6 +305,30 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
         bp.empty = !(hi > lo);
         bp.pad = 0;
         for (int e = 0; e < n_edges; ++e) r2f[(size_t)b * n_edges + e] = (float)r2_edges[(size_t)b * n_edges + e];
+        if (lg_cells) {
+            const double *ed = r2_edges + (size_t)b * n_edges;
+            double first = hi;  // smallest positive edge
+            for (int e = n_edges - 1; e >= 0; --e)
+                if (ed[e] > 0.0) first = ed[e];
+            const double L0 = first > 0.0 ? std::log2(first) : 0.0, L1 = hi > 0.0 ? std::log2(hi) : 0.0;
+            const double scale = L1 > L0 ? (double)lg_cells / (L1 - L0) : 0.0;
+            float *par = r2f.data() + (size_t)B * n_edges + 2 * (size_t)b;
+            par[0] = (float)scale;
+            // bias towards the lower cell (the table is a lower bound): twice the error of lg2.approx (2^-22
+            // relative) and of the float arithmetic on a value of this size, plus a margin
+            const double lmax = std::max(std::fabs(L0), std::fabs(L1)) + 1.0;
+            const double bias = 1.0e-3 + 2.0 * scale * lmax * 6.0e-7;
+            par[1] = (float)(-L0 * scale - bias);
+            unsigned short *T = reinterpret_cast<unsigned short *>(r2f.data() + (size_t)B * n_edges + 2 * (size_t)B) +
+                                (size_t)b * lg_cells;
+            for (int c = 0; c < lg_cells; ++c) {
+                const double start = scale > 0.0 ? std::exp2(L0 + (double)c / scale) * (1.0 - 1.0e-6) : 0.0;
+                int below = 0;
+                while (below < n_edges && ed[below] < start) ++below;
+                if (c == 0) below = 0;  // everything at or below the first positive edge starts from scratch
+                T[c] = (unsigned short)below;
+            }
+        }
     }
     double rmax_all = 0.0;
     for (int b = 0; b < B; ++b)
@@ -350,7 +379,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     DALLOC(d_pj, np1 * sizeof(int));
     DALLOC(d_base, (np1 + 1) * sizeof(long long));
     DALLOC(d_r2, (size_t)B * n_edges * sizeof(double));
-    DALLOC(d_r2f, (size_t)B * n_edges * sizeof(float));
+    DALLOC(d_r2f, r2f_words * sizeof(float));
     DALLOC(d_bp, B * sizeof(BinPar));
     DALLOC(d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long));
     if (weighted) DALLOC(d_w, std::max<size_t>(n_out, 1) * sizeof(double));
@@ -367,7 +396,7 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     }
     H2D_SMALL(d_base, item_base.data(), (n_pairs + 1) * sizeof(long long));
     H2D_SMALL(d_r2, r2_edges, (size_t)B * n_edges * sizeof(double));
-    H2D_SMALL(d_r2f, r2f.data(), (size_t)B * n_edges * sizeof(float));
+    H2D_SMALL(d_r2f, r2f.data(), r2f_words * sizeof(float));
     H2D_SMALL(d_bp, binpar.data(), B * sizeof(BinPar));
 #undef H2D_SMALL
     TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));

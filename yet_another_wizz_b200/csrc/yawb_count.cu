@@ -55,6 +55,10 @@ struct FastParams {
     int n_pairs, n_bins, n_edges;
     const double *r2;
     const float *r2f;
+    const float *lgpar;           // [n_bins][2] (scale, offset): cell = lg2(d2) * scale + offset (sub-bin paths)
+    const unsigned short *lgT;    // [n_bins][lg_cells] edges strictly below the start of a cell (lower bound)
+    int lg_cells;
+    int acc_global;               // general sub-bin path: segment histograms go straight to global atomics
     const BinPar *binpar;
     double rmax_all;  // largest search radius over the z-bins
     unsigned long long *out_cnt;
@@ -372,6 +376,9 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
     const int ne = P.n_edges;
     const float *ef = P.r2f + (size_t)b * ne;
     const double *ed = P.r2 + (size_t)b * ne;
+    const int nc = P.lg_cells;
+    const float lg_scale = P.lgpar[2 * b], lg_off = P.lgpar[2 * b + 1];
+    const unsigned short *lgT = P.lgT + (size_t)b * nc;
     for (int e = ea; e < eb; ++e) {
         const Cand c = S.list[e];
         const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
@@ -385,12 +392,12 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
             const float u = (r & 1) ? u2.y : u2.x;  // the compiler merges the two halves of a row pair
             if (fabsf(u) < h_out) {  // possibly inside [lo, hi]
                 const float d2f = u + mid;
-                int lo = 0, hi = ne;  // edges strictly below d2f (float copy of the edges)
-                while (lo < hi) {
-                    int m = (lo + hi) >> 1;
-                    if (ef[m] < d2f) lo = m + 1; else hi = m;
-                }
-                int k = lo;
+                // number of edges strictly below d2f (float copy of the edges): the edges are close to
+                // log-spaced, so a table over uniform cells of lg2(d2) gives a lower bound that is rarely
+                // off by more than one
+                const int cell = min(max((int)fmaf(__log2f(d2f), lg_scale, lg_off), 0), nc - 1);
+                int k = lgT[cell];
+                while (k < ne && ef[k] < d2f) ++k;
                 // distance to the neighbouring edges decides whether FP32 was good enough
                 float gap = FLT_MAX;
                 if (k > 0) gap = fminf(gap, d2f - ef[k - 1]);
@@ -538,6 +545,9 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.pair_i = a.d_pair_i; P.pair_j = a.d_pair_j; P.pair_item_base = a.d_pair_item_base;
     P.n_items = a.n_items; P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
     P.r2 = a.d_r2; P.r2f = a.d_r2f; P.binpar = a.d_binpar;
+    P.lg_cells = a.n_edges > 2 ? 2 * a.n_edges : 0;
+    P.lgpar = a.d_r2f + (size_t)a.n_bins * a.n_edges;
+    P.lgT = reinterpret_cast<const unsigned short *>(P.lgpar + 2 * (size_t)a.n_bins);
     P.out_cnt = a.d_out_cnt; P.out_w = a.d_out_w; P.counters = ctx->d_counters;
     if (a.n_items == 0) return 0;
 
@@ -587,10 +597,14 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         }
 #undef LAUNCH_WS
     } else {
-        // fewer warps per CTA when many z-bins x sub-bins make the per-warp accumulators large
+        // many z-bins x sub-bins: per-warp accumulators in shared memory would cost most of the occupancy, so
+        // the general sub-bin path sends every segment histogram straight to global atomics instead
+        const bool cumul = multi && !a.weighted && sat && a.n_edges <= CUM_MAX_EDGES;
+        const size_t acc_bytes = (size_t)a.n_bins * nsub * (a.weighted ? 16 : 8);
+        P.acc_global = multi && !cumul && acc_bytes > 2048;
         int warps = YAWB_WARPS;
-        while (warps > 1 && warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1) > 227 * 1024) warps /= 2;
-        const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1);
+        while (warps > 1 && warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global) > 227 * 1024) warps /= 2;
+        const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global);
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
         const int ctas = ctx->sms * YAWB_MIN_CTAS * (YAWB_WARPS / warps);
@@ -604,7 +618,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
             if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
         } else {
             // few sub-bins (multi-scale without r-weights): cumulative counts with the saturating test
-            if (multi && sat && a.n_edges <= CUM_MAX_EDGES) LAUNCH(false, true, true);
+            if (cumul) LAUNCH(false, true, true);
             else if (multi) LAUNCH(false, true, false);
             else if (sat) LAUNCH(false, false, true);
             else LAUNCH(false, false, false);

@@ -74,12 +74,17 @@ struct Channel {
     unsigned short *seg;
 };
 
-__host__ __device__ inline size_t ws_chan_bytes(bool weighted, bool multi, int n_bins, int nsub, int nbuf = 2) {
+// `acc_global`: the per-warp accumulators [n_bins][nsub] are NOT kept in shared memory (many sub-bins: they
+// would cost most of the occupancy); the histogram of every z-bin segment goes straight to global atomics.
+__host__ __device__ inline size_t ws_chan_bytes(bool weighted, bool multi, int n_bins, int nsub, int nbuf = 2,
+                                                bool acc_global = false) {
     size_t b = sizeof(ChanCtl);
     b += (size_t)nbuf * WS_LB * sizeof(Cand) + (size_t)n_bins * sizeof(float4);
     if (weighted) b += (size_t)nbuf * WS_LB * sizeof(double);
-    b += (size_t)n_bins * nsub * sizeof(unsigned long long);
-    if (weighted) b += (size_t)n_bins * nsub * sizeof(double);
+    if (!acc_global) {
+        b += (size_t)n_bins * nsub * sizeof(unsigned long long);
+        if (weighted) b += (size_t)n_bins * nsub * sizeof(double);
+    }
     if (multi && weighted) b += (size_t)nsub * sizeof(double);
     b += (size_t)n_bins * sizeof(float2);
     b += (size_t)nbuf * WS_LB * sizeof(int);
@@ -91,8 +96,8 @@ __host__ __device__ inline size_t ws_chan_bytes(bool weighted, bool multi, int n
 
 template <bool WEIGHTED>
 __device__ __forceinline__ void ws_carve(Channel<WEIGHTED> &C, unsigned char *p, bool multi, int n_bins, int nsub,
-                                         int nbuf = 2) {
-    const size_t nacc = (size_t)n_bins * nsub;
+                                         int nbuf = 2, bool acc_global = false) {
+    const size_t nacc = acc_global ? 0 : (size_t)n_bins * nsub;
     C.ctl = (ChanCtl *)p; p += sizeof(ChanCtl);
     C.list0 = (Cand *)p; p += (size_t)nbuf * WS_LB * sizeof(Cand);
     C.binrec = (float4 *)p; p += (size_t)n_bins * sizeof(float4);
@@ -350,7 +355,7 @@ template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WEIGHTED> &C, int buf, int L,
                                            const float2 (&rx)[HPL], const float2 (&ry)[HPL],
                                            const float2 (&rz)[HPL], const float2 (&rn)[HPL],
-                                           const Tile &tl, int lane, int nsub, unsigned &n_recheck) {
+                                           const Tile &tl, int lane, int nsub, unsigned &n_recheck, int cur_pair = 0) {
     WarpSmem<WEIGHTED> S;  // view of the current buffer for the shared phase-2 code
     S.list = C.list(buf); S.lw = C.lw(buf); S.lidx = C.lidx(buf); S.lbin = C.lbin(buf);
     S.hist = C.hist; S.histw = C.histw; S.acc = C.acc; S.accw = C.accw;
@@ -382,9 +387,17 @@ __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WE
             phase2_multi<WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, C.binrec[b].w, tl, lane, b,
                                    n_recheck);
             __syncwarp();
-            for (int k = lane; k < nsub; k += 32) {
-                S.acc[(size_t)b * nsub + k] += S.hist[k];
-                if (WEIGHTED) S.accw[(size_t)b * nsub + k] += S.histw[k];
+            if (P.acc_global) {  // straight to the result: one atomic per non-empty sub-bin of the segment
+                const size_t o = ((size_t)cur_pair * P.n_bins + b) * nsub;
+                for (int k = lane; k < nsub; k += 32) {
+                    if (S.hist[k]) atomicAdd(&P.out_cnt[o + k], (unsigned long long)S.hist[k]);
+                    if (WEIGHTED && S.histw[k] != 0.0) atomicAdd(&P.out_w[o + k], S.histw[k]);
+                }
+            } else {
+                for (int k = lane; k < nsub; k += 32) {
+                    S.acc[(size_t)b * nsub + k] += S.hist[k];
+                    if (WEIGHTED) S.accw[(size_t)b * nsub + k] += S.histw[k];
+                }
             }
             __syncwarp();
         } else {
@@ -623,10 +636,11 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_uni(co
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nsub = P.n_edges - 1;
-    const int nacc = P.n_bins * nsub;
+    const bool acc_global = MULTI && P.acc_global;
+    const int nacc = acc_global ? 0 : P.n_bins * nsub;  // accumulators kept in shared memory
     Channel<WEIGHTED> C;
-    ws_carve<WEIGHTED>(C, smem_raw + (size_t)warp * ws_chan_bytes(WEIGHTED, MULTI, P.n_bins, nsub, 1), MULTI, P.n_bins,
-                       nsub, 1);
+    ws_carve<WEIGHTED>(C, smem_raw + (size_t)warp * ws_chan_bytes(WEIGHTED, MULTI, P.n_bins, nsub, 1, acc_global), MULTI,
+                       P.n_bins, nsub, 1, acc_global);
     ChanCtl &ctl = *C.ctl;
     for (int k = lane; k < nacc; k += 32) {
         C.acc[k] = 0ull;
@@ -735,8 +749,9 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, YAWB_MIN_CTAS) k_count_uni(co
             const int L = ws_fill<WEIGHTED, 2>(P, C, 0, lane, done);
             __syncwarp();
             if (L > 0 && P.debug != 1) {
-                ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck);
-                if (P.debug == 2) ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck);
+                ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
+                if (P.debug == 2)
+                    ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
             }
             n_tests += (unsigned long long)L * (unsigned long long)tl.count;
             __syncwarp();
