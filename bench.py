@@ -44,6 +44,9 @@ WORKLOADS = {
     # C3 with three scales (sub-bin histogram path of the kernel) / with r-weights (resolution 50)
     "C4": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30,
                scales=dict(rmin=[100, 300, 500], rmax=[1000, 1500, 2000])),
+    # C3 with weights on the data samples (SURVEY.md section 8d "weighted variants")
+    "C3wt": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30,
+                 weighted=True),
     "C3w": dict(n=(1_000_000, 10_000_000, 10_000_000, 10_000_000), grid=(8, 8), zmin=0.07, zmax=1.42, bins=30,
                 scales=dict(rmin=100, rmax=1000, rweight=-1.0, resolution=50)),
 }
@@ -80,7 +83,8 @@ def make_workload(name: str, scale: float = 1.0, field: int = 0):
     for key, n in zip(("ref", "unk", "ref_rand", "unk_rand"), spec["n"]):
         n = max(int(n * scale), 1000)
         has_z = key in ("ref", "ref_rand")
-        gen = yb.BoxRandoms(*box, redshifts=pool if has_z else None, seed=SEEDS[key] + 100 * field)
+        wpool = np.random.default_rng(8).uniform(0.5, 1.5, 1_000_000) if (spec.get("weighted") and key in ("ref", "unk")) else None
+        gen = yb.BoxRandoms(*box, redshifts=pool if has_z else None, weights=wpool, seed=SEEDS[key] + 100 * field)
         cats[key] = yb.Catalog.from_random(key, gen, n, patch_centers=centers)
     t_cat = time.perf_counter() - t0
     t0 = time.perf_counter()
