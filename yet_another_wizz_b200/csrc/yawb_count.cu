@@ -607,7 +607,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global);
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
-        const int ctas = ctx->sms * YAWB_MIN_CTAS * (YAWB_WARPS / warps);
+        const int ctas = ctx->sms * (a.weighted ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS) * (YAWB_WARPS / warps);
 #define LAUNCH(W, M, T)                                                                                   \
     do {                                                                                                  \
         YAWB_CUDA(cudaFuncSetAttribute(k_count_uni<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
