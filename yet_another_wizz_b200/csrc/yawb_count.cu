@@ -259,15 +259,11 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
 // For up to CUM_EDGES edges the sub-bin histogram is obtained without classifying anything: for every edge
 // e_k the pairs with d2 <= e_k are COUNTED with the same saturating ramp as in the single-bin test,
 //     v_k = sat(K (e_k - mid - u) + 1/2),     sum(v_k) == sum(v_k^2)  <=>  every test was decided,
-// CUM_GROUP edges per pass over the chunk (the distance is recomputed per pass: 2 + 2 CUM_GROUP FP32
-// lane-operations per test and pass), and the histogram is the difference of neighbouring cumulative
-// counts.  Undecided chunks are recounted exactly per lane as in the single-bin path.
-#ifndef YAWB_CUM_GROUP
-#define YAWB_CUM_GROUP 3
-#endif
-constexpr int CUM_GROUP = YAWB_CUM_GROUP;
+// G edges per pass over the chunk (the distance is recomputed per pass: 2 + 2 G FP32 lane-operations per
+// test and pass; G is picked so that the edges need as few, as full passes as possible), and the histogram
+// is the difference of neighbouring cumulative counts.  Undecided chunks are recounted exactly per lane as in the single-bin path.
 constexpr int CUM_MAX_EDGES = 8;  // n_edges up to this selects the path
-constexpr int CUM_EDGES = ((CUM_MAX_EDGES + CUM_GROUP - 1) / CUM_GROUP) * CUM_GROUP;  // table stride (padded)
+constexpr int CUM_EDGES = 16;     // table stride: room for the padded last group of any group size
 constexpr int CUM_CHUNK = 8;
 
 template <int G>
@@ -294,7 +290,8 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
 }
 
 // entries [ea, eb) of the list belong to z-bin b; adds the sub-bin counts of the segment to S.acc
-__device__ __forceinline__ void phase2_cumul(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
+template <int CUM_GROUP>
+__device__ __forceinline__ void phase2_cumul_g(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
                                              const float2 (&rx)[HPL], const float2 (&ry)[HPL],
                                              const float2 (&rz)[HPL], const float2 (&rn)[HPL], float nk,
                                              const Tile &tl, int lane, int b, unsigned &n_recheck) {
@@ -364,6 +361,16 @@ __device__ __forceinline__ void phase2_cumul(const FastParams &P, const WarpSmem
     // pairs with r2[s] < d2 <= r2[s + 1]: difference of the cumulative counts
     if (lane < ne - 1) S.acc[(size_t)b * (ne - 1) + lane] += (unsigned long long)(S.cumtot[lane + 1] - S.cumtot[lane]);
     __syncwarp();
+}
+
+__device__ __forceinline__ void phase2_cumul(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
+                                             const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL], float nk,
+                                             const Tile &tl, int lane, int b, unsigned &n_recheck) {
+    const int ne = P.n_edges;  // measured on C4 (6 edges): one pass of 6 beats two of 3 beats three of 2
+    if (ne <= 3) phase2_cumul_g<3>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
+    else if (ne == 5 || ne == 6) phase2_cumul_g<6>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
+    else phase2_cumul_g<4>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
 }
 
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
@@ -607,7 +614,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global);
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
-        const int ctas = ctx->sms * (a.weighted ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS) * (YAWB_WARPS / warps);
+        const int ctas = ctx->sms * ((a.weighted || cumul) ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS) * (YAWB_WARPS / warps);
 #define LAUNCH(W, M, T)                                                                                   \
     do {                                                                                                  \
         YAWB_CUDA(cudaFuncSetAttribute(k_count_uni<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

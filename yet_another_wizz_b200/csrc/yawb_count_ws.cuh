@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32, 1) k_count_ws(const FastParams 
 // lives in the channel's shared-memory control block, so the registers of the hot loop are not shared
 // with long-lived scalars of the gather phase.
 template <bool WEIGHTED, bool MULTI, bool SAT>
-__global__ void __launch_bounds__(YAWB_WARPS * 32, WEIGHTED ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS)
+__global__ void __launch_bounds__(YAWB_WARPS * 32, (WEIGHTED || (MULTI && SAT)) ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS)
     k_count_uni(const FastParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;

@@ -73,7 +73,8 @@ constexpr int YAWB_WARPS = 4;             // warps per CTA in the count kernel
 #ifndef YAWB_MIN_CTAS_VALUE
 #define YAWB_MIN_CTAS_VALUE 5
 #endif
-constexpr int YAWB_MIN_CTAS_WEIGHTED = 4;   // weighted kernels keep FP64 row sums in registers: 128 registers, 4 CTAs per SM
+constexpr int YAWB_MIN_CTAS_WEIGHTED = 4;   // weighted kernels (FP64 row sums) and the cumulative sub-bin kernel (up to 12
+                                            // packed accumulators): 128 registers, 4 CTAs per SM
 constexpr int YAWB_MIN_CTAS = YAWB_MIN_CTAS_VALUE;  // CTAs per SM the count kernel is compiled for (register budget)
 constexpr int YAWB_MAX_EDGES = 256;
 
