@@ -16,9 +16,13 @@ two lines are directly comparable; `roofline` reports the tests the kernel actua
            the D2H of the per-patch-pair results, timed with CUDA events on the engine's stream
   e2e      the C-ABI calls with HOST buffers: H2D upload of every catalog from pinned memory,
            index build, counts, D2H of the results -- wall clock around the calls
+           (schedule: `yet_another_wizz_b200.pipeline.count_cross_pipelined`)
   --impl reference   the CPU implementation of the same path (oracle/cpu_port.py: scipy cKDTree
            dual-tree count_neighbors + multiprocessing task farm, exactly the reference's
            algorithm; /root/reference itself does not exist on the GPU box) on a bounded sample
+  --workload   C3 (default, the configuration the north-star target is quoted on), C1 (small), C5 (1e8-row
+           catalogs), C4 (C3 with three scales: cumulative sub-bin kernel), C3w (C3 with r-weights,
+           resolution 50: general sub-bin path), C3wt (C3 with weighted data samples)
 """
 
 from __future__ import annotations
@@ -57,6 +61,26 @@ FP32_INSTR_PER_TEST = 6  # 3 FSUB + FMUL + 2 FFMA, SURVEY.md section 8d
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+# stdout when NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the
+# result line goes to a private duplicate of the original stdout.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ---- workload ------------------------------------------------------------------------------------
@@ -288,7 +312,7 @@ def run_reference_arm(args):
         e2e=dict(value=value, unit="Gpairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------
@@ -558,7 +582,7 @@ def run_gpu_arm(args):
                    f"x 4 count types): tree build {cpu['t_build']:.2f}s + count {cpu['t_count']:.2f}s",
             extrapolated_full_job_s=t_cpu * total_naive / max(cpu["naive"], 1),
         )
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -579,6 +603,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one C3-sized field per GPU (default), strong = the one field split over the GPUs")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
