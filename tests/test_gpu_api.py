@@ -79,6 +79,25 @@ def test_pipelined_schedule_gpu(engine):
                 dev.free()
 
 
+def test_staging_cache_engine():
+    """`Engine(staging=True)`: catalogs prepared into the page-locked cache, blocks recycled between calls"""
+    from yet_another_wizz_b200 import Engine
+
+    eng = Engine(0, staging=True)
+    eng.staging_min_rows = 0
+    try:
+        g = golden_io.load("cross_unweighted")
+        for _ in range(3):
+            corrs = golden_cases.run_cross(g, eng)
+            golden_cases.check_corrfunc(g, "cross", corrs, ("dd", "dr", "rd", "rr"), exact=True)
+        assert len(eng._stage_used) == 0 and len(eng._stage_free) > 0
+        n_blocks = len(eng._stage_free)
+        golden_cases.run_cross(g, eng)
+        assert len(eng._stage_free) == n_blocks  # nothing new was page-locked
+    finally:
+        eng.close()
+
+
 def test_default_engine_and_stats():
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import measurements

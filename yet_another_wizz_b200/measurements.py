@@ -91,7 +91,7 @@ def _angles_per_bin(config) -> tuple[np.ndarray, np.ndarray]:
 
 
 def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = False,
-                           workers: int | None = None) -> dict:
+                           workers: int | None = None, alloc=None) -> dict:
     """Host preparation of one catalog for the C ABI: load every patch once, convert to unit
     vectors with the reference's formula (`AngularCoordinates.to_3d`: numpy cos / sin in double, so the
     device sees the doubles the reference's trees hold), digitise the redshifts (`trees.py:408-414`).
@@ -102,7 +102,9 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     call spends most of its time on, not the GPU.
 
     `kappa=True` prepares the "k" side of a scalar-field count: the per-row pair weight is
-    kappa x weight (kappa alone without weights), `AngularTree.get_pair_weights`, `trees.py:270-301`."""
+    kappa x weight (kappa alone without weights), `AngularTree.get_pair_weights`, `trees.py:270-301`.
+    `alloc(shape, dtype)` supplies the output arrays (page-locked staging of the engine; default numpy)."""
+    alloc = alloc or np.empty
     has_w = bool(catalog.has_weights) or kappa
     if binning is not None and not catalog.has_redshifts:
         raise ValueError("patch has no 'redshifts' attached")  # trees.py:397-398
@@ -112,9 +114,9 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     sizes = [int(n) for n in catalog.get_num_records()]
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n = int(off[-1])
-    xyz = np.empty((n, 3), dtype=np.float64)
-    ws = np.empty(n, dtype=np.float64) if has_w else None
-    zb = np.empty(n, dtype=np.int32) if binning is not None else None
+    xyz = alloc((n, 3), np.float64)
+    ws = alloc(n, np.float64) if has_w else None
+    zb = alloc(n, np.int32) if binning is not None else None
 
     def fill(pid: int) -> None:
         ra, dec, weights, redshifts, kappa_vals = _patch_rows(catalog[pid])
@@ -149,7 +151,10 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
 
 def upload_catalog(engine, catalog, binning: Binning | None, *, kappa: bool = False):
     """Replaces `Catalog.build_trees`: one upload, the index is built on the device."""
-    arrays = prepare_catalog_arrays(catalog, binning, kappa=kappa)
+    # opt-in (`Engine(staging=True)`): large catalogs are prepared straight into the engine's page-locked
+    # staging cache; the copy is then asynchronous and overlaps with the preparation of the next catalog
+    staged = getattr(engine, "staging", False) and sum(catalog.get_num_records()) >= engine.staging_min_rows
+    arrays = prepare_catalog_arrays(catalog, binning, kappa=kappa, alloc=engine.staging_empty if staged else None)
     return engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
 
 
@@ -170,6 +175,9 @@ class _Uploads:
         for dev in self._cache.values():
             dev.free()
         self._cache.clear()
+        if getattr(self.engine, "staging", False):  # every upload of this call has been consumed or dropped
+            self.engine.sync()
+            self.engine.staging_release()
 
 
 # ---- patch linkage ----------------------------------------------------------------------------------
