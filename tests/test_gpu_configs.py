@@ -209,3 +209,46 @@ def test_irregular_patch_footprints(engine):
     assert ei.sum() > 1e5
     assert fs["pair_tests"] < 0.02 * es["pair_tests"]  # pruning still effective on hollow boxes
     d1.free(); d2.free()
+
+
+def test_duplicates_and_dense_clumps(engine):
+    """collisions: many rows at exactly the same position (d2 == 0 must never be counted when the lower
+    edge is 0 <, and is counted in the first sub-bin otherwise), a clump much denser than the rest of the
+    patch (one sky cell holds thousands of rows), and single-row / empty z-bins"""
+    import oracle
+
+    rng = np.random.default_rng(23)
+    base_ra, base_dec = rng.uniform(0.0, 0.03, 4000), rng.uniform(-0.01, 0.01, 4000)
+    clump_ra, clump_dec = 0.011 + rng.normal(0, 2e-5, 6000), 0.002 + rng.normal(0, 2e-5, 6000)
+    dup_ra, dup_dec = np.full(3000, 0.02), np.full(3000, -0.004)  # 3000 identical points
+    ra = np.concatenate([base_ra, clump_ra, dup_ra]); dec = np.concatenate([base_dec, clump_dec, dup_dec])
+    order = rng.permutation(len(ra))
+    ra, dec = ra[order], dec[order]
+    xyz = oracle.radec_to_xyz(ra, dec)
+    patch_off = np.array([0, len(ra) // 2, len(ra)])
+    zbin = rng.integers(0, 3, len(ra)).astype(np.int32)
+    zbin[:5] = 5  # out of range: dropped
+    zbin[zbin == 2] = 1  # z-bin 2 is empty
+    zbin[7] = 2  # ... except for a single row
+    d1 = engine.upload_catalog(xyz, patch_off, zbin=zbin, n_bins=3)
+    d2 = engine.upload_catalog(xyz, patch_off)
+    pi, pj = np.array([0, 0, 1, 1]), np.array([0, 1, 0, 1])
+    for edges in (np.array([1e-5, 3e-4]), np.array([1e-6, 1e-5, 1e-4, 1e-3]), np.array([3e-5, 2e-3])):
+        r2 = np.tile(oracle.chord_sq_edges(edges), (3, 1))
+        fi, _, fs = engine.count(d1, d2, pi, pj, r2)
+        ei, _, _ = engine.count(d1, d2, pi, pj, r2, exact=True)
+        assert_array_equal(fi, ei)
+        assert ei.sum() > 1e6
+    # cross-check one case against the numpy oracle on a sub-sample of rows (self pairs at d2 == 0 excluded
+    # by the open lower edge)
+    sel = np.flatnonzero((zbin[: patch_off[1]] == 0))[:1500]
+    a = xyz[: patch_off[1]][sel]
+    sub_off = np.array([0, len(a)])
+    s1 = engine.upload_catalog(a, sub_off, zbin=np.zeros(len(a), dtype=np.int32), n_bins=1)
+    s2 = engine.upload_catalog(a, sub_off)
+    r2 = oracle.chord_sq_edges(np.array([1e-6, 1e-4, 1e-3]))[None, :]
+    fi, _, _ = engine.count(s1, s2, np.array([0]), np.array([0]), r2)
+    want = oracle.pair_histogram(a, a, None, None, r2[0])
+    assert_array_equal(fi[0, 0], want)
+    for d in (d1, d2, s1, s2):
+        d.free()
