@@ -749,11 +749,15 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, (WEIGHTED || (MULTI && SAT)) 
         while (!done) {
             const int L = ws_fill<WEIGHTED, 2>(P, C, 0, lane, done);
             __syncwarp();
+#ifdef YAWB_DEBUG_MODES  // development builds: YAWB_DEBUG_MODE=1 skips the pair tests, 2 runs them twice (phase timing)
             if (L > 0 && P.debug != 1) {
                 ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
                 if (P.debug == 2)
                     ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
             }
+#else
+            if (L > 0) ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
+#endif
             n_tests += (unsigned long long)L * (unsigned long long)tl.count;
             __syncwarp();
         }
