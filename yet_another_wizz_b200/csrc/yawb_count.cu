@@ -578,32 +578,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     const char *variant = getenv("YAWB_PAIR_TEST");
     const bool sat = !(variant && strcmp(variant, "pred") == 0);
 
-    // default: unified kernel (every warp gathers for itself, then tests); YAWB_KERNEL=ws selects the
-    // warp-specialised variant (gather warps + test warps, one CTA per SM) kept for experiments
-    const size_t smem_ws = WS_CONSUMERS * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub);
-    const char *kern = getenv("YAWB_KERNEL");
-    const bool use_ws = smem_ws <= 227 * 1024 && kern && strcmp(kern, "ws") == 0;
-    if (use_ws) {
-#define LAUNCH_WS(W, M, T)                                                                              \
-    do {                                                                                                \
-        cudaFuncAttributes fa;                                                                          \
-        YAWB_CUDA(cudaFuncGetAttributes(&fa, k_count_ws<W, M, T>));                                     \
-        /* setmaxnreg.inc would wait forever if the CTA were launched with fewer registers */           \
-        YAWB_REQUIRE(fa.numRegs >= WS_REGS_LAUNCH, "k_count_ws compiled with %d registers, needs %d",   \
-                     fa.numRegs, WS_REGS_LAUNCH);                                                       \
-        YAWB_CUDA(cudaFuncSetAttribute(k_count_ws<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem_ws));                                                  \
-        k_count_ws<W, M, T><<<ctx->sms, WS_WARPS * 32, smem_ws, ctx->stream>>>(P);                      \
-    } while (0)
-        if (a.weighted) {
-            if (multi) LAUNCH_WS(true, true, false); else LAUNCH_WS(true, false, false);
-        } else {
-            if (multi) LAUNCH_WS(false, true, false);
-            else if (sat) LAUNCH_WS(false, false, true);
-            else LAUNCH_WS(false, false, false);
-        }
-#undef LAUNCH_WS
-    } else {
+    {
         // many z-bins x sub-bins: per-warp accumulators in shared memory would cost most of the occupancy, so
         // the general sub-bin path sends every segment histogram straight to global atomics instead
         const bool cumul = multi && !a.weighted && sat && a.n_edges <= CUM_MAX_EDGES;

@@ -1,61 +1,35 @@
-// Warp-specialised pair-count kernel (included by yawb_count.cu after the shared device functions).
+// The production pair-count kernel k_count_uni and its building blocks (included by yawb_count.cu after
+// the shared device functions).
 //
-// One CTA per SM, 24 warps: 8 GATHER warps feed 16 TEST warps through shared-memory channels; the
-// register file is re-balanced with setmaxnreg (gather warps 48 registers, test warps 96).
-//
-//   test warp    owns a register tile (YAWB_RPL rows per lane) of the second catalog; it posts the
-//                tile's box to its channel and then only runs the FP32 pair test (phase 2) on the
-//                candidate lists that arrive -- no global-memory latency on its critical path;
-//   gather warp  serves 2 channels round-robin: per item it derives the per-z-bin query boxes, cell
-//                rows and thresholds (step 1), resolves (z-bin, cell-row) runs (step 2) and streams
-//                the flattened candidates through the cull into the channel's double-buffered list
-//                (step 3).  Its loads are latency bound and overlap with the test warps' arithmetic.
-//
-// Hand-over: per buffer one `full` word in shared memory (0 = free, else 1 + 2 L + done), written after
-// a block-level fence and polled with volatile loads; all warps of a CTA are co-resident, so the
-// spin-waits cannot deadlock.
+// Every warp owns a shared-memory channel (control block + tables + one candidate list) and loops over
+// work items (register tile of the second catalog x linked first-catalog patch):
+//   step 1  ws_begin_item  one lane per z-bin: query box -> cell rows, FP32 error bound, thresholds
+//   step 2  ws_fill        one lane per (z-bin, cell row): the contiguous run of candidate rows
+//   step 3  ws_fill        flattened gather of the runs, cull against the z-bin's box, stage the survivors
+//                          in the tile-local frame
+//   tests   ws_consume     one pass of the FP32 pair test per z-bin segment of the staged list
+// A warp-specialised variant (8 gather warps feeding 16 test warps per SM through double-buffered
+// channels, setmaxnreg-rebalanced registers) was measured slower on B200 in round 1 (11-16 ms against
+// 7 ms for C3) and removed; see DESIGN.md section 4.1 and the git history.
 #pragma once
 
-constexpr int WS_PRODUCERS = 8;      // two warpgroups of gather warps
-constexpr int WS_PER_PRODUCER = 2;   // channels served by one gather warp
-constexpr int WS_CONSUMERS = WS_PRODUCERS * WS_PER_PRODUCER;
-constexpr int WS_WARPS = WS_PRODUCERS + WS_CONSUMERS;
 #ifndef YAWB_WS_LB
 #define YAWB_WS_LB 192
 #endif
 constexpr int WS_LB = YAWB_WS_LB;  // entries per list buffer
-#ifndef YAWB_WS_SUB
-#define YAWB_WS_SUB 4
-#endif
-#ifndef YAWB_WS_REGS_GATHER
-#define YAWB_WS_REGS_GATHER 48
-#endif
-#ifndef YAWB_WS_REGS_TEST
-#define YAWB_WS_REGS_TEST 96
-#endif
-constexpr int WS_SUB = YAWB_WS_SUB;  // sub-batches of 32 candidates gathered per iteration (3 * WS_SUB loads in flight per lane)
-// setmaxnreg budget: the CTA is launched with WS_REGS_LAUNCH registers per thread (768 threads, 1 CTA/SM);
-// gather warps shrink to WS_REGS_GATHER, test warps grow to WS_REGS_TEST:  8*32*48 + 16*32*96 = 768*80
-constexpr int WS_REGS_GATHER = YAWB_WS_REGS_GATHER, WS_REGS_TEST = YAWB_WS_REGS_TEST, WS_REGS_LAUNCH = 80;
-static_assert(WS_PRODUCERS * WS_REGS_GATHER + WS_CONSUMERS * WS_REGS_TEST <= WS_WARPS * WS_REGS_LAUNCH,
-              "setmaxnreg budget exceeds the registers the CTA is launched with");
 
 struct __align__(16) ChanCtl {
     double ou, ov, ot;                            // centre of the tile box = origin of the staged vectors
     double umin, umax, vmin, vmax, tmin, tmax;    // tile box in the frame of patch p1
-    int seq;                                      // test -> gather: bumped when an item (or quit) is posted
-    int quit;
     int p1;
     int b_lo, b_hi;
-    int full[2];                                  // gather -> test: 0 = free, else 1 + 2 * L + done
     int st_cb, st_ncand, st_t0, st_have, st_ncombo;  // gather progress of the current item
-    int p_seen, p_buf, p_active, p_quit;             // gather-warp private view of the channel
 };
 
 template <bool WEIGHTED>
 struct Channel {
     ChanCtl *ctl;
-    Cand *list0;              // two buffers of WS_LB entries each, addressed arithmetically (no
+    Cand *list0;              // `nbuf` buffers of WS_LB entries each, addressed arithmetically (no
     double *lw0;              // runtime-indexed pointer arrays: those would live in local memory)
     int *lidx0;
     unsigned short *lbin0;
@@ -125,10 +99,8 @@ __device__ __forceinline__ void ws_carve(Channel<WEIGHTED> &C, unsigned char *p,
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
-__device__ __forceinline__ void st_flag(int *p, int v) { *(volatile int *)p = v; }
 
-// ---- gather warp: step 1 for a freshly posted item ------------------------------------------------
+// ---- step 1 for a fresh item ------------------------------------------------
 template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void ws_begin_item(const FastParams &P, const Channel<WEIGHTED> &C, int lane) {
     ChanCtl &ctl = *C.ctl;
@@ -200,7 +172,7 @@ __device__ __forceinline__ void ws_begin_item(const FastParams &P, const Channel
     __syncwarp();
 }
 
-// ---- gather warp: produce one list buffer; returns L, sets `done` when the item is exhausted --------
+// ---- steps 2 + 3: produce one list buffer; returns L, sets `done` when the item is exhausted --------
 template <bool WEIGHTED, int SUB>
 __device__ __forceinline__ int ws_fill(const FastParams &P, const Channel<WEIGHTED> &C, int buf, int lane, bool &done) {
     ChanCtl &ctl = *C.ctl;
@@ -417,219 +389,9 @@ __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WE
     }
 }
 
-template <bool WEIGHTED, bool MULTI, bool SAT>
-__global__ void __launch_bounds__(WS_WARPS * 32, 1) k_count_ws(const FastParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nsub = P.n_edges - 1;
-    const int nacc = P.n_bins * nsub;
-    const size_t cbytes = ws_chan_bytes(WEIGHTED, MULTI, P.n_bins, nsub);
-
-    // channel control words must be valid before anybody polls them
-    for (int c = warp; c < WS_CONSUMERS; c += WS_WARPS) {
-        Channel<WEIGHTED> C;
-        ws_carve<WEIGHTED>(C, smem_raw + (size_t)c * cbytes, MULTI, P.n_bins, nsub);
-        if (lane == 0) {
-            C.ctl->seq = 0;
-            C.ctl->quit = 0;
-            C.ctl->full[0] = 0;
-            C.ctl->full[1] = 0;
-            C.ctl->p_seen = 0;
-            C.ctl->p_buf = 0;
-            C.ctl->p_active = 0;
-            C.ctl->p_quit = 0;
-        }
-        for (int k = lane; k < nacc; k += 32) {
-            C.acc[k] = 0ull;
-            if (WEIGHTED) C.accw[k] = 0.0;
-        }
-    }
-    __syncthreads();
-
-    if (warp < WS_PRODUCERS) {
-        // ================================ gather warp ================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_REGS_GATHER));
-        int n_quit = 0;
-        while (n_quit < WS_PER_PRODUCER) {
-            bool progressed = false;
-            for (int c = 0; c < WS_PER_PRODUCER; ++c) {
-                Channel<WEIGHTED> C;
-                ws_carve<WEIGHTED>(C, smem_raw + (size_t)(warp * WS_PER_PRODUCER + c) * cbytes, MULTI, P.n_bins, nsub);
-                ChanCtl &ctl = *C.ctl;
-                if (ctl.p_quit) continue;
-                if (!ctl.p_active) {
-                    const int s = ld_flag(&ctl.seq);
-                    if (s == ctl.p_seen) continue;
-                    __threadfence_block();
-                    if (ld_flag(&ctl.quit)) {
-                        __syncwarp();
-                        if (lane == 0) ctl.p_quit = 1;
-                        __syncwarp();
-                        ++n_quit;
-                        continue;
-                    }
-                    ws_begin_item<WEIGHTED, MULTI, SAT>(P, C, lane);
-                    if (lane == 0) {
-                        ctl.p_seen = s;
-                        ctl.p_active = 1;
-                    }
-                    __syncwarp();
-                }
-                const int buf = ctl.p_buf;
-                if (ld_flag(&ctl.full[buf]) != 0) continue;  // the test warp still reads this buffer
-                __threadfence_block();
-                bool done = false;
-                const int L = ws_fill<WEIGHTED, WS_SUB>(P, C, buf, lane, done);
-                __syncwarp();
-                if (lane == 0) {
-                    ctl.p_buf = buf ^ 1;
-                    if (done) ctl.p_active = 0;
-                    __threadfence_block();
-                    st_flag(&ctl.full[buf], 1 + 2 * L + (done ? 1 : 0));
-                }
-                __syncwarp();
-                progressed = true;
-            }
-            if (!progressed) __nanosleep(100);
-        }
-        return;
-    }
-
-    // ================================== test warp ==================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REGS_TEST));
-    Channel<WEIGHTED> C;
-    ws_carve<WEIGHTED>(C, smem_raw + (size_t)(warp - WS_PRODUCERS) * cbytes, MULTI, P.n_bins, nsub);
-    ChanCtl &ctl = *C.ctl;
-    int cur_pair = -1, buf = 0, seq = 0;
-    unsigned long long n_tests = 0;
-    unsigned n_recheck = 0;
-    const long long n_live = (long long)P.counters[4];  // written by k_plan
-
-    auto flush_pair = [&]() {
-        if (cur_pair < 0) return;
-        __syncwarp();
-        for (int k = lane; k < nacc; k += 32) {
-            const unsigned long long c = C.acc[k];
-            if (c) {
-                atomicAdd(&P.out_cnt[(size_t)cur_pair * nacc + k], c);
-                C.acc[k] = 0ull;
-            }
-            if (WEIGHTED) {
-                const double w = C.accw[k];
-                if (w != 0.0) {
-                    atomicAdd(&P.out_w[(size_t)cur_pair * nacc + k], w);
-                    C.accw[k] = 0.0;
-                }
-            }
-        }
-        __syncwarp();
-    };
-
-    long long grab_lo = 0, grab_hi = 0;  // items are taken GRAB at a time: neighbours share the patch pair
-    while (true) {
-        if (grab_lo >= grab_hi) {
-            if (lane == 0) grab_lo = (long long)atomicAdd(&P.counters[0], (unsigned long long)GRAB);
-            grab_lo = __shfl_sync(FULL, grab_lo, 0);
-            if (grab_lo >= n_live) break;
-            grab_hi = min(grab_lo + GRAB, n_live);
-        }
-        const int2 rec = P.live[grab_lo++];
-        if (rec.x != cur_pair) {
-            flush_pair();
-            cur_pair = rec.x;
-        }
-        const int p1 = P.pair_i[cur_pair];
-        const Tile tl = P.tiles[rec.y];
-        const PatchFrame &F = P.sframe[p1];
-
-        // rows of this lane in the frame of patch p1: pass 1 finds the tile box, pass 2 re-derives the
-        // coordinates relative to the box centre and rounds them ONCE to float
-        const double c0 = F.c[0], c1 = F.c[1], c2 = F.c[2];
-        const double a0 = F.e1[0], a1 = F.e1[1], a2 = F.e1[2];
-        const double g0 = F.e2[0], g1 = F.e2[1], g2 = F.e2[2];
-        double umin = DBL_MAX, umax = -DBL_MAX, vmin = DBL_MAX, vmax = -DBL_MAX, tmin = DBL_MAX, tmax = -DBL_MAX;
-#pragma unroll
-        for (int r = 0; r < YAWB_RPL; ++r) {
-            const int k = lane + 32 * r;
-            if (k < tl.count) {
-                const int j = tl.start + k;
-                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                const double lu = dx * a0 + dy * a1 + dz * a2;
-                const double lv = dx * g0 + dy * g1 + dz * g2;
-                const double lt = dx * c0 + dy * c1 + dz * c2;
-                umin = fmin(umin, lu); umax = fmax(umax, lu);
-                vmin = fmin(vmin, lv); vmax = fmax(vmax, lv);
-                tmin = fmin(tmin, lt); tmax = fmax(tmax, lt);
-            }
-        }
-        umin = warp_min(umin); umax = warp_max(umax);
-        vmin = warp_min(vmin); vmax = warp_max(vmax);
-        tmin = warp_min(tmin); tmax = warp_max(tmax);
-        const double ou = 0.5 * (umin + umax), ov = 0.5 * (vmin + vmax), ot = 0.5 * (tmin + tmax);
-
-        // post the item, then prepare the registers while the gather warp starts on it
-        if (lane == 0) {
-            ctl.ou = ou; ctl.ov = ov; ctl.ot = ot;
-            ctl.umin = umin; ctl.umax = umax; ctl.vmin = vmin; ctl.vmax = vmax; ctl.tmin = tmin; ctl.tmax = tmax;
-            ctl.p1 = p1;
-            ctl.b_lo = tl.bin >= 0 ? tl.bin : 0;
-            ctl.b_hi = tl.bin >= 0 ? tl.bin + 1 : P.n_bins;
-            __threadfence_block();
-            st_flag(&ctl.seq, ++seq);
-        }
-        float2 rx[HPL], ry[HPL], rz[HPL], rn[HPL];  // rows (2k, 2k+1) of the lane share one register pair
-#pragma unroll
-        for (int r = 0; r < YAWB_RPL; ++r) {
-            const int k = lane + 32 * r;
-            float x = FAR, y = FAR, z = FAR, n = 3.0f * FAR * FAR;  // padding rows are never in range
-            if (k < tl.count) {
-                const int j = tl.start + k;
-                const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
-                x = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
-                y = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
-                z = (float)(dx * c0 + dy * c1 + dz * c2 - ot);
-                n = x * x + y * y + z * z;
-            }
-            if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; rn[r >> 1].y = n; }
-            else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; rn[r >> 1].x = n; }
-        }
-
-        // ---- consume the lists of this item ----
-        while (true) {
-            int v;
-            while ((v = ld_flag(&ctl.full[buf])) == 0) __nanosleep(20);
-            __threadfence_block();
-            __syncwarp();
-            const int L = (v - 1) >> 1;
-            const bool done = ((v - 1) & 1) != 0;
-            ws_consume<WEIGHTED, MULTI, SAT>(P, C, buf, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck);
-            n_tests += (unsigned long long)L * (unsigned long long)tl.count;
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                st_flag(&ctl.full[buf], 0);
-            }
-            buf ^= 1;
-            if (done) break;
-        }
-    }
-    flush_pair();
-    if (lane == 0) {
-        ctl.quit = 1;
-        __threadfence_block();
-        st_flag(&ctl.seq, ++seq);
-        if (n_tests) atomicAdd(&P.counters[1], n_tests);
-    }
-    const unsigned rc = __reduce_add_sync(FULL, n_recheck);
-    if (lane == 0 && rc) atomicAdd(&P.counters[2], (unsigned long long)rc);
-}
-
-
-// ---- unified kernel: every warp gathers for itself, then tests (used when the warp-specialised
-// kernel is not selected).  Same building blocks as above, one list buffer per warp; all gather state
-// lives in the channel's shared-memory control block, so the registers of the hot loop are not shared
-// with long-lived scalars of the gather phase.
+// ---- the kernel: every warp gathers for itself, then tests.  All gather state lives in the channel's
+// shared-memory control block, so the registers of the hot loop are not shared with long-lived scalars
+// of the gather phase.
 template <bool WEIGHTED, bool MULTI, bool SAT>
 __global__ void __launch_bounds__(YAWB_WARPS * 32, (WEIGHTED || (MULTI && SAT)) ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS)
     k_count_uni(const FastParams P) {
