@@ -142,6 +142,14 @@ int yawb_sync(yawb_ctx *ctx);
 int yawb_timer_start(yawb_ctx *ctx);
 int yawb_timer_stop(yawb_ctx *ctx, double *ms);
 
+/* Nearest patch centre of every row, the catalog-creation step that precedes the hot path (SURVEY.md
+ * section 8f, rank 2).  Replaces `assign_patch_centers` (src/yaw/catalog/catalog.py:229-249), i.e.
+ * scipy.cluster.vq.vq(xyz, centers): squared Euclidean distance summed x -> y -> z in double without FMA,
+ * first minimum wins.  xyz: n x 3 and centers_xyz: n_centers x 3 float64 on the host, out_ids: n int32 on
+ * the host.  Synchronous. */
+int yawb_assign_patches(yawb_ctx *ctx, const double *xyz, int64_t n, const double *centers_xyz, int n_centers,
+                        int32_t *out_ids);
+
 /* Library version and number of SMs of the context's device. */
 int yawb_version(void);
 int yawb_device_sms(const yawb_ctx *ctx);

@@ -289,3 +289,32 @@ def test_device_memory_is_recycled(engine):
     free1, _ = torch.cuda.mem_get_info(0)
     assert free0 - free1 < 32 << 20, f"device footprint grew by {(free0 - free1) >> 20} MiB"
     assert all(c > 0 for c in first)
+
+
+def test_assign_patches_matches_scipy_vq(engine):
+    """`yawb_assign_patches` against `scipy.cluster.vq.vq` (what the reference's `assign_patch_centers` calls,
+    catalog.py:229-249): random rows, many centres (several shared-memory blocks), exact ties (first
+    centre wins), and the catalog constructor that uses it"""
+    from scipy.cluster import vq
+
+    import yet_another_wizz_b200 as yb
+
+    rng = np.random.default_rng(17)
+    for n, p in ((200_000, 64), (50_000, 2500), (1000, 1)):
+        xyz = oracle.radec_to_xyz(rng.uniform(0, 0.7, n), rng.uniform(-0.2, 0.2, n))
+        cen = oracle.radec_to_xyz(rng.uniform(0, 0.7, p), rng.uniform(-0.2, 0.2, p))
+        want, _ = vq.vq(xyz, cen)
+        assert_array_equal(engine.assign_patches(xyz, cen), want.astype(np.int32))
+    # exact ties: rows on the mirror plane of two centres, duplicated centres
+    cen = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    rows = np.array([[0.5, 0.5, 0.0], [0.25, 0.25, 0.1], [1.0, 0.0, 0.0], [0.0, 0.5, 0.5], [0.3, 0.3, 0.3]])
+    want, _ = vq.vq(rows, cen)
+    assert_array_equal(engine.assign_patches(rows, cen), want.astype(np.int32))
+    # through the catalog constructor
+    ra, dec = rng.uniform(0, 40, 30_000), rng.uniform(-12, 12, 30_000)
+    centers = yb.AngularCoordinates(np.deg2rad([[5.0, -6.0], [15.0, 6.0], [25.0, -6.0], [35.0, 6.0]]))
+    a = yb.Catalog.from_arrays(ra, dec, patch_centers=centers)
+    b = yb.Catalog.from_arrays(ra, dec, patch_centers=centers, engine=engine)
+    assert a.get_num_records() == b.get_num_records()
+    for pid in a.keys():
+        assert_array_equal(a[pid].load_data()["ra"], b[pid].load_data()["ra"])

@@ -145,10 +145,13 @@ def read_patch_data(path) -> np.ndarray:
     return raw.view(np.dtype([(a, "f8") for a in attrs]))
 
 
-def _nearest_center(xyz: np.ndarray, centers_xyz: np.ndarray) -> np.ndarray:
+def _nearest_center(xyz: np.ndarray, centers_xyz: np.ndarray, engine=None) -> np.ndarray:
     """index of the nearest patch centre in Euclidean xyz (what
     `scipy.cluster.vq.vq` computes in `assign_patch_centers`,
-    `src/yaw/catalog/catalog.py:229-249`), evaluated in row blocks"""
+    `src/yaw/catalog/catalog.py:229-249`); with an `engine` the same arithmetic runs on the device
+    (`yawb_assign_patches`)"""
+    if engine is not None and hasattr(engine, "assign_patches"):
+        return engine.assign_patches(xyz, centers_xyz)
     from scipy.cluster import vq
 
     ids, _ = vq.vq(xyz, centers_xyz)
@@ -171,7 +174,8 @@ class Catalog(Mapping):
     # ---- constructors -----------------------------------------------------------------------
     @classmethod
     def from_arrays(cls, ra, dec, *, patch_centers=None, patch_ids=None, weights=None, redshifts=None,
-                    kappa=None, degrees: bool = True, cache_directory=None) -> "Catalog":
+                    kappa=None, degrees: bool = True, cache_directory=None, engine=None) -> "Catalog":
+        """`engine`: assign rows to the nearest patch centre on the device instead of scipy's vq."""
         ra = np.asarray(ra, dtype=np.float64)
         dec = np.asarray(dec, dtype=np.float64)
         if degrees:
@@ -189,7 +193,7 @@ class Catalog(Mapping):
                 getattr(patch_centers, "data", patch_centers))
             if patch_ids is None:  # with both given, the ids assign rows and the centres fix the meta data
                 xyz = AngularCoordinates(np.column_stack([ra, dec])).to_3d()
-                patch_ids = _nearest_center(xyz, centers.to_3d())
+                patch_ids = _nearest_center(xyz, centers.to_3d(), engine)
         patch_ids = np.asarray(patch_ids)
         order = np.argsort(patch_ids, kind="stable")
         sorted_ids = patch_ids[order]
@@ -208,7 +212,7 @@ class Catalog(Mapping):
     @classmethod
     def from_dataframe(cls, cache_directory, dataframe, *, ra_name, dec_name, weight_name=None,
                        redshift_name=None, patch_centers=None, patch_name=None, patch_num=None,
-                       kappa_name=None, degrees: bool = True, **_ignored) -> "Catalog":
+                       kappa_name=None, degrees: bool = True, engine=None, **_ignored) -> "Catalog":
         """Signature of `yaw.Catalog.from_dataframe` (`src/yaw/catalog/catalog.py:980-1108`);
         `patch_num` (treecorr k-means) is not supported -- pass centres or a patch column."""
         if patch_num is not None and patch_centers is None and patch_name is None:
@@ -218,16 +222,17 @@ class Catalog(Mapping):
             get(ra_name), get(dec_name), patch_centers=patch_centers,
             patch_ids=None if patch_centers is not None else get(patch_name),
             weights=get(weight_name), redshifts=get(redshift_name), kappa=get(kappa_name), degrees=degrees,
-            cache_directory=cache_directory,
+            cache_directory=cache_directory, engine=engine,
         )
 
     @classmethod
-    def from_random(cls, cache_directory, generator, num_randoms: int, *, patch_centers=None, **_ignored) -> "Catalog":
+    def from_random(cls, cache_directory, generator, num_randoms: int, *, patch_centers=None, engine=None,
+                    **_ignored) -> "Catalog":
         """Signature of `yaw.Catalog.from_random` (`src/yaw/catalog/catalog.py:1245-1343`)."""
         chunk = generator(int(num_randoms))
         return cls.from_arrays(chunk["ra"], chunk["dec"], patch_centers=patch_centers,
                                weights=chunk.get("weights"), redshifts=chunk.get("redshifts"),
-                               degrees=False, cache_directory=cache_directory)
+                               degrees=False, cache_directory=cache_directory, engine=engine)
 
     @classmethod
     def from_cache(cls, cache_directory) -> "Catalog":

@@ -54,7 +54,75 @@ int yawb_h2d_small(yawb_ctx *ctx, void *dst, const void *src, size_t bytes) {
     return 0;
 }
 
+// nearest centre in xyz: the arithmetic of scipy.cluster.vq.vq for fewer than 5 features (differences
+// code - obs, squares summed in order, strict "<" so the first minimum wins), centres staged in shared
+// memory in blocks
+__global__ void k_assign_patches(const double *__restrict__ xyz, long long n, const double *__restrict__ centers,
+                                 int n_centers, int *__restrict__ out) {
+    extern __shared__ double cs[];  // [block of centres][3]
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (i < n) {
+        x = xyz[3 * i];
+        y = xyz[3 * i + 1];
+        z = xyz[3 * i + 2];
+    }
+    double best = 1.0e308 * 10.0;  // +inf
+    int arg = 0;
+    constexpr int CB = 1024;
+    for (int c0 = 0; c0 < n_centers; c0 += CB) {
+        const int nc = min(CB, n_centers - c0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < 3 * nc; k += blockDim.x) cs[k] = centers[3 * (size_t)c0 + k];
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+            const double dx = __dsub_rn(cs[3 * c], x), dy = __dsub_rn(cs[3 * c + 1], y), dz = __dsub_rn(cs[3 * c + 2], z);
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (d < best) {
+                best = d;
+                arg = c0 + c;
+            }
+        }
+    }
+    if (i < n) out[i] = arg;
+}
+
 extern "C" {
+
+int yawb_assign_patches(yawb_ctx *ctx, const double *xyz, int64_t n, const double *centers_xyz, int n_centers,
+                        int32_t *out_ids) {
+    YAWB_REQUIRE(ctx != nullptr, "yawb_assign_patches: ctx is NULL");
+    YAWB_REQUIRE(n >= 0 && (n == 0 || (xyz && out_ids)), "yawb_assign_patches: NULL rows");
+    YAWB_REQUIRE(n_centers >= 1 && centers_xyz, "yawb_assign_patches: at least one centre is required");
+    if (n == 0) return 0;
+    YAWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t chunk = 1 << 24;  // rows per pass: bounded device footprint for any catalog size
+    double *d_xyz = nullptr, *d_c = nullptr;
+    int *d_out = nullptr;
+    if (yawb_dalloc(ctx, (void **)&d_xyz, (size_t)std::min(n, chunk) * 3 * sizeof(double), st) ||
+        yawb_dalloc(ctx, (void **)&d_c, (size_t)n_centers * 3 * sizeof(double), st) ||
+        yawb_dalloc(ctx, (void **)&d_out, (size_t)std::min(n, chunk) * sizeof(int), st)) {
+        yawb_dfree(ctx, d_xyz, st); yawb_dfree(ctx, d_c, st); yawb_dfree(ctx, d_out, st);
+        return 1;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_c, centers_xyz, (size_t)n_centers * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
+    for (int64_t o = 0; o < n && e == cudaSuccess; o += chunk) {
+        const int64_t m = std::min(chunk, n - o);
+        e = cudaMemcpyAsync(d_xyz, xyz + 3 * o, (size_t)m * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        k_assign_patches<<<(unsigned)((m + 255) / 256), 256, 3 * 1024 * sizeof(double), st>>>(d_xyz, m, d_c, n_centers, d_out);
+        e = cudaMemcpyAsync(out_ids + o, d_out, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    yawb_dfree(ctx, d_xyz, st); yawb_dfree(ctx, d_c, st); yawb_dfree(ctx, d_out, st);
+    if (e != cudaSuccess) {
+        yawb_set_error("yawb_assign_patches: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
 
 const char *yawb_last_error(void) { return g_err; }
 

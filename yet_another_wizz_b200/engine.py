@@ -174,6 +174,16 @@ class Engine:
         )
         return stats.as_dict()
 
+    def assign_patches(self, xyz: np.ndarray, centers_xyz: np.ndarray) -> np.ndarray:
+        """Index of the nearest patch centre of every row (`scipy.cluster.vq.vq` arithmetic on the device;
+        replaces `assign_patch_centers`, reference `src/yaw/catalog/catalog.py:229-249`)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        centers_xyz = np.ascontiguousarray(centers_xyz, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(len(xyz), dtype=np.int32)
+        _lib.check(self.lib.yawb_assign_patches(self._h, _ptr(xyz), len(xyz), _ptr(centers_xyz), len(centers_xyz),
+                                                _ptr(out)))
+        return out
+
     def timer_start(self) -> None:
         _lib.check(self.lib.yawb_timer_start(self._h))
 
