@@ -149,29 +149,75 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     return dict(xyz=xyz, patch_off=off, weights=ws, zbin=zb, n_bins=len(binning) if binning is not None else 1)
 
 
-def upload_catalog(engine, catalog, binning: Binning | None, *, kappa: bool = False):
-    """Replaces `Catalog.build_trees`: one upload, the index is built on the device."""
+def _prepare_for(engine, catalog, binning: Binning | None, kappa: bool) -> dict:
     # opt-in (`Engine(staging=True)`): large catalogs are prepared straight into the engine's page-locked
     # staging cache; the copy is then asynchronous and overlaps with the preparation of the next catalog
     staged = getattr(engine, "staging", False) and sum(catalog.get_num_records()) >= engine.staging_min_rows
-    arrays = prepare_catalog_arrays(catalog, binning, kappa=kappa, alloc=engine.staging_empty if staged else None)
+    return prepare_catalog_arrays(catalog, binning, kappa=kappa, alloc=engine.staging_empty if staged else None)
+
+
+def upload_catalog(engine, catalog, binning: Binning | None, *, kappa: bool = False):
+    """Replaces `Catalog.build_trees`: one upload, the index is built on the device."""
+    arrays = _prepare_for(engine, catalog, binning, kappa)
     return engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
 
 
 class _Uploads:
-    """Device catalogs of one measurement call, uploaded once and shared by DD/DR/RD/RR."""
+    """Device catalogs of one measurement call, uploaded once and shared by DD/DR/RD/RR.
+
+    `enqueue` takes the catalogs of the call in the order they should travel: their host preparation
+    (numpy releases the GIL) runs one catalog ahead on a helper thread, so preparing catalog k + 1
+    overlaps with the copy of catalog k, which for pageable host memory blocks the calling thread."""
 
     def __init__(self, engine) -> None:
         self.engine = engine
         self._cache: dict[tuple[int, bool, bool], object] = {}
+        self._pending: dict[tuple[int, bool, bool], object] = {}
+        self._pool = None
+
+    @staticmethod
+    def _key(catalog, binning, kappa):
+        return (id(catalog), binning is not None, bool(kappa))
+
+    def enqueue(self, requests) -> None:
+        """`requests`: iterable of (catalog or None, binning or None[, kappa])."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        todo = []
+        for req in requests:
+            catalog, binning, kappa = (*req, False)[:3]
+            key = self._key(catalog, binning, kappa)
+            if catalog is not None and key not in self._cache and key not in self._pending:
+                todo.append((key, catalog, binning, kappa))
+        if not todo:
+            return
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=1)
+        for key, catalog, binning, kappa in todo:
+            self._pending[key] = self._pool.submit(_prepare_for, self.engine, catalog, binning, kappa)
+        for key, *_ in todo:  # upload in order; each wait overlaps with the preparation of the next catalog
+            self._resolve(key)
+
+    def _resolve(self, key):
+        arrays = self._pending.pop(key).result()
+        self._cache[key] = self.engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
+        return self._cache[key]
 
     def get(self, catalog, binning: Binning | None, kappa: bool = False):
-        key = (id(catalog), binning is not None, kappa)
+        key = self._key(catalog, binning, kappa)
+        if key in self._pending:
+            return self._resolve(key)
         if key not in self._cache:
             self._cache[key] = upload_catalog(self.engine, catalog, binning, kappa=kappa)
         return self._cache[key]
 
     def free(self) -> None:
+        for fut in self._pending.values():
+            fut.cancel()
+        self._pending.clear()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for dev in self._cache.values():
             dev.free()
         self._cache.clear()
@@ -402,6 +448,8 @@ def autocorrelate(config, data, random, *, count_rr: bool = True, progress: bool
     links._uploads = _Uploads(engine or get_default_engine())
     _last_stats.clear()
     try:
+        binning = _as_binning(config)
+        links._uploads.enqueue(((data, binning), (random, binning)))
         DD = links.count_pairs(data, count_type_info="DD")
         DR = links.count_pairs(data, random, count_type_info="DR", binned_second=True)
         RR = links.count_pairs_optional(random if count_rr else None, count_type_info="RR")
@@ -433,9 +481,7 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
         # transfer, RD / DR follow, and only RR waits for the last catalog (same schedule as
         # `pipeline.count_cross_pipelined`)
         binning = _as_binning(config)
-        for cat, bins in ((reference, binning), (unknown, None), (ref_rand, binning), (unk_rand, None)):
-            if cat is not None:
-                links._uploads.get(cat, bins)
+        links._uploads.enqueue(((reference, binning), (unknown, None), (ref_rand, binning), (unk_rand, None)))
         DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
         RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
         DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
