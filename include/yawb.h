@@ -86,6 +86,10 @@ int yawb_destroy(yawb_ctx *ctx);
  */
 int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);
+/* Same with byte-sized z-bin ids (n_bins <= 254; any id >= n_bins, e.g. 255, marks a dropped row): the ids
+ * are 5 % of the bytes of a z-binned catalog as int32, 1.3 % as bytes. */
+int yawb_upload_catalog_u8(yawb_ctx *ctx, const double *xyz, const double *w, const uint8_t *zbin,
+                           const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);
 int yawb_free_catalog(yawb_cat *cat);
 
 /* Build (or rebuild) the device-side index for a role ahead of time; otherwise

@@ -221,13 +221,15 @@ int yawb_host_free(void *ptr) {
     return 0;
 }
 
-int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
-                        const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+static int upload_common(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin, const uint8_t *zbin8,
+                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
     YAWB_REQUIRE(ctx && out && patch_off, "yawb_upload_catalog: NULL argument");
     *out = nullptr;
     YAWB_REQUIRE(n_patch >= 1 && n_patch <= 65535, "n_patch must be in 1..65535 (got %d)", n_patch);
-    if (!zbin) n_bins = 1;
+    const bool binned = zbin != nullptr || zbin8 != nullptr;
+    if (!binned) n_bins = 1;
     YAWB_REQUIRE(n_bins >= 1 && n_bins <= 4096, "n_bins must be in 1..4096 (got %d)", n_bins);
+    YAWB_REQUIRE(!zbin8 || n_bins <= 254, "byte-sized z-bin ids need n_bins <= 254 (got %d)", n_bins);
     YAWB_REQUIRE(patch_off[0] == 0, "patch_off[0] must be 0");
     for (int p = 0; p < n_patch; ++p)
         YAWB_REQUIRE(patch_off[p + 1] >= patch_off[p], "patch_off must be non-decreasing");
@@ -242,15 +244,25 @@ int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const
     cat->n_in = n;
     cat->n_patch = n_patch;
     cat->n_bins = n_bins;
-    cat->binned = zbin != nullptr;
+    cat->binned = binned;
     cat->weighted = w != nullptr;
-    if (yawb_index_upload(ctx, cat, xyz, w, zbin, patch_off)) {
+    if (yawb_index_upload(ctx, cat, xyz, w, zbin8, zbin, patch_off)) {
         yawb_index_free(cat, true);
         delete cat;
         return 1;
     }
     *out = cat;
     return 0;
+}
+
+int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
+                        const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+    return upload_common(ctx, xyz, w, zbin, nullptr, patch_off, n_patch, n_bins, out);
+}
+
+int yawb_upload_catalog_u8(yawb_ctx *ctx, const double *xyz, const double *w, const uint8_t *zbin,
+                           const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+    return upload_common(ctx, xyz, w, nullptr, zbin, patch_off, n_patch, n_bins, out);
 }
 
 int yawb_free_catalog(yawb_cat *cat) {

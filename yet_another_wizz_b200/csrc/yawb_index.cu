@@ -79,6 +79,12 @@ __device__ __forceinline__ unsigned long long enc_double(double v) {
 }
 // ---- upload kernels ---------------------------------------------------------------------
 
+// z-bin ids that travelled as bytes (a quarter of the PCIe traffic of int32): widen; ids >= n_bins stay out of range
+__global__ void k_widen_bins(const unsigned char *__restrict__ b8, long long n, int *__restrict__ bin) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) bin[i] = (int)b8[i];
+}
+
 // AoS (n x 3) -> SoA, plus the patch id of every row from the row offsets
 __global__ void k_deinterleave(const double *__restrict__ xyz, const long long *__restrict__ patch_off,
                                int n_patch, long long n, double *__restrict__ x, double *__restrict__ y,
@@ -526,7 +532,7 @@ int build_second_sorted(yawb_cat *cat, int hbits) {
 #endif
 static constexpr size_t kCopyChunk = (size_t)YAWB_COPY_CHUNK_MB << 20;
 
-int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
+int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w, const uint8_t *zbin8,
                       const int32_t *zbin, const int64_t *patch_off) {
     const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
@@ -540,7 +546,8 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
         dev_alloc(cat, &cat->patch, n, st))
         return 1;
     if (w && dev_alloc(cat, &cat->w, n, st)) return 1;
-    if (zbin && dev_alloc(cat, &cat->bin, n, st)) return 1;
+    if ((zbin || zbin8) && dev_alloc(cat, &cat->bin, n, st)) return 1;
+    if (zbin8 && dev_alloc(cat, &cat->d_stage_bin8, n, st)) return 1;
     if (dev_alloc(cat, &cat->d_frames, P, st) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1, st)) return 1;
     if (dev_alloc(cat, &cat->d_stage_xyz, (size_t)n * 3, st) || dev_alloc(cat, &cat->d_stage_poff, P + 1, st)) return 1;
 
@@ -558,6 +565,7 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     YAWB_CUDA(cudaMemcpyAsync(cat->d_stage_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     if (w && n > 0) YAWB_CUDA(h2d(cat->w, w, n * sizeof(double)));
     if (zbin && n > 0) YAWB_CUDA(h2d(cat->bin, zbin, n * sizeof(int32_t)));
+    if (zbin8 && n > 0) YAWB_CUDA(h2d(cat->d_stage_bin8, zbin8, n));
     YAWB_CUDA(cudaEventCreateWithFlags(&cat->ev_meta, cudaEventDisableTiming));
     YAWB_CUDA(cudaEventRecord(cat->ev_meta, st));
     YAWB_CUDA(cudaGetLastError());
@@ -601,6 +609,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         if (n > 0) {
             k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_xyz, cat->d_stage_poff, P, n, cat->x, cat->y,
                                                                cat->z, cat->patch);
+            if (cat->d_stage_bin8) k_widen_bins<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_bin8, n, cat->bin);
             const bool use_smem = B <= kSumMaxBins;
             const size_t smem =
                 4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (cat->w ? sizeof(double) : 0)) : 0);
@@ -615,6 +624,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
         dev_free(cat, cat->d_stage_xyz, (size_t)n * 3);
         dev_free(cat, cat->d_stage_poff, P + 1);
+        dev_free(cat, cat->d_stage_bin8, (size_t)n);
 
         // meta data (frames, row counts, sums of weights) through pinned staging
         const size_t b_frames = (((size_t)std::max(P, 1) * sizeof(PatchFrame)) + 63) & ~(size_t)63;
@@ -867,6 +877,7 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
         const size_t ni = (size_t)cat->n_in;
         dev_free(cat, cat->d_stage_xyz, ni * 3);
         dev_free(cat, cat->d_stage_poff, P + 1);
+        dev_free(cat, cat->d_stage_bin8, ni);
         dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
         dev_free(cat, cat->w, ni);
         dev_free(cat, cat->bin, ni);

@@ -112,6 +112,7 @@ struct yawb_cat {
     cudaEvent_t ev_meta = nullptr;            // recorded on the copy stream after the last host-to-device copy
     double *d_stage_xyz = nullptr;            // interleaved rows as uploaded, until yawb_cat_finalize()
     long long *d_stage_poff = nullptr;        // row offsets of the patches, until yawb_cat_finalize()
+    unsigned char *d_stage_bin8 = nullptr;    // z-bin ids uploaded as bytes, widened by yawb_cat_finalize()
     unsigned long long *hp_counts = nullptr;  // pinned staging [n_bins][n_patch]
     double *hp_sumw = nullptr;                // pinned staging [n_bins][n_patch]
     PatchFrame *hp_frames = nullptr;          // pinned staging [n_patch]
@@ -152,7 +153,7 @@ struct yawb_cat {
 };
 
 // index construction (yawb_index.cu)
-int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w,
+int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w, const uint8_t *zbin8,
                       const int32_t *zbin, const int64_t *patch_off);
 // device memory (yawb_alloc.cu): stream-aware caching allocator on top of cudaMalloc
 int yawb_dalloc(yawb_ctx *ctx, void **out, size_t bytes, cudaStream_t st);

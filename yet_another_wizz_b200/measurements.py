@@ -116,7 +116,9 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     n = int(off[-1])
     xyz = alloc((n, 3), np.float64)
     ws = alloc(n, np.float64) if has_w else None
-    zb = alloc(n, np.int32) if binning is not None else None
+    # z-bin ids travel as bytes when they fit (255 = outside the binning): a quarter of the PCIe traffic
+    small_bins = binning is not None and len(binning) <= 254
+    zb = alloc(n, np.uint8 if small_bins else np.int32) if binning is not None else None
 
     def fill(pid: int) -> None:
         ra, dec, weights, redshifts, kappa_vals = _patch_rows(catalog[pid])
@@ -134,7 +136,10 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
         elif has_w:
             ws[s:e] = weights
         if binning is not None:
-            zb[s:e] = binning.digitize(redshifts)
+            ids = binning.digitize(redshifts)  # -1 below, len(binning) above the binning
+            if small_bins:
+                ids[ids < 0] = 255
+            zb[s:e] = ids
 
     if workers is None:
         workers = min(16, os.cpu_count() or 1)
