@@ -209,7 +209,7 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
                                               const float2 (&rz)[HPL], const float2 (&rn)[HPL],
                                               float ta, float tb, const Tile &tl, int lane, double lo,
                                               double hi, unsigned &cnt_total, double &w_total,
-                                              unsigned &n_recheck) {
+                                              unsigned &n_recheck, const double (&rwt)[YAWB_RPL]) {
     for (int e0 = ea; e0 < eb; e0 += CHUNK) {
         const int e1 = min(e0 + CHUNK, eb);
         float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
@@ -233,10 +233,7 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
         double wsum = 0.0;
         if (WEIGHTED) {
 #pragma unroll
-            for (int r = 0; r < YAWB_RPL; ++r) {
-                const int k = lane + 32 * r;
-                if (ws[r] != 0.0) wsum += ws[r] * (P.rw ? P.rw[tl.start + min(k, tl.count - 1)] : 1.0);
-            }
+            for (int r = 0; r < YAWB_RPL; ++r) wsum += ws[r] * rwt[r];  // row weights live in registers
         }
         unsigned flagged = __ballot_sync(FULL, sa != sb);
         while (flagged) {  // warp-uniform: some lane met the uncertainty band of an edge

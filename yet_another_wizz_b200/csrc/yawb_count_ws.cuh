@@ -327,7 +327,8 @@ template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WEIGHTED> &C, int buf, int L,
                                            const float2 (&rx)[HPL], const float2 (&ry)[HPL],
                                            const float2 (&rz)[HPL], const float2 (&rn)[HPL],
-                                           const Tile &tl, int lane, int nsub, unsigned &n_recheck, int cur_pair = 0) {
+                                           const Tile &tl, int lane, int nsub, unsigned &n_recheck, int cur_pair,
+                                           const double (&rwt)[YAWB_RPL]) {
     WarpSmem<WEIGHTED> S;  // view of the current buffer for the shared phase-2 code
     S.list = C.list(buf); S.lw = C.lw(buf); S.lidx = C.lidx(buf); S.lbin = C.lbin(buf);
     S.hist = C.hist; S.histw = C.histw; S.acc = C.acc; S.accw = C.accw;
@@ -377,7 +378,7 @@ __device__ __forceinline__ void ws_consume(const FastParams &P, const Channel<WE
             double w_total = 0.0;
             phase2_single<WEIGHTED, SAT && !WEIGHTED>(P, S, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane,
                                                       P.binpar[b].lo, P.binpar[b].hi, cnt_total, w_total,
-                                                      n_recheck);
+                                                      n_recheck, rwt);
             const unsigned tot = __reduce_add_sync(FULL, cnt_total);
             double wtot = 0.0;
             if (WEIGHTED) wtot = warp_sum(w_total);
@@ -491,12 +492,15 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, (WEIGHTED || (MULTI && SAT)) 
         }
         __syncwarp();
         float2 rx[HPL], ry[HPL], rz[HPL], rn[HPL];  // rows (2k, 2k+1) of the lane share one register pair
+        double rwt[YAWB_RPL];                       // their weights (weighted kernels only)
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
             const int k = lane + 32 * r;
             float x = FAR, y = FAR, z = FAR, n = 3.0f * FAR * FAR;  // padding rows are never in range
+            rwt[r] = 0.0;
             if (k < tl.count) {
                 const int j = tl.start + k;
+                if (WEIGHTED) rwt[r] = P.rw ? P.rw[j] : 1.0;
                 const double dx = P.rx[j] - c0, dy = P.ry[j] - c1, dz = P.rz[j] - c2;
                 x = (float)(dx * a0 + dy * a1 + dz * a2 - ou);
                 y = (float)(dx * g0 + dy * g1 + dz * g2 - ov);
@@ -513,12 +517,12 @@ __global__ void __launch_bounds__(YAWB_WARPS * 32, (WEIGHTED || (MULTI && SAT)) 
             __syncwarp();
 #ifdef YAWB_DEBUG_MODES  // development builds: YAWB_DEBUG_MODE=1 skips the pair tests, 2 runs them twice (phase timing)
             if (L > 0 && P.debug != 1) {
-                ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
+                ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair, rwt);
                 if (P.debug == 2)
-                    ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
+                    ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair, rwt);
             }
 #else
-            if (L > 0) ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair);
+            if (L > 0) ws_consume<WEIGHTED, MULTI, SAT>(P, C, 0, L, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair, rwt);
 #endif
             n_tests += (unsigned long long)L * (unsigned long long)tl.count;
             __syncwarp();
