@@ -195,8 +195,10 @@ __device__ __forceinline__ void test_candidate(const Cand c, double swt, const f
             if (a0 < tb) acc_b.x += 1.f;
             if (a1 < tb) acc_b.y += 1.f;
             if (WEIGHTED) {
-                if (in0) ws[2 * k] += swt;
-                if (in1) ws[2 * k + 1] += swt;
+                // ws += [in] * swt as one select on the high word of a 0.0 / 1.0 double plus one DFMA (a
+                // conditional FP64 add is lowered to an add plus two selects)
+                ws[2 * k] = fma(__hiloint2double(in0 ? 0x3ff00000 : 0, 0), swt, ws[2 * k]);
+                ws[2 * k + 1] = fma(__hiloint2double(in1 ? 0x3ff00000 : 0, 0), swt, ws[2 * k + 1]);
             }
         }
     }
