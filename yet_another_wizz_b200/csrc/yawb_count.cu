@@ -4,7 +4,7 @@
 // (reference src/yaw/catalog/trees.py:348-353) and the per-z-bin loop of
 // process_patch_pair (src/yaw/correlation/measurements.py:109-124).
 //
-// k_count_uni   -- the production kernel (yawb_count_ws.cuh).  One warp owns a register tile of YAWB_TILE
+// k_count_uni   -- the production kernel (yawb_count_uni.cuh).  One warp owns a register tile of YAWB_TILE
 //   second-catalog points (YAWB_RPL per lane).  For every z-bin it gathers the
 //   first-catalog points of the linked patch that fall into the tile's bounding box
 //   grown by the bin's search radius (sky-cell rows -> contiguous runs -> per-point
@@ -453,7 +453,7 @@ __global__ void k_plan(const FastParams P, int2 *__restrict__ live_out) {
     if (ok) live_out[base + __popc(m & ((1u << lane) - 1u))] = make_int2(k, t0 + t);
 }
 
-#include "yawb_count_ws.cuh"
+#include "yawb_count_uni.cuh"
 
 // ---- exact all-pairs kernel -------------------------------------------------------------------
 struct ExactParams {
