@@ -427,15 +427,29 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
         }
     }
 
-    int *d_pi = nullptr, *d_pj = nullptr;
-    long long *d_base = nullptr;
-    double *d_r2 = nullptr, *d_w = nullptr;
-    float *d_r2f = nullptr;
-    BinPar *d_bp = nullptr;
+    // the six small tables of a count travel as ONE block (one allocation, one pull kernel): pair lists,
+    // item offsets, edges (double and float + bin lookup), per-bin parameters -- each 16-byte aligned
+    const size_t np1 = std::max(n_pairs, 1);
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t o_pi = 0, o_pj = o_pi + up16(np1 * sizeof(int)), o_base = o_pj + up16(np1 * sizeof(int)),
+                 o_r2 = o_base + up16((np1 + 1) * sizeof(long long)),
+                 o_r2f = o_r2 + up16((size_t)B * n_edges * sizeof(double)), o_bp = o_r2f + up16(r2f_words * sizeof(float)),
+                 tab_bytes = o_bp + up16(B * sizeof(BinPar));
+    std::vector<unsigned char> tab(tab_bytes, 0);
+    if (n_pairs) {
+        memcpy(tab.data() + o_pi, pair_i, n_pairs * sizeof(int));
+        memcpy(tab.data() + o_pj, pair_j, n_pairs * sizeof(int));
+    }
+    memcpy(tab.data() + o_base, item_base.data(), (n_pairs + 1) * sizeof(long long));
+    memcpy(tab.data() + o_r2, r2_edges, (size_t)B * n_edges * sizeof(double));
+    memcpy(tab.data() + o_r2f, r2f.data(), r2f_words * sizeof(float));
+    memcpy(tab.data() + o_bp, binpar.data(), B * sizeof(BinPar));
+
+    unsigned char *d_tab = nullptr;
+    double *d_w = nullptr;
     unsigned long long *d_cnt = nullptr;
     auto cleanup = [&]() {
-        for (void *p : {(void *)d_pi, (void *)d_pj, (void *)d_base, (void *)d_r2, (void *)d_r2f, (void *)d_bp,
-                        (void *)d_cnt, (void *)d_w})
+        for (void *p : {(void *)d_tab, (void *)d_cnt, (void *)d_w})
             if (p) yawb_dfree(ctx, p, st);
     };
 #define TRY(call)                                                                        \
@@ -454,31 +468,18 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
             return 1;                                                \
         }                                                            \
     } while (0)
-    const size_t np1 = std::max(n_pairs, 1);
-    DALLOC(d_pi, np1 * sizeof(int));
-    DALLOC(d_pj, np1 * sizeof(int));
-    DALLOC(d_base, (np1 + 1) * sizeof(long long));
-    DALLOC(d_r2, (size_t)B * n_edges * sizeof(double));
-    DALLOC(d_r2f, r2f_words * sizeof(float));
-    DALLOC(d_bp, B * sizeof(BinPar));
+    DALLOC(d_tab, tab_bytes);
     DALLOC(d_cnt, std::max<size_t>(n_out, 1) * sizeof(unsigned long long));
     if (weighted) DALLOC(d_w, std::max<size_t>(n_out, 1) * sizeof(double));
-#define H2D_SMALL(dst, src, bytes)                          \
-    do {                                                    \
-        if (yawb_h2d_small(ctx, (dst), (src), (bytes))) {   \
-            cleanup();                                      \
-            return 1;                                       \
-        }                                                   \
-    } while (0)
-    if (n_pairs) {
-        H2D_SMALL(d_pi, pair_i, n_pairs * sizeof(int));
-        H2D_SMALL(d_pj, pair_j, n_pairs * sizeof(int));
+    if (yawb_h2d_small(ctx, d_tab, tab.data(), tab_bytes)) {
+        cleanup();
+        return 1;
     }
-    H2D_SMALL(d_base, item_base.data(), (n_pairs + 1) * sizeof(long long));
-    H2D_SMALL(d_r2, r2_edges, (size_t)B * n_edges * sizeof(double));
-    H2D_SMALL(d_r2f, r2f.data(), r2f_words * sizeof(float));
-    H2D_SMALL(d_bp, binpar.data(), B * sizeof(BinPar));
-#undef H2D_SMALL
+    int *d_pi = (int *)(d_tab + o_pi), *d_pj = (int *)(d_tab + o_pj);
+    long long *d_base = (long long *)(d_tab + o_base);
+    double *d_r2 = (double *)(d_tab + o_r2);
+    float *d_r2f = (float *)(d_tab + o_r2f);
+    BinPar *d_bp = (BinPar *)(d_tab + o_bp);
     TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
     if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
     TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
