@@ -53,7 +53,12 @@ int yawb_dalloc(yawb_ctx *ctx, void **out, size_t bytes, cudaStream_t st) {
     const size_t limit = size + size / 4 + (1u << 20);
     for (auto it = c->parked.lower_bound(size); it != c->parked.end() && it->first <= limit; ++it) {
         DevBlock &b = it->second;
-        if (b.stream == st || cudaEventQuery(b.ev) == cudaSuccess) {
+        bool usable = b.stream == st;
+        if (!usable) {
+            usable = cudaEventQuery(b.ev) == cudaSuccess;
+            if (!usable) cudaGetLastError();  // cudaEventQuery leaves cudaErrorNotReady behind: clear it right away
+        }
+        if (usable) {
             DevBlock blk = b;
             c->parked.erase(it);
             c->live.emplace(blk.ptr, blk);
@@ -61,7 +66,6 @@ int yawb_dalloc(yawb_ctx *ctx, void **out, size_t bytes, cudaStream_t st) {
             return 0;
         }
     }
-    cudaGetLastError();  // cudaEventQuery leaves cudaErrorNotReady behind
     DevBlock blk{nullptr, size, st, nullptr};
     cudaError_t e = cudaMalloc(&blk.ptr, size);
     if (e == cudaErrorMemoryAllocation) {
