@@ -315,11 +315,13 @@ int yawb_sum_weights(const yawb_cat *cat, double *out) {
     return 0;
 }
 
-int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pair_i, const int32_t *pair_j,
-               int n_pairs, const double *r2_edges, int n_edges, uint32_t flags, double *out_f64,
-               int64_t *out_i64, yawb_stats *stats) {
+// Shared body of yawb_count (one first catalog) and yawb_count2 (two first catalogs counted against the same
+// second catalog in one pass over a fused first-role index).
+static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *cat2, const int32_t *pair_i,
+                      const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
+                      double *const out_f64[2], int64_t *const out_i64[2], yawb_stats *stats) {
     YAWB_REQUIRE(ctx && cat1 && cat2, "yawb_count: NULL context or catalog");
-    YAWB_REQUIRE(cat1->ctx == ctx && cat2->ctx == ctx, "catalogs belong to a different context");
+    YAWB_REQUIRE(cat1->ctx == ctx && cat2->ctx == ctx && (!cat1b || cat1b->ctx == ctx), "catalogs belong to a different context");
     YAWB_REQUIRE(n_pairs >= 0, "n_pairs < 0");
     YAWB_REQUIRE(n_edges >= 2 && n_edges <= YAWB_MAX_EDGES, "n_edges must be in 2..%d (got %d)", YAWB_MAX_EDGES, n_edges);
     YAWB_REQUIRE(r2_edges != nullptr, "r2_edges is NULL");
@@ -328,7 +330,14 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     YAWB_REQUIRE(!(cat2->binned && !cat1->binned), "a binned second catalog needs a binned first catalog");
     YAWB_REQUIRE(!cat2->binned || cat2->n_bins == cat1->n_bins, "z-bin counts differ (%d vs %d)", cat1->n_bins,
                  cat2->n_bins);
+    if (cat1b) {
+        YAWB_REQUIRE(cat1b != cat1, "yawb_count2: the two first catalogs must differ");
+        YAWB_REQUIRE(cat1b->n_patch == cat1->n_patch && cat1b->n_bins == cat1->n_bins && cat1b->binned == cat1->binned,
+                     "yawb_count2: the two first catalogs need the same patches and z-bins");
+        YAWB_REQUIRE(!(flags & YAWB_FLAG_EXACT_BRUTEFORCE), "yawb_count2: the exact cross-check counts one catalog at a time");
+    }
     YAWB_REQUIRE(n_pairs == 0 || (pair_i && pair_j), "pair lists are NULL");
+    const int n_types = cat1b ? 2 : 1;
     const int B = cat1->n_bins, P = cat1->n_patch, nsub = n_edges - 1;
     for (int k = 0; k < n_pairs; ++k)
         YAWB_REQUIRE(pair_i[k] >= 0 && pair_i[k] < P && pair_j[k] >= 0 && pair_j[k] < P,
@@ -345,15 +354,27 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     // copies of the second one: with asynchronous uploads that work overlaps with the transfer.  Timed with
     // events that are only read after the final synchronisation of this call (waiting for copies excluded).
     if (yawb_cat_finalize(cat1)) return 1;
+    if (cat1b && yawb_cat_finalize(cat1b)) return 1;
     float t_idx = 0.f;
-    if (!cat1->has_sindex) {
-        float t = 0.f;
-        YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
-        if (yawb_index_build_first(cat1)) return 1;
-        YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
-        YAWB_CUDA(cudaEventSynchronize(ctx->ev_i1));
-        YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
-        t_idx += t;
+    FIndex *fi = nullptr;
+    {
+        const bool need = cat1b ? true : cat1->findex == nullptr;
+        bool built = false;
+        if (need) YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
+        if (cat1b) {
+            if (yawb_findex_get_fused(ctx, cat1, cat1b, &fi, &built)) return 1;
+        } else {
+            if (yawb_index_build_first(cat1)) return 1;
+            fi = cat1->findex;
+            built = need;
+        }
+        if (built) {
+            float t = 0.f;
+            YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
+            YAWB_CUDA(cudaEventSynchronize(ctx->ev_i1));
+            YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
+            t_idx += t;
+        }
     }
     if (yawb_cat_finalize(cat2)) return 1;
     const bool second_built = !cat2->has_rtiles;
@@ -363,8 +384,9 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
         YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
     }
 
-    const bool weighted = cat1->weighted || cat2->weighted;
-    const size_t n_out = (size_t)n_pairs * B * nsub;
+    const bool weighted = fi->weighted || cat2->weighted;
+    const size_t n_out1 = (size_t)n_pairs * B * nsub;  // one catalog's results
+    const size_t n_out = n_out1 * n_types;
 
     // host-side preparation of thresholds and the item table
     std::vector<BinPar> binpar(B);
@@ -414,12 +436,16 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     for (int b = 0; b < B; ++b)
         if (!binpar[b].empty) rmax_all = std::max(rmax_all, binpar[b].rmax);
     std::vector<long long> item_base(n_pairs + 1, 0);
+    long long flat_diag = 0;
     for (int k = 0; k < n_pairs; ++k) {
         const int q = pair_j[k];
-        item_base[k + 1] = item_base[k] + (cat2->h_ptile_off[q + 1] - cat2->h_ptile_off[q]);
+        const long long nt = cat2->h_ptile_off[q + 1] - cat2->h_ptile_off[q];
+        item_base[k + 1] = item_base[k] + nt;
         const int p = pair_i[k];
+        if (p == q) flat_diag += nt;
         for (int b = 0; b < B; ++b) {
-            const long long n1 = cat1->h_counts[(size_t)b * P + p];
+            long long n1 = cat1->h_counts[(size_t)b * P + p];
+            if (cat1b) n1 += cat1b->h_counts[(size_t)b * P + p];
             long long n2 = 0;
             if (cat2->binned) n2 = cat2->h_counts[(size_t)b * P + q];
             else n2 = cat2->h_counts[q];
@@ -480,46 +506,61 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     double *d_r2 = (double *)(d_tab + o_r2);
     float *d_r2f = (float *)(d_tab + o_r2f);
     BinPar *d_bp = (BinPar *)(d_tab + o_bp);
-    TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
-    if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
-    TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
 
     CountArgs a{};
-    a.c1 = cat1; a.c2 = cat2;
+    a.c1 = fi; a.c1_cat = cat1; a.c2 = cat2;
     a.d_pair_i = d_pi; a.d_pair_j = d_pj; a.d_pair_item_base = d_base;
     a.n_items = item_base[n_pairs];
+    // work-item lists: a patch with itself needs an item per tile (a few more where items are split), of the
+    // tiles of neighbouring patches only the boundary strip survives; if a list turns out too small the
+    // count is repeated with the exact sizes
+    a.cap_heavy = 2 * flat_diag + 1024;
+    a.cap_light = (a.n_items - flat_diag) + 1024;
     a.n_pairs = n_pairs; a.n_bins = B; a.n_edges = n_edges;
     a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp; a.rmax_all = rmax_all;
     a.d_out_cnt = d_cnt; a.d_out_w = d_w; a.weighted = weighted;
 
     int launches = 0;
-    TRY(cudaEventRecord(ctx->ev0, st));
-    int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
-                                                  : yawb_launch_count_fast(ctx, a, &launches);
-    if (rc) { cleanup(); return rc; }
-    TRY(cudaEventRecord(ctx->ev1, st));
+    unsigned long long h_counters[8] = {0};
+    for (int attempt = 0;; ++attempt) {
+        TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
+        if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
+        TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+        TRY(cudaEventRecord(ctx->ev0, st));
+        int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
+                                                      : yawb_launch_count_fast(ctx, a, &launches);
+        if (rc) { cleanup(); return rc; }
+        TRY(cudaEventRecord(ctx->ev1, st));
+        TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+        if (!h_counters[6]) break;
+        YAWB_REQUIRE(attempt == 0, "work-item lists overflowed twice (%llu + %llu items)", h_counters[4], h_counters[5]);
+        a.cap_heavy = (long long)h_counters[4] + 1024;
+        a.cap_light = (long long)h_counters[5] + 1024;
+    }
 
     // results
     const cudaMemcpyKind kind = (flags & YAWB_FLAG_OUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (out_i64 && n_out) TRY(cudaMemcpyAsync(out_i64, d_cnt, n_out * sizeof(int64_t), kind, st));
-    if (out_f64 && n_out) {
-        if (weighted) {
-            TRY(cudaMemcpyAsync(out_f64, d_w, n_out * sizeof(double), kind, st));
-        } else if (flags & YAWB_FLAG_OUT_DEVICE) {
-            k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, out_f64, (long long)n_out);
-            launches += 1;
-        } else {
-            double *d_tmp = nullptr;
-            DALLOC(d_tmp, n_out * sizeof(double));
-            k_u64_to_f64<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(d_cnt, d_tmp, (long long)n_out);
-            launches += 1;
-            cudaError_t e = cudaMemcpyAsync(out_f64, d_tmp, n_out * sizeof(double), kind, st);
-            yawb_dfree(ctx, d_tmp, st);
-            TRY(e);
+    double *d_tmp = nullptr;
+    for (int t = 0; t < n_types && n_out1; ++t) {
+        if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), kind, st));
+        if (out_f64[t]) {
+            if (weighted) {
+                TRY(cudaMemcpyAsync(out_f64[t], d_w + t * n_out1, n_out1 * sizeof(double), kind, st));
+            } else if (flags & YAWB_FLAG_OUT_DEVICE) {
+                k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, out_f64[t], (long long)n_out1);
+                launches += 1;
+            } else {
+                if (!d_tmp) DALLOC(d_tmp, n_out * sizeof(double));
+                k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, d_tmp + t * n_out1, (long long)n_out1);
+                launches += 1;
+                cudaError_t e = cudaMemcpyAsync(out_f64[t], d_tmp + t * n_out1, n_out1 * sizeof(double), kind, st);
+                if (e != cudaSuccess) yawb_dfree(ctx, d_tmp, st);
+                TRY(e);
+            }
         }
     }
-    unsigned long long h_counters[8] = {0};
-    TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    if (d_tmp) yawb_dfree(ctx, d_tmp, st);
     TRY(cudaStreamSynchronize(st));
     TRY(cudaGetLastError());
     float t_k = 0.f;
@@ -531,14 +572,32 @@ int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pai
     }
     s.index_ms = t_idx;
 #undef TRY
+#undef DALLOC
     cleanup();
     s.kernel_ms = t_k;
     s.pair_tests = h_counters[1];
     s.rechecks = h_counters[2];
-    s.work_items = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? (uint64_t)n_pairs * B : h_counters[4];
+    s.work_items = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? (uint64_t)n_pairs * B : h_counters[4] + h_counters[5];
     s.launches = (uint64_t)launches;
     if (stats) *stats = s;
     return 0;
+}
+
+int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pair_i, const int32_t *pair_j,
+               int n_pairs, const double *r2_edges, int n_edges, uint32_t flags, double *out_f64,
+               int64_t *out_i64, yawb_stats *stats) {
+    double *const of[2] = {out_f64, nullptr};
+    int64_t *const oi[2] = {out_i64, nullptr};
+    return count_impl(ctx, cat1, nullptr, cat2, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
+}
+
+int yawb_count2(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2, const int32_t *pair_i,
+                const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
+                double *out_f64_a, int64_t *out_i64_a, double *out_f64_b, int64_t *out_i64_b, yawb_stats *stats) {
+    YAWB_REQUIRE(cat1b != nullptr, "yawb_count2: the second first-role catalog is NULL");
+    double *const of[2] = {out_f64_a, out_f64_b};
+    int64_t *const oi[2] = {out_i64_a, out_i64_b};
+    return count_impl(ctx, cat1a, cat1b, cat2, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
 }
 
 }  // extern "C"

@@ -4,22 +4,25 @@
 // (reference src/yaw/catalog/trees.py:348-353) and the per-z-bin loop of
 // process_patch_pair (src/yaw/correlation/measurements.py:109-124).
 //
-// k_count_uni   -- the production kernel (yawb_count_uni.cuh).  One warp owns a register tile of YAWB_TILE
-//   second-catalog points (YAWB_RPL per lane).  For every z-bin it gathers the
-//   first-catalog points of the linked patch that fall into the tile's bounding box
-//   grown by the bin's search radius (sky-cell rows -> contiguous runs -> per-point
-//   cull), rotates them into the tile-local frame in FP64, rounds ONCE to float and
-//   stages them as float4 (-2x, -2y, -2z, |s|^2 - mid) in shared memory.  The pair test is
-//       u = (|r|^2 + |s|^2 - mid) - 2 r.s = d2 - mid      4 FP32 ops (FADD + 3 FFMA)
-//       in  = |u| < h - eps,   maybe = |u| < h + eps      2 FSETP + 2 predicated FADD
-//   on the CUDA cores; eps bounds the FP32 error of u.  Whenever a lane's counts of
-//   `in` and `maybe` differ after a chunk of candidates, that lane re-evaluates the
-//   chunk with the reference's exact FP64 expression ((dx*dx + dy*dy) + dz*dz, no FMA),
-//   so the returned integers are bit-identical to the reference's.
+// k_plan          -- one thread per (patch pair, register tile of the second catalog): the tile's bounding box is
+//   rotated into the frame of the first catalog's patch, tested against that patch's box grown by the largest
+//   search radius, and the survivors are written as self-contained work items (split so that an item never
+//   holds more than YAWB_CCAP (z-bin, cell row) runs).
+// k_count_stream  -- the production kernel (yawb_count_stream.cuh).  One warp owns a register tile of YAWB_TILE
+//   second-catalog points (YAWB_RPL per lane).  For every z-bin it gathers the first-catalog rows of the linked
+//   patch that fall into the tile's bounding box grown by the bin's search radius (sky-cell rows -> contiguous
+//   runs -> asynchronous 16-byte copies of fixed-point rows -> per-row cull), re-expresses them relative to the
+//   tile's origin, rounds ONCE to float and stages them as (-2x, -2y, -2z, |s|^2 - mid) in shared memory.  The
+//   pair test is
+//       u = (|r|^2 + |s|^2 - mid) - 2 r.s = d2 - mid      4 FP32 ops (FADD + 3 FFMA, packed f32x2)
+//       v = sat(C - K |u|)                                 1 FP32 op; sum(v), sum(v^2): 2 FP32 ops
+//   on the CUDA cores; K is set by the bound on the FP32 error of u.  Whenever sum(v) != sum(v^2) for a lane's
+//   share of a few candidates, that share is re-evaluated with the reference's exact FP64 expression
+//   ((dx*dx + dy*dy) + dz*dz, no FMA), so the returned integers are bit-identical to the reference's.
 //   Tensor cores are not used: K = 3 is not a dense contraction.
-//
-// k_count_exact -- all-pairs FP64 kernel without pruning (validation and cross-check).
+// k_count_exact   -- all-pairs FP64 kernel without pruning (validation and cross-check).
 #include <cfloat>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 
@@ -34,24 +37,25 @@ constexpr float EPS32 = 5.9604645e-8f;  // 2^-24
 #endif
 constexpr int CHUNK = YAWB_CHUNK;       // candidates between consistency checks (power of two)
 constexpr float FAR = 1.0e15f;          // coordinates of padding points (never in range)
+#ifndef YAWB_CCAP
+#define YAWB_CCAP 160
+#endif
 
 struct FastParams {
-    // first catalog (sky-cell index)
+    // first-role index (one catalog, or two fused)
     const double *sx, *sy, *sz, *sw;
-    const double *su, *sv, *st;  // the same rows in the frame of their own patch
+    const SRec *rec;
     const int *cell_start;
     const SGrid *sgrid;
     const PatchFrame *sframe;
-    // second catalog (register tiles)
+    int n_types;
+    // second catalog (register tiles); rx2.. = second catalog of a joint launch (Item::src == 1)
     const double *rx, *ry, *rz, *rw;
-    const Tile *tiles;
-    const int *ptile_off;
-    // work
-    const int *pair_i, *pair_j;
-    const long long *pair_item_base;
-    long long n_items;
-    const int2 *live;  // (patch pair, tile) work items that survived the bounding-sphere test
-    int debug;         // development only: 1 = skip the pair tests, 2 = run them twice (timing experiments)
+    const double *rx2, *ry2, *rz2, *rw2;
+    // work items written by the planner: patch-diagonal items first, then the boundary items
+    const Item *items_heavy, *items_light;
+    long long cap_heavy, cap_light;
+    int debug;
     int n_pairs, n_bins, n_edges;
     const double *r2;
     const float *r2f;
@@ -60,11 +64,34 @@ struct FastParams {
     int lg_cells;
     int acc_global;               // general sub-bin path: segment histograms go straight to global atomics
     const BinPar *binpar;
-    double rmax_all;  // largest search radius over the z-bins
-    unsigned long long *out_cnt;
+    unsigned long long *out_cnt;  // [n_types][n_pairs][n_bins][n_edges - 1]
     double *out_w;
-    unsigned long long *counters;  // [0] next item, [1] tests, [2] rechecks, [3] live items
+    size_t type_stride;           // n_pairs * n_bins * (n_edges - 1)
+    unsigned long long *counters;  // [0] next item, [1] tests, [2] rechecks, [4] heavy items, [5] light items, [6] overflow
 };
+
+// Cell rows of the query of one z-bin: the tile box (in the frame of the patch) grown by the bin's search radius,
+// on the sky-cell grid of the patch.  Shared by the planner (which sizes the items) and the kernel.
+struct BinRows {
+    int iv0, nrows, iu0, iu1;
+};
+__device__ __forceinline__ BinRows bin_rows(const SGrid &G, double ulo, double uhi, double vlo, double vhi, const BinPar &bp,
+                                            int row_lo, int row_hi) {
+    BinRows r{0, 0, 0, 0};
+    if (bp.empty) return r;
+    // query box = tile box grown by the search radius (sound: |du|, |dv|, |dt| <= chord)
+    const double fu0 = floor((ulo - bp.rmax - G.u0) * G.inv_c), fu1 = floor((uhi + bp.rmax - G.u0) * G.inv_c);
+    const double fv0 = floor((vlo - bp.rmax - G.v0) * G.inv_c), fv1 = floor((vhi + bp.rmax - G.v0) * G.inv_c);
+    if (fu1 < 0.0 || fv1 < 0.0 || fu0 > (double)(G.gu - 1) || fv0 > (double)(G.gv - 1)) return r;
+    r.iu0 = (int)fmax(fu0, 0.0);
+    r.iu1 = (int)fmin(fu1, (double)(G.gu - 1));
+    const int iv0 = (int)fmax(fv0, 0.0), iv1 = (int)fmin(fv1, (double)(G.gv - 1));
+    const int n = iv1 - iv0 + 1;
+    const int lo = min(row_lo, n), hi = min(row_hi, n);  // an item may cover part of the rows only
+    r.iv0 = iv0 + lo;
+    r.nrows = max(hi - lo, 0);
+    return r;
+}
 
 // The reference's comparison value: products rounded separately, summed x -> y -> z.
 __device__ __forceinline__ double exact_d2(double ax, double ay, double az, double bx, double by, double bz) {
@@ -103,13 +130,7 @@ struct __align__(16) Cand {
 };
 constexpr int HPL = YAWB_RPL / 2;  // row pairs per lane
 
-// ---- per-warp shared memory -------------------------------------------------------------------
-constexpr int CCAP = 128;  // (z-bin, cell-row) combinations resolved per batch
-#ifndef YAWB_GRAB
-#define YAWB_GRAB 1
-#endif
-constexpr int GRAB = YAWB_GRAB;  // work items taken per atomic
-
+// ---- view of a warp's staged list for the phase-2 functions --------------------------------------
 template <bool WEIGHTED>
 struct WarpSmem {
     Cand *list;               // [LCAP] staged candidates
@@ -146,6 +167,31 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
         const int e = e0 + (t & (CHUNK - 1));
         const int k = src + 32 * (t / CHUNK);
         if (e < e1 && k < tl.count) {
+            const int i = S.lidx[e], j = tl.start + k;
+            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+            if (d2 > lo && d2 <= hi) {
+                cnt += 1;
+                if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
+            }
+            n_recheck += 1;
+        }
+    }
+    cnt_out = __reduce_add_sync(FULL, cnt);
+    if (WEIGHTED) w_out = warp_sum(wsum);
+}
+
+// The same for an arbitrary span [e0, e1) of the list (the streaming kernel checks once per <= 16 candidates).
+template <bool WEIGHTED>
+__device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem<WEIGHTED> &S, int e0, int e1,
+                                             const Tile &tl, int lane, int src, double lo, double hi,
+                                             unsigned &cnt_out, double &w_out, unsigned &n_recheck) {
+    unsigned cnt = 0;
+    double wsum = 0.0;
+    const int ne = e1 - e0;
+    for (int t = lane; t < ne * YAWB_RPL; t += 32) {
+        const int e = e0 + t % ne;
+        const int k = src + 32 * (t / ne);
+        if (k < tl.count) {
             const int i = S.lidx[e], j = tl.start + k;
             const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
             if (d2 > lo && d2 <= hi) {
@@ -424,36 +470,148 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
     }
 }
 
-// ---- planner: which (patch pair, tile) items can hold pairs at all -------------------------------
-// grid (tile blocks, patch pairs).  A tile of the second catalog survives for pair (p1, p2) if its
-// bounding sphere comes within the largest search radius of the bounding sphere of patch p1 of the first
-// catalog (chord distances obey the triangle inequality).  Survivors are appended to `live` with one
-// atomic per warp; counters[4] ends up holding their number.
-__global__ void k_plan(const FastParams P, int2 *__restrict__ live_out) {
-    const int k = blockIdx.y;
-    const int p1 = P.pair_i[k], p2 = P.pair_j[k];
-    const int t0 = P.ptile_off[p2], nt = P.ptile_off[p2 + 1] - t0;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= nt) return;
-    bool ok = false;
-    if (t < nt) {
-        const Tile tl = P.tiles[t0 + t];
-        const PatchFrame &F = P.sframe[p1];
-        const double dx = (double)tl.cx - F.c[0], dy = (double)tl.cy - F.c[1], dz = (double)tl.cz - F.c[2];
-        const double rmax = tl.bin >= 0 ? (P.binpar[tl.bin].empty ? 0.0 : P.binpar[tl.bin].rmax) : P.rmax_all;
-        const double reach = F.radius + (double)tl.rad + rmax + 1e-9;
-        ok = rmax > 0.0 && dx * dx + dy * dy + dz * dz <= reach * reach;
+// ---- planner: work items of a pair count ---------------------------------------------------------------
+// One thread per (patch pair, tile of the second catalog's patch).  The tile's bounding box, known in the frame
+// of its own patch, is carried into the frame of the first catalog's patch as the hull of its eight rotated
+// corners (a box is convex and the map is affine, so the hull contains every row).  The item survives if that
+// box, grown by the largest search radius, meets the (u, v) box of the first catalog's patch and holds at least
+// one cell row of some z-bin.  Items are split so that none exceeds YAWB_CCAP (z-bin, cell row) runs: by z-bin
+// ranges, and a single z-bin with more rows than that by row ranges.  Items of a patch with itself (nearly
+// all of the work) are listed first, the boundary items of neighbouring patches after them, so that the tail of
+// the launch consists of light items.
+struct PlanParams {
+    const Tile *tiles;
+    const TileBox *tile_box;
+    const int *ptile_off;
+    const PatchFrame *frames2;  // frames of the second catalog (tile boxes live in these)
+    const PatchFrame *frames1;  // frames of the first-role index
+    const SGrid *sgrid;
+    const int *pair_i, *pair_j;
+    const long long *pair_item_base;
+    int n_pairs;
+    long long n_flat;
+    const BinPar *binpar;
+    int n_bins;
+    double rmax_all;
+    Item *heavy, *light;
+    long long cap_heavy, cap_light;
+    unsigned long long *counters;
+};
+
+template <typename Emit>
+__device__ __forceinline__ void plan_walk(const SGrid &G, const BinPar *__restrict__ binpar, int b_lo, int b_hi, double ulo,
+                                          double uhi, double vlo, double vhi, Emit emit) {
+    int acc = 0, seg = b_lo;
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int r = bin_rows(G, ulo, uhi, vlo, vhi, binpar[b], 0, INT_MAX).nrows;
+        if (r > YAWB_CCAP) {
+            if (acc > 0) emit(seg, b, 0, INT_MAX);
+            for (int r0 = 0; r0 < r; r0 += YAWB_CCAP) emit(b, b + 1, r0, min(r0 + YAWB_CCAP, r));
+            seg = b + 1;
+            acc = 0;
+        } else if (acc + r > YAWB_CCAP) {
+            emit(seg, b, 0, INT_MAX);
+            seg = b;
+            acc = r;
+        } else {
+            acc += r;
+        }
     }
-    const unsigned m = __ballot_sync(FULL, ok);
-    if (m == 0u) return;
-    const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&P.counters[4], (unsigned long long)__popc(m));
-    base = __shfl_sync(FULL, base, 0);
-    if (ok) live_out[base + __popc(m & ((1u << lane) - 1u))] = make_int2(k, t0 + t);
+    if (acc > 0) emit(seg, b_hi, 0, INT_MAX);
 }
 
-#include "yawb_count_uni.cuh"
+__global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
+    const long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int n_emit = 0;
+    bool heavy = false;
+    Item it{};
+    SGrid G{};
+    if (f < Q.n_flat) {
+        int lo = 0, hi = Q.n_pairs;  // last pair with pair_item_base[k] <= f
+        while (hi - lo > 1) {
+            const int m = (lo + hi) >> 1;
+            if (Q.pair_item_base[m] <= f) lo = m; else hi = m;
+        }
+        const int k = lo;
+        const int p1 = Q.pair_i[k], p2 = Q.pair_j[k];
+        const int t = Q.ptile_off[p2] + (int)(f - Q.pair_item_base[k]);
+        const Tile tl = Q.tiles[t];
+        const PatchFrame &F1 = Q.frames1[p1];
+        const double rmax = tl.bin >= 0 ? (Q.binpar[tl.bin].empty ? 0.0 : Q.binpar[tl.bin].rmax) : Q.rmax_all;
+        // bounding spheres first (chord distances obey the triangle inequality)
+        const double dx = (double)tl.cx - F1.c[0], dy = (double)tl.cy - F1.c[1], dz = (double)tl.cz - F1.c[2];
+        const double reach = F1.radius + (double)tl.rad + rmax + 1e-9;
+        if (rmax > 0.0 && dx * dx + dy * dy + dz * dz <= reach * reach) {
+            const PatchFrame &F2 = Q.frames2[tl.patch];
+            const TileBox bx = Q.tile_box[t];
+            double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double u = (c & 1) ? bx.hi[0] : bx.lo[0], v = (c & 2) ? bx.hi[1] : bx.lo[1], w = (c & 4) ? bx.hi[2] : bx.lo[2];
+                // corner in world coordinates, then relative to the centre of the first catalog's patch
+                const double X = F2.c[0] + u * F2.e1[0] + v * F2.e2[0] + w * F2.c[0] - F1.c[0];
+                const double Y = F2.c[1] + u * F2.e1[1] + v * F2.e2[1] + w * F2.c[1] - F1.c[1];
+                const double Z = F2.c[2] + u * F2.e1[2] + v * F2.e2[2] + w * F2.c[2] - F1.c[2];
+                const double q[3] = {X * F1.e1[0] + Y * F1.e1[1] + Z * F1.e1[2], X * F1.e2[0] + Y * F1.e2[1] + Z * F1.e2[2],
+                                     X * F1.c[0] + Y * F1.c[1] + Z * F1.c[2]};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    lo3[d] = fmin(lo3[d], q[d]);
+                    hi3[d] = fmax(hi3[d], q[d]);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {  // far more than the rounding of the two rotations
+                const double pad = 1e-14 + 1e-12 * fmax(fabs(lo3[d]), fabs(hi3[d]));
+                lo3[d] -= pad;
+                hi3[d] += pad;
+            }
+            if (lo3[0] - rmax <= F1.umax && hi3[0] + rmax >= F1.umin && lo3[1] - rmax <= F1.vmax && hi3[1] + rmax >= F1.vmin) {
+                G = Q.sgrid[p1];
+                it.pair = k; it.p1 = p1; it.start = tl.start; it.count = tl.count; it.src = 0;
+                it.b_lo = tl.bin >= 0 ? tl.bin : 0;
+                it.b_hi = tl.bin >= 0 ? tl.bin + 1 : Q.n_bins;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { it.lo[d] = lo3[d]; it.hi[d] = hi3[d]; }
+                heavy = p1 == p2;
+                plan_walk(G, Q.binpar, it.b_lo, it.b_hi, lo3[0], hi3[0], lo3[1], hi3[1], [&](int, int, int, int) { ++n_emit; });
+            }
+        }
+    }
+    // one atomic per warp and list
+    int pre_h = heavy ? n_emit : 0, pre_l = heavy ? 0 : n_emit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int vh = __shfl_up_sync(FULL, pre_h, o), vl = __shfl_up_sync(FULL, pre_l, o);
+        if (lane >= o) { pre_h += vh; pre_l += vl; }
+    }
+    const int tot_h = __shfl_sync(FULL, pre_h, 31), tot_l = __shfl_sync(FULL, pre_l, 31);
+    if (tot_h + tot_l == 0) return;
+    unsigned long long base_h = 0, base_l = 0;
+    if (lane == 0) {
+        if (tot_h) base_h = atomicAdd(&Q.counters[4], (unsigned long long)tot_h);
+        if (tot_l) base_l = atomicAdd(&Q.counters[5], (unsigned long long)tot_l);
+    }
+    base_h = __shfl_sync(FULL, base_h, 0);
+    base_l = __shfl_sync(FULL, base_l, 0);
+    if (n_emit == 0) return;
+    long long pos = heavy ? (long long)base_h + pre_h - n_emit : (long long)base_l + pre_l - n_emit;
+    Item *const out = heavy ? Q.heavy : Q.light;
+    const long long cap = heavy ? Q.cap_heavy : Q.cap_light;
+    plan_walk(G, Q.binpar, it.b_lo, it.b_hi, it.lo[0], it.hi[0], it.lo[1], it.hi[1], [&](int b0, int b1, int r0, int r1) {
+        if (pos < cap) {
+            Item w = it;
+            w.b_lo = b0; w.b_hi = b1; w.row_lo = r0; w.row_hi = r1;
+            out[pos] = w;
+        } else {
+            Q.counters[6] = 1ull;  // list too small: the host repeats the call with the exact sizes
+        }
+        ++pos;
+    });
+}
+
+#include "yawb_count_stream.cuh"
 
 // ---- exact all-pairs kernel -------------------------------------------------------------------
 struct ExactParams {
@@ -541,32 +699,37 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
 
 // -----------------------------------------------------------------------------------------------
 int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
+    const FIndex *fi = a.c1;
     FastParams P{};
-    P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw;
-    P.su = a.c1->su; P.sv = a.c1->sv; P.st = a.c1->st;
-    P.rmax_all = a.rmax_all;
-    P.cell_start = a.c1->cell_start; P.sgrid = a.c1->d_sgrid; P.sframe = a.c1->d_frames;
+    P.sx = fi->sx; P.sy = fi->sy; P.sz = fi->sz; P.sw = fi->sw; P.rec = fi->rec;
+    P.cell_start = fi->cell_start; P.sgrid = fi->d_sgrid; P.sframe = fi->d_frames; P.n_types = fi->n_types;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
-    P.tiles = a.c2->d_tiles; P.ptile_off = a.c2->d_ptile_off;
-    P.pair_i = a.d_pair_i; P.pair_j = a.d_pair_j; P.pair_item_base = a.d_pair_item_base;
-    P.n_items = a.n_items; P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
+    P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
+    P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
     P.r2 = a.d_r2; P.r2f = a.d_r2f; P.binpar = a.d_binpar;
     P.lg_cells = a.n_edges > 2 ? 2 * a.n_edges : 0;
     P.lgpar = a.d_r2f + (size_t)a.n_bins * a.n_edges;
     P.lgT = reinterpret_cast<const unsigned short *>(P.lgpar + 2 * (size_t)a.n_bins);
     P.out_cnt = a.d_out_cnt; P.out_w = a.d_out_w; P.counters = ctx->d_counters;
+    P.type_stride = (size_t)a.n_pairs * a.n_bins * (a.n_edges - 1);
     if (a.n_items == 0) return 0;
 
-    // planner: compact list of the (patch pair, tile) items that can hold pairs
-    int2 *d_live = nullptr;
-    if (yawb_dalloc(ctx, (void **)&d_live, (size_t)a.n_items * sizeof(int2), ctx->stream)) return 1;
-    P.live = d_live;
-    int max_tiles = 1;
-    for (size_t p = 0; p + 1 < a.c2->h_ptile_off.size(); ++p)
-        max_tiles = std::max(max_tiles, a.c2->h_ptile_off[p + 1] - a.c2->h_ptile_off[p]);
+    // planner: self-contained work items (patch-diagonal ones first)
+    const long long cap_heavy = a.cap_heavy, cap_light = a.cap_light;
+    Item *d_items = nullptr;
+    if (yawb_dalloc(ctx, (void **)&d_items, (size_t)(cap_heavy + cap_light) * sizeof(Item), ctx->stream)) return 1;
+    P.items_heavy = d_items;
+    P.items_light = d_items + cap_heavy;
+    P.cap_heavy = cap_heavy; P.cap_light = cap_light;
     {
-        dim3 grid((unsigned)((max_tiles + 255) / 256), (unsigned)a.n_pairs);
-        k_plan<<<grid, 256, 0, ctx->stream>>>(P, d_live);
+        PlanParams Q{};
+        Q.tiles = a.c2->d_tiles; Q.tile_box = a.c2->d_tile_box; Q.ptile_off = a.c2->d_ptile_off;
+        Q.frames2 = a.c2->d_frames; Q.frames1 = fi->d_frames; Q.sgrid = fi->d_sgrid;
+        Q.pair_i = a.d_pair_i; Q.pair_j = a.d_pair_j; Q.pair_item_base = a.d_pair_item_base;
+        Q.n_pairs = a.n_pairs; Q.n_flat = a.n_items; Q.binpar = a.d_binpar; Q.n_bins = a.n_bins; Q.rmax_all = a.rmax_all;
+        Q.heavy = d_items; Q.light = d_items + cap_heavy; Q.cap_heavy = cap_heavy; Q.cap_light = cap_light;
+        Q.counters = ctx->d_counters;
+        k_plan<<<(unsigned)((a.n_items + 255) / 256), 256, 0, ctx->stream>>>(Q);
         *launches += 1;
     }
 
@@ -576,24 +739,25 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     // unweighted single-bin counts use the 7-instruction saturating test unless YAWB_PAIR_TEST=pred
     const char *variant = getenv("YAWB_PAIR_TEST");
     const bool sat = !(variant && strcmp(variant, "pred") == 0);
-
     {
         // many z-bins x sub-bins: per-warp accumulators in shared memory would cost most of the occupancy, so
         // the general sub-bin path sends every segment histogram straight to global atomics instead
         const bool cumul = multi && !a.weighted && sat && a.n_edges <= CUM_MAX_EDGES;
-        const size_t acc_bytes = (size_t)a.n_bins * nsub * (a.weighted ? 16 : 8);
+        const size_t acc_bytes = (size_t)fi->n_types * a.n_bins * nsub * (a.weighted ? 16 : 8);
         P.acc_global = multi && !cumul && acc_bytes > 2048;
-        int warps = YAWB_WARPS;
-        while (warps > 1 && warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global) > 227 * 1024) warps /= 2;
-        const size_t smem = warps * ws_chan_bytes(a.weighted, multi, a.n_bins, nsub, 1, P.acc_global);
+        const size_t per_warp = a.weighted
+                                    ? stream_carve<true>(nullptr, nullptr, multi, a.n_bins, nsub, fi->n_types, P.acc_global)
+                                    : stream_carve<false>(nullptr, nullptr, multi, a.n_bins, nsub, fi->n_types, P.acc_global);
+        const size_t smem = STREAM_WARPS * per_warp;
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
-        const int ctas = ctx->sms * ((a.weighted || cumul) ? YAWB_MIN_CTAS_WEIGHTED : YAWB_MIN_CTAS) * (YAWB_WARPS / warps);
-#define LAUNCH(W, M, T)                                                                                   \
-    do {                                                                                                  \
-        YAWB_CUDA(cudaFuncSetAttribute(k_count_uni<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                       \
-        k_count_uni<W, M, T><<<ctas, warps * 32, smem, ctx->stream>>>(P);                           \
+        const int per_sm = std::max(1, std::min(STREAM_CTAS, (int)((227 * 1024) / (smem + 1024))));
+        const int ctas = ctx->sms * per_sm;
+#define LAUNCH(W, M, T)                                                                                      \
+    do {                                                                                                     \
+        YAWB_CUDA(cudaFuncSetAttribute(k_count_stream<W, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                          \
+        k_count_stream<W, M, T><<<ctas, STREAM_WARPS * 32, smem, ctx->stream>>>(P);                         \
     } while (0)
         if (a.weighted) {
             if (multi) LAUNCH(true, true, false); else LAUNCH(true, false, false);
@@ -606,7 +770,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         }
 #undef LAUNCH
     }
-    yawb_dfree(ctx, d_live, ctx->stream);
+    yawb_dfree(ctx, d_items, ctx->stream);
     YAWB_CUDA(cudaGetLastError());
     *launches += 1;
     return 0;
@@ -614,9 +778,9 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
 
 int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     ExactParams P{};
-    P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw; P.s_seg = a.c1->d_seg_off;
+    P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw; P.s_seg = a.c1_cat->d_seg_off;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw; P.r_seg = a.c2->d_seg_off;
-    P.b1 = a.c1->n_bins; P.b2 = a.c2->n_bins;
+    P.b1 = a.c1_cat->n_bins; P.b2 = a.c2->n_bins;
     P.pair_i = a.d_pair_i; P.pair_j = a.d_pair_j;
     P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
     P.r2 = a.d_r2; P.out_cnt = a.d_out_cnt; P.out_w = a.d_out_w; P.counters = ctx->d_counters;
@@ -624,8 +788,8 @@ int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches) {
 
     // rows of the largest (patch, bin) segment of cat1 decide grid.y
     int max_seg = 0;
-    for (size_t s = 0; s + 1 < a.c1->h_seg_off.size(); ++s)
-        max_seg = std::max(max_seg, a.c1->h_seg_off[s + 1] - a.c1->h_seg_off[s]);
+    for (size_t s = 0; s + 1 < a.c1_cat->h_seg_off.size(); ++s)
+        max_seg = std::max(max_seg, a.c1_cat->h_seg_off[s + 1] - a.c1_cat->h_seg_off[s]);
     int gy = std::max(1, std::min(64, (max_seg + EX_THREADS - 1) / EX_THREADS));
     const int nsub = a.n_edges - 1;
     const size_t smem = (size_t)(a.n_edges + 4 * EX_THREADS + nsub) * sizeof(double) + (size_t)nsub * 8;

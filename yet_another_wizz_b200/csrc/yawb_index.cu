@@ -209,6 +209,23 @@ __global__ void k_init_box(unsigned long long *__restrict__ box, int n_patch) {
     box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
 }
 
+// boxes as they stand in the frames (the starting point when a second catalog's rows are added)
+__global__ void k_box_from_frames(const PatchFrame *__restrict__ frames, int n_patch, unsigned long long *__restrict__ box) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patch) return;
+    const PatchFrame &f = frames[p];
+    if (f.radius == 0.0 && f.umin == 0.0 && f.umax == 0.0 && f.vmin == 0.0 && f.vmax == 0.0) {  // no rows so far
+        box[5 * p] = box[5 * p + 2] = ~0ull;
+        box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
+        return;
+    }
+    box[5 * p] = enc_double(f.umin);
+    box[5 * p + 1] = enc_double(f.umax);
+    box[5 * p + 2] = enc_double(f.vmin);
+    box[5 * p + 3] = enc_double(f.vmax);
+    box[5 * p + 4] = enc_double(f.radius * f.radius);
+}
+
 __global__ void k_finish_frames(const unsigned long long *__restrict__ box, int n_patch,
                                 PatchFrame *__restrict__ frames) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,10 +306,12 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
                              const double *__restrict__ z, const int *__restrict__ bin,
                              const int *__restrict__ patch, long long n, int n_bins,
                              const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
-                             K *__restrict__ keys, unsigned *__restrict__ vals) {
+                             K *__restrict__ keys, unsigned *__restrict__ vals, long long off) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    vals[i] = (unsigned)i;
+    keys += off;  // rows of the second catalog of a fused index follow those of the first
+    vals += off;
+    vals[i] = (unsigned)(off + i);
     int b = bin ? bin[i] : 0;
     if (b < 0 || b >= n_bins) {
         keys[i] = (K)~(K)0;
@@ -376,26 +395,42 @@ __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const d
     if (w) ow[i] = w[j];
 }
 
-// first-role gather: also the coordinates of every row in the frame of its own patch
-__global__ void k_gather_local(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
-                               const double *__restrict__ y, const double *__restrict__ z,
-                               const double *__restrict__ w, const int *__restrict__ patch,
-                               const PatchFrame *__restrict__ frames, double *__restrict__ ox,
-                               double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ow,
-                               double *__restrict__ ou, double *__restrict__ ov, double *__restrict__ ot) {
+// first-role gather (rows of one catalog, or of two for a fused index): the exact rows in sorted order plus
+// their fixed-point record in the frame of the patch (SGrid: origin and power-of-two scale)
+__global__ void k_gather_rec(const unsigned *__restrict__ perm, long long n, long long n_a,
+                             const double *__restrict__ ax, const double *__restrict__ ay, const double *__restrict__ az,
+                             const double *__restrict__ aw, const int *__restrict__ apatch,
+                             const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
+                             const double *__restrict__ bw, const int *__restrict__ bpatch,
+                             const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
+                             double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
+                             double *__restrict__ ow, SRec *__restrict__ orec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned j = perm[i];
-    const double X = x[j], Y = y[j], Z = z[j];
+    long long j = perm[i];
+    const bool second = j >= n_a;
+    if (second) j -= n_a;
+    const double X = second ? bx[j] : ax[j], Y = second ? by[j] : ay[j], Z = second ? bz[j] : az[j];
     ox[i] = X;
     oy[i] = Y;
     oz[i] = Z;
-    if (w) ow[i] = w[j];
-    const PatchFrame &f = frames[patch[j]];
+    if (ow) {
+        const double *w = second ? bw : aw;
+        ow[i] = w ? w[j] : 1.0;  // fused index of a weighted and an unweighted catalog
+    }
+    const int p = second ? bpatch[j] : apatch[j];
+    const PatchFrame &f = frames[p];
+    const SGrid &g = grids[p];
     const double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
-    ou[i] = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
-    ov[i] = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
-    ot[i] = dx * f.c[0] + dy * f.c[1] + dz * f.c[2];
+    const double u = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
+    const double v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
+    const double t = dx * f.c[0] + dy * f.c[1] + dz * f.c[2];
+    SRec r;
+    r.ku = (int)fmin(fmax(rint((u - g.u0) * g.qscale), 0.0), 2147483647.0);
+    r.kv = (int)fmin(fmax(rint((v - g.v0) * g.qscale), 0.0), 2147483647.0);
+    r.kt = (int)fmin(fmax(rint((t - g.t0) * g.qscale), 0.0), 2147483647.0);
+    r.aux = (unsigned)i | (second ? 0x80000000u : 0u);
+    orec[i] = r;
 }
 
 // cell_start[g] = first sorted row whose key is >= g (one thread per cell, binary search)
@@ -412,19 +447,42 @@ __global__ void k_cell_start(const K *__restrict__ keys, long long n, long long 
     cell_start[g] = (int)lo;
 }
 
-// bounding sphere of each register tile: one warp per tile
+// bounding sphere of each register tile, and its bounding box in the frame of its own patch: one warp per tile
 __global__ void k_tile_spheres(const double *__restrict__ x, const double *__restrict__ y,
-                               const double *__restrict__ z, Tile *__restrict__ tiles, int n_tiles) {
+                               const double *__restrict__ z, Tile *__restrict__ tiles, int n_tiles,
+                               const PatchFrame *__restrict__ frames, TileBox *__restrict__ boxes) {
     int t = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     int lane = threadIdx.x & 31;
     if (t >= n_tiles) return;
     Tile tl = tiles[t];
     const unsigned full = 0xffffffffu;
+    const PatchFrame &f = frames[tl.patch];
     double sx = 0, sy = 0, sz = 0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int k = lane; k < tl.count; k += 32) {
-        sx += x[tl.start + k];
-        sy += y[tl.start + k];
-        sz += z[tl.start + k];
+        const double X = x[tl.start + k], Y = y[tl.start + k], Z = z[tl.start + k];
+        sx += X;
+        sy += Y;
+        sz += Z;
+        const double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
+        const double q[3] = {dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2], dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2],
+                             dx * f.c[0] + dy * f.c[1] + dz * f.c[2]};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            lo[d] = fmin(lo[d], q[d]);
+            hi[d] = fmax(hi[d], q[d]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        for (int o = 16; o; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(full, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(full, hi[d], o));
+        }
+    if (lane < 3) {  // padded by far more than the rounding of the three dot products
+        const double pad = 1e-14 + 1e-12 * fmax(fabs(lo[lane]), fabs(hi[lane]));
+        boxes[t].lo[lane] = lo[lane] - pad;
+        boxes[t].hi[lane] = hi[lane] + pad;
     }
     for (int o = 16; o; o >>= 1) {
         sx += __shfl_xor_sync(full, sx, o);
@@ -475,28 +533,43 @@ int bits_for(unsigned long long max_key) {
     return b;
 }
 
+template <typename T>
+int fi_alloc(FIndex *fi, T **ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    if (yawb_dalloc(fi->ctx, (void **)ptr, count * sizeof(T), fi->ctx->stream)) return 1;
+    fi->device_bytes += (int64_t)(count * sizeof(T));
+    return 0;
+}
+
 template <typename K>
-int build_first_sorted(yawb_cat *cat, long long base) {
-    yawb_ctx *ctx = cat->ctx;
+int build_first_sorted(FIndex *fi, long long base) {
+    yawb_ctx *ctx = fi->ctx;
     cudaStream_t st = ctx->stream;
-    const long long n_in = cat->n_in, n = cat->n;
+    const yawb_cat *a = fi->a, *b = fi->b;
+    const long long na_in = a->n_in, nb_in = b ? b->n_in : 0, n_in = na_in + nb_in, n = fi->n;
     Scratch scr(ctx, st);
     const size_t nn = std::max<long long>(n_in, 1);
     K *k0 = scr.get<K>(nn), *k1 = scr.get<K>(nn);
     unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
     YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
     if (n_in > 0) {
-        k_keys_first<K><<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in,
-                                                               cat->n_bins, cat->d_frames, cat->d_sgrid, k0, v0);
+        if (na_in > 0)
+            k_keys_first<K><<<blocks_for(na_in), kThreads, 0, st>>>(a->x, a->y, a->z, a->bin, a->patch, na_in, fi->n_bins,
+                                                                    fi->d_frames, fi->d_sgrid, k0, v0, 0);
+        if (nb_in > 0)
+            k_keys_first<K><<<blocks_for(nb_in), kThreads, 0, st>>>(b->x, b->y, b->z, b->bin, b->patch, nb_in, fi->n_bins,
+                                                                    fi->d_frames, fi->d_sgrid, k0, v0, na_in);
         // dropped rows carry the all-ones key: sort every bit only if something was dropped
         const int end_bit = (n == n_in) ? bits_for((unsigned long long)std::max<long long>(base, 1)) : (int)(8 * sizeof(K));
         if (sort_pairs<K>(ctx, scr, k0, k1, v0, v1, n_in, end_bit)) return 1;
     }
     if (n > 0)
-        k_gather_local<<<blocks_for(n), kThreads, 0, st>>>(v1, n, cat->x, cat->y, cat->z, cat->w, cat->patch,
-                                                           cat->d_frames, cat->sx, cat->sy, cat->sz, cat->sw,
-                                                           cat->su, cat->sv, cat->st);
-    k_cell_start<K><<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, cat->cell_start);
+        k_gather_rec<<<blocks_for(n), kThreads, 0, st>>>(v1, n, na_in, a->x, a->y, a->z, a->w, a->patch, b ? b->x : nullptr,
+                                                         b ? b->y : nullptr, b ? b->z : nullptr, b ? b->w : nullptr,
+                                                         b ? b->patch : nullptr, fi->d_frames, fi->d_sgrid, fi->sx, fi->sy,
+                                                         fi->sz, fi->sw, fi->rec);
+    k_cell_start<K><<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, fi->cell_start);
     return 0;
 }
 
@@ -673,19 +746,78 @@ int yawb_cat_finalize(yawb_cat *cat) {
 }
 
 // -------------------------------------------------------------------------------------------
-int yawb_index_build_first(yawb_cat *cat) {
-    if (yawb_cat_finalize(cat)) return 1;
-    if (cat->has_sindex) return 0;
-    yawb_ctx *ctx = cat->ctx;
-    const long long n = cat->n;
-    const int P = cat->n_patch, B = cat->n_bins;
+// Frames of a first-role index.  One catalog: its own frames.  Two catalogs: per patch the frame of the
+// catalog with more rows there; the (u, v) box and the radius are then grown over the rows of both.
+static int findex_frames(FIndex *fi) {
+    yawb_ctx *ctx = fi->ctx;
+    cudaStream_t st = ctx->stream;
+    const yawb_cat *a = fi->a, *b = fi->b;
+    const int P = fi->n_patch, B = fi->n_bins;
+    fi->h_frames = a->h_frames;
+    if (fi_alloc(fi, &fi->d_frames, P)) return 1;
+    if (!b) return yawb_h2d_small(ctx, fi->d_frames, fi->h_frames.data(), P * sizeof(PatchFrame));
+    bool a_chosen = false, b_chosen = false;
+    for (int p = 0; p < P; ++p) {
+        const long long ra = a->h_seg_off[(size_t)(p + 1) * B] - a->h_seg_off[(size_t)p * B];
+        const long long rb = b->h_seg_off[(size_t)(p + 1) * B] - b->h_seg_off[(size_t)p * B];
+        if (rb >= ra && rb > 0) {
+            fi->h_frames[p] = b->h_frames[p];
+            b_chosen = true;
+        } else {
+            a_chosen = true;
+        }
+    }
+    if (yawb_h2d_small(ctx, fi->d_frames, fi->h_frames.data(), P * sizeof(PatchFrame))) return 1;
+    Scratch scr(ctx, st);
+    unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
+    YAWB_REQUIRE(d_box != nullptr, "out of device memory (frames)");
+    const int pb = (P + 127) / 128;
+    // a patch that uses the frame of one catalog starts from that catalog's box; the rows of the other
+    // catalog extend it (re-adding a catalog's own rows changes nothing)
+    k_box_from_frames<<<pb, 128, 0, st>>>(fi->d_frames, P, d_box);
+    if (b_chosen && a->n_in > 0)
+        k_patch_bbox<<<blocks_for(a->n_in, kSumRows), kThreads, 0, st>>>(a->x, a->y, a->z, a->patch, a->n_in, fi->d_frames, d_box);
+    if (a_chosen && b->n_in > 0)
+        k_patch_bbox<<<blocks_for(b->n_in, kSumRows), kThreads, 0, st>>>(b->x, b->y, b->z, b->patch, b->n_in, fi->d_frames, d_box);
+    k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, fi->d_frames);
+    YAWB_CUDA(cudaMemcpyAsync(fi->h_frames.data(), fi->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
+    YAWB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
 
-    // grid per patch: cell edge from the mean density of one z-bin of this patch
-    cat->h_sgrid.assign(P, SGrid{});
+static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
+    *out = nullptr;
+    if (yawb_cat_finalize(a)) return 1;
+    if (b && yawb_cat_finalize(b)) return 1;
+    FIndex *fi = new (std::nothrow) FIndex();
+    YAWB_REQUIRE(fi != nullptr, "out of host memory");
+    fi->ctx = ctx;
+    fi->a = a;
+    fi->b = b;
+    fi->n = a->n + (b ? b->n : 0);
+    fi->n_patch = a->n_patch;
+    fi->n_bins = a->n_bins;
+    fi->n_types = b ? 2 : 1;
+    fi->weighted = a->weighted || (b && b->weighted);
+    const long long n = fi->n;
+    const int P = fi->n_patch, B = fi->n_bins;
+    auto fail = [&]() {
+        yawb_findex_free(fi);
+        return 1;
+    };
+    if (n >= (1ll << 31) - 1024) {
+        yawb_set_error("a first-role index is limited to 2^31 rows (got %lld)", n);
+        return fail();
+    }
+    if (findex_frames(fi)) return fail();
+
+    // grid per patch: cell edge from the mean density of one z-bin of this patch; fixed-point scale of the rows
+    fi->h_sgrid.assign(P, SGrid{});
     long long base = 0;
     for (int p = 0; p < P; ++p) {
-        const PatchFrame &f = cat->h_frames[p];
-        long long np = cat->h_seg_off[(size_t)(p + 1) * B] - cat->h_seg_off[(size_t)p * B];
+        const PatchFrame &f = fi->h_frames[p];
+        long long np = a->h_seg_off[(size_t)(p + 1) * B] - a->h_seg_off[(size_t)p * B];
+        if (b) np += b->h_seg_off[(size_t)(p + 1) * B] - b->h_seg_off[(size_t)p * B];
         double du = std::max(f.umax - f.umin, 0.0), dv = std::max(f.vmax - f.vmin, 0.0);
         double per_bin = std::max((double)np / B, 1.0);
         double area = std::max(du * dv, 1e-30);
@@ -693,7 +825,7 @@ int yawb_index_build_first(yawb_cat *cat) {
         double span = std::max(du, dv);
         if (!(c > 0.0) || span <= 0.0) c = 1.0;
         c = std::max(c, span / 2048.0);  // bound the grid, <= 2048 x 2048 cells
-        SGrid &g = cat->h_sgrid[p];
+        SGrid &g = fi->h_sgrid[p];
         g.u0 = f.umin;
         g.v0 = f.vmin;
         g.inv_c = 1.0 / c;
@@ -706,25 +838,74 @@ int yawb_index_build_first(yawb_cat *cat) {
         }
         g.cell_base = base;
         base += (long long)B * g.gu * g.gv;
+        // t = (P - c).c = -chord^2 / 2 lies in [-radius^2 / 2, 0]; one power-of-two scale for (u, v, t)
+        const double tspan = 0.5 * f.radius * f.radius * (1.0 + 1e-9) + 1e-12;
+        g.t0 = -tspan;
+        const double extent = std::max(std::max(du, dv), tspan) * (1.0 + 1e-9) + 1e-12;
+        int m = (int)std::floor(std::log2(2147483000.0 / extent));
+        m = std::min(std::max(m, 0), 60);
+        g.qscale = std::ldexp(1.0, m);
+        g.qinv = std::ldexp(1.0, -m);
     }
-    cat->n_cells = base;
-    YAWB_REQUIRE(base < (1ll << 40), "sky-cell index too large (%lld cells)", base);
-    if (dev_alloc(cat, &cat->d_sgrid, P)) return 1;
-    if (yawb_h2d_small(ctx, cat->d_sgrid, cat->h_sgrid.data(), P * sizeof(SGrid))) return 1;
-
-    if (dev_alloc(cat, &cat->sx, n) || dev_alloc(cat, &cat->sy, n) || dev_alloc(cat, &cat->sz, n)) return 1;
-    if (dev_alloc(cat, &cat->su, n) || dev_alloc(cat, &cat->sv, n) || dev_alloc(cat, &cat->st, n)) return 1;
-    if (cat->weighted && dev_alloc(cat, &cat->sw, n)) return 1;
-    if (dev_alloc(cat, &cat->cell_start, base + 1)) return 1;
+    fi->n_cells = base;
+    if (base >= (1ll << 40)) {
+        yawb_set_error("sky-cell index too large (%lld cells)", base);
+        return fail();
+    }
+    if (fi_alloc(fi, &fi->d_sgrid, P)) return fail();
+    if (yawb_h2d_small(ctx, fi->d_sgrid, fi->h_sgrid.data(), P * sizeof(SGrid))) return fail();
+    if (fi_alloc(fi, &fi->sx, n) || fi_alloc(fi, &fi->sy, n) || fi_alloc(fi, &fi->sz, n) || fi_alloc(fi, &fi->rec, n)) return fail();
+    if (fi->weighted && fi_alloc(fi, &fi->sw, n)) return fail();
+    if (fi_alloc(fi, &fi->cell_start, base + 1)) return fail();
     // 32-bit sort keys whenever the cell ids fit (they nearly always do): a third less radix-sort traffic
-    if (base < 0xffffffffll) {
-        if (build_first_sorted<unsigned>(cat, base)) return 1;
-    } else {
-        if (build_first_sorted<unsigned long long>(cat, base)) return 1;
+    if (base < 0xffffffffll ? build_first_sorted<unsigned>(fi, base) : build_first_sorted<unsigned long long>(fi, base)) return fail();
+    if (cudaGetLastError() != cudaSuccess) {
+        yawb_set_error("first-role index build failed");
+        return fail();
     }
-    YAWB_CUDA(cudaGetLastError());
-    cat->has_sindex = true;
+    *out = fi;
     return 0;
+}
+
+void yawb_findex_free(FIndex *fi) {
+    if (!fi) return;
+    yawb_ctx *ctx = fi->ctx;
+    for (void *p : {(void *)fi->rec, (void *)fi->sx, (void *)fi->sy, (void *)fi->sz, (void *)fi->sw, (void *)fi->cell_start,
+                    (void *)fi->d_sgrid, (void *)fi->d_frames})
+        if (p) yawb_dfree(ctx, p, ctx->stream);
+    delete fi;
+}
+
+int yawb_index_build_first(yawb_cat *cat) {
+    if (yawb_cat_finalize(cat)) return 1;
+    if (cat->findex) return 0;
+    if (findex_build(cat->ctx, cat, nullptr, &cat->findex)) return 1;
+    cat->device_bytes += cat->findex->device_bytes;
+    return 0;
+}
+
+int yawb_findex_get_fused(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out, bool *built) {
+    *built = false;
+    for (FIndex *fi : ctx->fused)
+        if (fi->a == a && fi->b == b) {
+            *out = fi;
+            return 0;
+        }
+    if (findex_build(ctx, a, b, out)) return 1;
+    ctx->fused.push_back(*out);
+    *built = true;
+    return 0;
+}
+
+void yawb_findex_drop_fused(yawb_ctx *ctx, const yawb_cat *cat) {
+    for (size_t k = 0; k < ctx->fused.size();) {
+        if (ctx->fused[k]->a == cat || ctx->fused[k]->b == cat) {
+            yawb_findex_free(ctx->fused[k]);
+            ctx->fused.erase(ctx->fused.begin() + k);
+        } else {
+            ++k;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -802,8 +983,11 @@ int yawb_index_build_second(yawb_cat *cat) {
         if (yawb_h2d_small(ctx, d_tmp, tiles.data(), tiles.size() * sizeof(Tile))) return 1;
         if (yawb_h2d_small(ctx, d_thr, thr.data(), P * sizeof(float))) return 1;
         YAWB_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
+        TileBox *d_box_tmp = nullptr;
+        if (dev_alloc(cat, &d_box_tmp, tiles.size())) return 1;
+        cat->d_tile_box = d_box_tmp;
         k_tile_spheres<<<blocks_for((long long)tiles.size() * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, d_tmp,
-                                                                                      (int)tiles.size());
+                                                                                      (int)tiles.size(), cat->d_frames, d_box_tmp);
         k_count_oversized<<<blocks_for((long long)tiles.size()), kThreads, 0, st>>>(d_tmp, (int)tiles.size(), d_thr, d_nbig);
         unsigned n_big = 0;
         YAWB_CUDA(cudaMemcpyAsync(&n_big, d_nbig, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -813,6 +997,7 @@ int yawb_index_build_second(yawb_cat *cat) {
             YAWB_CUDA(cudaMemcpyAsync(tiles.data(), d_tmp, tiles.size() * sizeof(Tile), cudaMemcpyDeviceToHost, st));
             YAWB_CUDA(cudaStreamSynchronize(st));
             dev_free(cat, cat->d_tiles, n_tmp);
+            dev_free(cat, cat->d_tile_box, n_tmp);
             std::vector<Tile> out;
             out.reserve(tiles.size() + 8 * (size_t)n_big);
             std::vector<int> new_off(P + 1, 0);
@@ -841,10 +1026,11 @@ int yawb_index_build_second(yawb_cat *cat) {
     if (!table_on_device && dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;
     if (dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
     if (yawb_h2d_small(ctx, cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int))) return 1;
-    if (!table_on_device && !tiles.empty()) {  // the split tiles need their own spheres
+    if (!table_on_device && dev_alloc(cat, &cat->d_tile_box, tiles.size())) return 1;
+    if (!table_on_device && !tiles.empty()) {  // the split tiles need their own spheres and boxes
         if (yawb_h2d_small(ctx, cat->d_tiles, tiles.data(), tiles.size() * sizeof(Tile))) return 1;
-        k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz,
-                                                                                      cat->d_tiles, cat->n_tiles);
+        k_tile_spheres<<<blocks_for((long long)cat->n_tiles * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, cat->d_tiles,
+                                                                                      cat->n_tiles, cat->d_frames, cat->d_tile_box);
     }
     YAWB_CUDA(cudaGetLastError());
     cat->has_rtiles = true;
@@ -853,18 +1039,17 @@ int yawb_index_build_second(yawb_cat *cat) {
 
 void yawb_index_free(yawb_cat *cat, bool everything) {
     const size_t n = (size_t)cat->n, P = (size_t)cat->n_patch;
-    if (cat->has_sindex || everything) {
-        dev_free(cat, cat->sx, n); dev_free(cat, cat->sy, n); dev_free(cat, cat->sz, n);
-        dev_free(cat, cat->sw, n);
-        dev_free(cat, cat->su, n); dev_free(cat, cat->sv, n); dev_free(cat, cat->st, n);
-        dev_free(cat, cat->d_sgrid, P);
-        dev_free(cat, cat->cell_start, (size_t)cat->n_cells + 1);
-        cat->has_sindex = false;
+    if (cat->findex) {
+        cat->device_bytes -= cat->findex->device_bytes;
+        yawb_findex_free(cat->findex);
+        cat->findex = nullptr;
     }
+    yawb_findex_drop_fused(cat->ctx, cat);
     if (cat->has_rtiles || everything) {
         dev_free(cat, cat->rx, n); dev_free(cat, cat->ry, n); dev_free(cat, cat->rz, n);
         dev_free(cat, cat->rw, n);
         dev_free(cat, cat->d_tiles, (size_t)cat->n_tiles);
+        dev_free(cat, cat->d_tile_box, (size_t)cat->n_tiles);
         dev_free(cat, cat->d_ptile_off, P + 1);
         cat->has_rtiles = false;
     }

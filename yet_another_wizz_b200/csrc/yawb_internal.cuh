@@ -41,11 +41,47 @@ struct PatchFrame {
 };
 
 // ---- sky-cell grid of one patch (first-role index); identical for every z-bin ------------
+// The rows of the index are stored as fixed-point records in the frame of their patch:
+//   k = rint((coordinate - origin) * qscale),  origin = (u0, v0, t0),  qscale = 2^m
+// with m chosen per patch so that every k fits 31 bits.  A coordinate is recovered to within
+// 0.5001 / qscale (a few 1e-11 for a 5-degree patch: finer than the float rounding of a tile-local
+// vector), and the exact doubles stay available for the FP64 recheck.
 struct SGrid {
     double u0, v0, inv_c;  // cell (iu, iv) covers u0 + iu/inv_c ...
     int gu, gv;            // cells per row / number of rows
     long long cell_base;   // global cell id of (bin 0, iv 0, iu 0); bin stride = gu * gv
+    double t0;             // origin of the third coordinate (t = (P - c).c <= 0)
+    double qscale, qinv;   // 2^m and 2^-m
 };
+
+// One row of a first-role index: fixed-point (u, v, t) in the frame of its patch; `aux` = position of
+// the row in the sorted arrays (bits 0..30) | catalog of a fused index (bit 31).
+struct __align__(16) SRec {
+    int ku, kv, kt;
+    unsigned aux;
+};
+
+// Bounding box of a register tile in the frame of its OWN patch (second-role index): lo / hi of (u, v, t).
+struct TileBox {
+    double lo[3], hi[3];
+};
+
+// One work item of a pair count, written by the planner: a register tile of the second catalog against
+// the z-bins [b_lo, b_hi) of one linked patch of the first catalog.  `box` is the tile's bounding box in
+// the frame of that patch (hull of the rotated corners of the own-frame box, so it contains every row).
+struct __align__(16) Item {
+    int pair;              // index into the pair list (result row)
+    int p1;                // patch of the first catalog
+    int start;             // first row of the tile in the Hilbert-sorted arrays
+    int count;             // rows of the tile (<= YAWB_TILE)
+    int b_lo, b_hi;        // z-bins of the first catalog covered by this item
+    int row_lo, row_hi;    // cell rows of the query covered, relative to its first row (whole query: 0, INT_MAX);
+                           // a restriction only occurs on items of a single z-bin
+    int src;               // second catalog of a joint launch (0 or 1)
+    int pad[3];
+    double lo[3], hi[3];
+};
+static_assert(sizeof(Item) == 96, "Item is copied as six 16-byte pieces");
 
 // ---- register tile of the second-role catalog -------------------------------------------
 struct Tile {
@@ -95,6 +131,7 @@ struct yawb_ctx {
     // pinned arena that small host tables pass through on their way to the device (yawb_h2d_small)
     unsigned char *h2d_base = nullptr;
     size_t h2d_size = 0, h2d_used = 0;
+    std::vector<struct FIndex *> fused;  // first-role indexes over pairs of catalogs (yawb_count2)
 };
 
 struct yawb_cat {
@@ -133,23 +170,39 @@ struct yawb_cat {
     std::vector<int> h_seg_off;        // [(n_patch * n_bins) + 1], patch-major, bin-minor
     int *d_seg_off = nullptr;
 
-    // first-role index: rows sorted by global sky-cell id
-    bool has_sindex = false;
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *sw = nullptr;
-    double *su = nullptr, *sv = nullptr, *st = nullptr;  // rows in the frame of their own patch
-    std::vector<SGrid> h_sgrid;
-    SGrid *d_sgrid = nullptr;
-    int *cell_start = nullptr;
-    long long n_cells = 0;
+    // first-role index: rows sorted by global sky-cell id (built on first use)
+    struct FIndex *findex = nullptr;
 
     // second-role index: rows sorted by (patch, bin, Hilbert index), cut into register tiles
     bool has_rtiles = false;
     double *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
     Tile *d_tiles = nullptr;
+    TileBox *d_tile_box = nullptr;  // [n_tiles] bounding boxes in the frame of the tile's own patch
     std::vector<Tile> h_tiles;     // host copy of the tile table (source of an async upload)
     std::vector<int> h_ptile_off;  // [n_patch + 1] first tile of each patch
     int *d_ptile_off = nullptr;
     int n_tiles = 0;
+};
+
+// First-role ("sky-cell") index over the rows of one catalog, or over the union of two catalogs with the
+// same patches and z-bins (fused counts: both are counted against a second catalog in ONE pass, the
+// catalog of a row travels in bit 31 of SRec::aux).  Rows sorted by (patch, z-bin, row-major cell).
+struct FIndex {
+    yawb_ctx *ctx = nullptr;
+    const yawb_cat *a = nullptr, *b = nullptr;  // sources (b == nullptr: single catalog)
+    long long n = 0;                            // rows (z-bin in range)
+    int n_patch = 0, n_bins = 1, n_types = 1;
+    bool weighted = false;
+    SRec *rec = nullptr;                                    // fixed-point rows in the frame of their patch
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr;     // the exact rows (FP64 recheck)
+    double *sw = nullptr;                                   // weights (1.0 for rows of an unweighted catalog)
+    int *cell_start = nullptr;
+    long long n_cells = 0;
+    std::vector<SGrid> h_sgrid;
+    SGrid *d_sgrid = nullptr;
+    std::vector<PatchFrame> h_frames;  // frames of the index (the larger catalog's, boxes grown over both)
+    PatchFrame *d_frames = nullptr;
+    int64_t device_bytes = 0;
 };
 
 // index construction (yawb_index.cu)
@@ -166,17 +219,22 @@ int yawb_cat_finalize(yawb_cat *cat);
 // pulled over by a kernel, so it never queues behind the bulk uploads of later catalogs.
 int yawb_h2d_small(yawb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int yawb_index_build_first(yawb_cat *cat);
+// fused first-role index over (a, b); cached in the context until either catalog is dropped or freed
+int yawb_findex_get_fused(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out, bool *built);
+void yawb_findex_drop_fused(yawb_ctx *ctx, const yawb_cat *cat);
+void yawb_findex_free(FIndex *fi);
 int yawb_index_build_second(yawb_cat *cat);
 void yawb_index_free(yawb_cat *cat, bool everything);
 
 // pair counting (yawb_count.cu)
 struct CountArgs {
-    const yawb_cat *c1;
+    const FIndex *c1;    // first-role index (one catalog, or two fused)
     const yawb_cat *c2;
     const int *d_pair_i;
     const int *d_pair_j;
     const long long *d_pair_item_base;  // [n_pairs + 1] prefix of tiles per pair
-    long long n_items;
+    long long n_items;                  // (patch pair, tile) combinations = threads of the planner
+    long long cap_heavy, cap_light;     // capacities of the two work-item lists
     int n_pairs;
     int n_bins;
     int n_edges;
@@ -184,9 +242,11 @@ struct CountArgs {
     const float *d_r2f;      // same, rounded to float
     const BinPar *d_binpar;  // [n_bins]
     double rmax_all;         // max search radius over non-empty z-bins
-    unsigned long long *d_out_cnt;  // [n_pairs][n_bins][n_edges-1]
-    double *d_out_w;                // same or nullptr if both catalogs are unweighted
+    unsigned long long *d_out_cnt;  // [n_types][n_pairs][n_bins][n_edges-1]
+    double *d_out_w;                // same or nullptr if every catalog is unweighted
     bool weighted;
+    // exact all-pairs kernel only (single catalogs): the first catalog's raw (patch, bin)-sorted rows
+    const yawb_cat *c1_cat;
 };
 int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches);
 int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches);
