@@ -226,26 +226,29 @@ class ClockSampler:
 
 
 # ---- CPU arm (oracle port of the reference's dual-tree path) --------------------------------------------
-def cpu_sample(wl, budget_s: float, workers: int | None = None, fixed_m: int | None = None):
-    """Time the CPU implementation on a bounded sample: the first `m` patches' diagonal pairs plus all
-    their links, all four count types, trees built for exactly the patches touched."""
+def cpu_sample(wl, budget_s: float, workers: int | None = None, fixed_m: int | None = None, tags=None):
+    """Time the CPU port on a bounded sample: the first `m` patches' diagonal pairs plus all their links, the
+    count types in `tags`, trees built (on the worker pool) for exactly the patches touched.  Returns the
+    per-patch-pair counts as well, so that the caller can check the GPU result against them."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_port
 
     workers = workers or cpu_port.physical_cores()
+    tags = list(tags or COUNT_TYPES)
     pi, pj = wl["pair_i"], wl["pair_j"]
     n_bins = len(wl["config"].binning.binning)
     plan = wl["plan"]
     ang_min = np.array([lim[:, 0] for lim in plan.limits])
     ang_max = np.array([lim[:, 1] for lim in plan.limits])
+    scales = wl["config"].scales
 
     def rows_of(key, patches, binned):
         a = wl["arrays"][key]
         out = {}
         for p in patches:
             s, e = a["patch_off"][p], a["patch_off"][p + 1]
-            out[p] = (a["xyz"][s:e], None if a["weights"] is None else a["weights"][s:e],
-                      a["zbin"][s:e] if binned else None)
+            zb = a["zbin"][s:e].astype(np.int32) if binned else None
+            out[p] = (a["xyz"][s:e], None if a["weights"] is None else a["weights"][s:e], zb)
         return out
 
     def run(m):
@@ -256,21 +259,27 @@ def cpu_sample(wl, budget_s: float, workers: int | None = None, fixed_m: int | N
         t_build = t_count = 0.0
         naive = 0
         trees = {}
+        used = {k for t in tags for k in COUNT_TYPES[t]}
         for key, binned, need in (("ref", True, need1), ("ref_rand", True, need1), ("unk", False, need2),
                                   ("unk_rand", False, need2)):
+            if key not in used:
+                continue
             rows = rows_of(key, need, binned)
-            built, dt = cpu_port.build_catalog_trees([rows[p] for p in need], n_bins if binned else None)
+            built, dt = cpu_port.build_catalog_trees([rows[p] for p in need], n_bins if binned else None, workers=workers)
             trees[key] = dict(zip(need, built))
             t_build += dt
-        for tag, (a, b) in COUNT_TYPES.items():
-            _, dt = cpu_port.count_pairs(trees[a], trees[b], sel, ang_min, ang_max, workers=workers)
+        counts = {}
+        for tag in tags:
+            a, b = COUNT_TYPES[tag]
+            counts[tag], dt = cpu_port.count_pairs(trees[a], trees[b], sel, ang_min, ang_max, rweight=scales.rweight,
+                                                   resolution=scales.resolution, workers=workers)
             t_count += dt
             ca, cb = wl["arrays"][a], wl["arrays"][b]
             for i, j in sel:
                 zb = ca["zbin"][ca["patch_off"][i]:ca["patch_off"][i + 1]]
                 n1 = int(((zb >= 0) & (zb < n_bins)).sum())
                 naive += n1 * int(cb["patch_off"][j + 1] - cb["patch_off"][j])
-        return dict(patches=m, pairs=len(sel), t_build=t_build, t_count=t_count, naive=naive, workers=workers)
+        return dict(patches=m, pairs=len(sel), t_build=t_build, t_count=t_count, naive=naive, workers=workers, counts=counts)
 
     if fixed_m is not None:
         return run(fixed_m)
@@ -284,10 +293,84 @@ def cpu_sample(wl, budget_s: float, workers: int | None = None, fixed_m: int | N
     return res
 
 
+def check_parity(wl, results: dict, cpu: dict) -> int:
+    """GPU result of the full job against the CPU port's per-patch-pair counts (scipy cKDTree, the reference's
+    arithmetic): bit-exact for unweighted catalogs, 1e-12 relative with weights.  Raises on any difference;
+    returns the number of (count type, patch pair) results compared."""
+    plan = wl["plan"]
+    index = {(int(i), int(j)): k for k, (i, j) in enumerate(zip(wl["pair_i"], wl["pair_j"]))}
+    checked = 0
+    for tag, per_pair in cpu["counts"].items():
+        got = plan.finish(results[tag])  # (n_scales, n_pairs, n_bins)
+        a, b = COUNT_TYPES[tag]
+        weighted = wl["arrays"][a]["weights"] is not None or wl["arrays"][b]["weights"] is not None
+        exact = not weighted and wl["config"].scales.rweight is None
+        for (i, j), want in per_pair.items():
+            mine = got[:, index[(i, j)], :]
+            ok = np.array_equal(mine, want) if exact else np.allclose(mine, want, rtol=1e-12, atol=0.0)
+            if not ok:
+                raise AssertionError(f"parity failure: {tag} counts of patch pair ({i}, {j}) differ from the CPU reference "
+                                     f"algorithm: max |diff| = {np.abs(mine - want).max()}")
+            checked += 1
+    return checked
+
+
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  With the
+    reference installed under `baseline/_ref` (`__graft_entry__.build()`), that is the UNMODIFIED package run
+    through its own `Catalog.build_trees` / `PatchLinkage.count_pairs` (`oracle/ref_runner.py`, a separate
+    process: it forks worker pools) on a bounded sample of the workload -- the first declination stripes of the
+    patch grid at the full densities; otherwise the oracle's port of the same algorithm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    spec = WORKLOADS[args.workload]
+    plain = "scales" not in spec and not spec.get("weighted")
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "yaw"))
+    if have_ref and plain:
+        runner = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--workload", args.workload,
+                  "--scale", str(args.scale)]
+
+        def call(stripes, steps, warmup):
+            out = subprocess.run(runner + ["--stripes", str(stripes), "--steps", str(steps), "--warmup", str(warmup)],
+                                 capture_output=True, text=True)
+            if out.returncode != 0:
+                raise RuntimeError(out.stderr[-2000:])
+            return json.loads(out.stdout.strip().splitlines()[-1])
+
+        try:
+            probe = call(1, 1, 0)  # one stripe, one step: what a stripe costs on this box
+            ny = probe["stripes_total"]
+            t1 = probe["steps"][0]["build_s"] + probe["steps"][0]["count_s"]
+            total_budget = max(args.cpu_budget, 10.0) * 12.0  # the whole --steps/--warmup run: a few minutes
+            stripes = int(max(1, min(ny, total_budget / max(args.steps + args.warmup, 1) / max(t1, 1e-3))))
+            res = call(stripes, args.steps, args.warmup)
+            times = [s_["build_s"] + s_["count_s"] for s_ in res["steps"]]
+            t = float(np.mean(times))
+            naive = sum(res["naive_pair_tests"].values())
+            value = naive / t / 1e9
+            full = call(ny, 1, 0) if args.full_reference and stripes < ny else (res if stripes == ny else None)
+            cb = dict(value=value, unit="Gpairs/s", cores=res["workers"], kind="reference",
+                      sample=f"unmodified yaw {res['version']} from baseline/_ref: {res['patches']}/{res['patches_total']} patches "
+                             f"({stripes} of {ny} declination stripes at full density, {res['linked_pairs']} linked patch pairs x 4 "
+                             f"count types), build_trees {np.mean([s_['build_s'] for s_ in res['steps']]):.2f}s + count_pairs "
+                             f"{np.mean([s_['count_s'] for s_ in res['steps']]):.2f}s per step",
+                      host_cores=res["host_cores"], rows=res["rows"])
+            if full is not None:
+                tf = full["steps"][0]["build_s"] + full["steps"][0]["count_s"]
+                cb["full_job_s"] = tf
+                cb["full_job_value"] = sum(full["naive_pair_tests"].values()) / tf / 1e9
+                cb["full_job_pairs_in_scale"] = full["pairs_in_scale"]
+            emit(dict(
+                impl="reference", metric="crosscorrelate_effective_pair_tests_per_s", value=value, unit="Gpairs/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=f"{args.workload} crosscorrelate DD+DR+RD+RR, BoxRandoms, scale={args.scale}", sample=cb["sample"]),
+                cpu_baseline=cb, e2e=dict(value=value, unit="Gpairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0))
+            return
+        except Exception as exc:  # fall back to the port, and say so
+            log(f"[bench] reference runner failed ({exc}); falling back to the oracle's port")
     wl = make_workload(args.workload, args.scale)
     total_naive = sum(wl["naive"].values())
     times, last = [], None
@@ -318,14 +401,13 @@ def run_reference_arm(args):
 # ---- GPU arm ------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
     import yet_another_wizz_b200 as yb
-    from yet_another_wizz_b200 import _lib
     from yet_another_wizz_b200.pipeline import count_cross_pipelined
     from yet_another_wizz_b200.sharding import assign_patches_contiguous, pair_costs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
+    dist = torch = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -342,9 +424,7 @@ def run_gpu_arm(args):
     pi, pj, plan = wl["pair_i"], wl["pair_j"], wl["plan"]
     total_naive = sum(wl["naive"].values())
     if weak:  # one independent field per GPU: the job is the union of the fields
-        import torch
-
-        t = torch.tensor([float(total_naive), float(len(pi)), -float(len(pi))], dtype=torch.float64, device="cuda")
+        t = torch.tensor([float(total_naive), float(len(pi))], dtype=torch.float64, device="cuda")
         tsum, tmax = t.clone(), t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -353,10 +433,10 @@ def run_gpu_arm(args):
     else:
         n_pairs_max = len(pi)
 
-    # this rank's share: second-catalog patches are dealt out as spatially compact groups of equal summed
-    # pair cost, a rank
-    # counts every linked pair of its patches and holds only the rows it needs (its own second-catalog
-    # patches, plus the first-catalog patches linked to them)
+    # this rank's share of a strong-scaling run: second-catalog patches are dealt out as spatially compact groups
+    # of equal summed pair cost (`sharding.assign_patches_contiguous`), a rank counts every linked pair of its
+    # patches and holds only the rows it needs (its own second-catalog patches, plus the first-catalog patches
+    # linked to them)
     own = np.arange(len(pi))
     arrays = wl["arrays"]
     if world > 1 and not weak:
@@ -389,54 +469,81 @@ def run_gpu_arm(args):
         host[key] = h
 
     def upload_all():
-        # big catalogs first: the pair counts that need them (RR, RD) then overlap with the remaining copies
         return {k: eng.upload_catalog(host[k]["xyz"], host[k]["patch_off"], weights=host[k]["weights"],
                                       zbin=host[k]["zbin"], n_bins=host[k]["n_bins"])
-                for k in ("ref_rand", "unk_rand", "unk", "ref")}
+                for k in ("ref", "ref_rand", "unk", "unk_rand")}
 
-    n_out = len(pi) * plan.n_bins * (plan.n_edges - 1)
-    d2h_bytes = 4 * len(opi) * plan.n_bins * (plan.n_edges - 1) * 16
+    n_sub = plan.n_edges - 1
+    shape_own = (len(opi), plan.n_bins, n_sub)
+    weighted_tag = {tag: arrays[a]["weights"] is not None or arrays[b]["weights"] is not None for tag, (a, b) in COUNT_TYPES.items()}
+    any_weighted = any(weighted_tag.values())
+    # the reference sample and its randoms are counted in one pass against each unbinned catalog (yawb_count2)
+    # unless only one of them carries weights
+    fuse = (arrays["ref"]["weights"] is None) == (arrays["ref_rand"]["weights"] is None) and not args.no_fuse
+    d2h_bytes = 4 * len(opi) * plan.n_bins * n_sub * 16
 
-    def reduce_results(results):
-        if world == 1:
-            return results
-        import torch
-
-        # weak: every field owns one slab of the result tensor; strong: every rank owns its patch pairs
+    # multi-GPU: every rank counts into device buffers, ONE NCCL sum-reduce of the (4, n_pairs, n_bins, n_sub)
+    # tensor to rank 0 -- inside the timed region
+    red = None
+    if dist is not None:
         slabs = world if weak else 1
-        full = np.zeros((slabs, 4, n_pairs_max, plan.n_bins, plan.n_edges - 1), dtype=np.int64)
-        for t, tag in enumerate(COUNT_TYPES):
-            full[rank if weak else 0, t, own] = results[tag]
-        ten = torch.from_numpy(full).cuda()
-        dist.reduce(ten, dst=0, op=dist.ReduceOp.SUM)  # the single NCCL reduce of the count tensors
-        torch.cuda.synchronize()
-        return {tag: ten[:, t].cpu().numpy() for t, tag in enumerate(COUNT_TYPES)}
+        red = dict(full=torch.zeros((slabs, 4, n_pairs_max, plan.n_bins, n_sub), dtype=torch.float64 if any_weighted else torch.int64,
+                                    device="cuda"),
+                   own=torch.from_numpy(own).cuda(),
+                   buf={tag: (torch.zeros(shape_own, dtype=torch.float64, device="cuda"), torch.zeros(shape_own, dtype=torch.int64, device="cuda"))
+                        for tag in COUNT_TYPES})
 
-    def count_all(dev):
+    def count_all(dev, on_device: bool):
         results, stats = {}, {}
-        # order follows the uploads (ref_rand, unk_rand, unk, ref): RR and RD run while the remaining
-        # catalogs are still on their way through PCIe
-        for tag in ("RR", "RD", "DR", "DD"):
-            a, b = COUNT_TYPES[tag]
-            ci, _, st = eng.count(dev[a], dev[b], opi, opj, plan.r2)
-            results[tag], stats[tag] = ci, st
+
+        def pick(tag, ci, cf):
+            return cf if weighted_tag[tag] else ci
+
+        if fuse:
+            for (ta, tb), k2 in ((("DD", "RD"), "unk"), (("DR", "RR"), "unk_rand")):
+                if on_device:
+                    ptrs = (red["buf"][ta][0].data_ptr(), red["buf"][ta][1].data_ptr(), red["buf"][tb][0].data_ptr(),
+                            red["buf"][tb][1].data_ptr())
+                    _, _, st = eng.count2(dev["ref"], dev["ref_rand"], dev[k2], opi, opj, plan.r2, out_device=ptrs)
+                else:
+                    (ia, fa), (ib, fb), st = eng.count2(dev["ref"], dev["ref_rand"], dev[k2], opi, opj, plan.r2)
+                    results[ta], results[tb] = pick(ta, ia, fa), pick(tb, ib, fb)
+                stats[f"{ta}+{tb}"] = st
+        else:
+            for tag in ("DD", "RD", "DR", "RR"):
+                a, b = COUNT_TYPES[tag]
+                if on_device:
+                    st = eng.count_into_device(dev[a], dev[b], opi, opj, plan.r2, red["buf"][tag][0].data_ptr(), red["buf"][tag][1].data_ptr())
+                else:
+                    ci, cf, st = eng.count(dev[a], dev[b], opi, opj, plan.r2)
+                    results[tag] = pick(tag, ci, cf)
+                stats[tag] = st
         return results, stats
+
+    def reduce_device():
+        """scatter this rank's rows into the job-wide tensor and sum-reduce it to rank 0 (NCCL over NVLink)"""
+        full = red["full"]
+        full.zero_()
+        for t, tag in enumerate(COUNT_TYPES):
+            src = red["buf"][tag][0 if weighted_tag[tag] else 1]
+            full[rank if weak else 0, t].index_copy_(0, red["own"], src.to(full.dtype))
+        dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
+        return full
 
     def barrier():
         if dist is not None:
             dist.barrier()
+            torch.cuda.synchronize()
         eng.sync()
 
     def max_over_ranks(x: float) -> float:
         if dist is None:
             return x
-        import torch
-
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: raw inputs resident in HBM -> index build + counts ----
+    # ---- value: raw inputs resident in HBM -> index build + counts (+ the NCCL reduce) ----
     dev = upload_all()
     step_ms, kernel_ms, index_ms, stats_last, launches = [], [], [], None, 0
     clocks = ClockSampler(local_rank)
@@ -446,11 +553,21 @@ def run_gpu_arm(args):
         for d in dev.values():
             d.drop_index()
         barrier()
-        eng.timer_start()
-        results, stats = count_all(dev)  # builds the dropped indexes on first use, inside the timed region
+        if dist is None:
+            eng.timer_start()
+            results, stats = count_all(dev, False)  # builds the dropped indexes on first use, inside the timed region
+            ms = eng.timer_stop()
+        else:
+            # device timeline of this rank: the counts run on the engine's stream (each call returns once its
+            # results are complete), the reduce on torch's; both lie between the two events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, stats = count_all(dev, True)
+            full = reduce_device()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
         t_idx = sum(s["index_ms"] for s in stats.values())
-        ms = eng.timer_stop()
-        results = reduce_results(results)
         barrier()
         if rank == 0:
             log(f"[bench] step {step}: {ms:.2f} ms (index {t_idx:.2f}, kernels "
@@ -461,6 +578,9 @@ def run_gpu_arm(args):
             index_ms.append(t_idx)
             stats_last = stats
             launches += sum(s["launches"] for s in stats.values())
+    if dist is not None:
+        full = full.cpu().numpy()
+        results = {tag: (full[:, t] if weak else full[0, t]) for t, tag in enumerate(COUNT_TYPES)}
     for d in dev.values():
         d.free()
 
@@ -472,9 +592,14 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         # the package's schedule for host-resident inputs: every copy enqueued up front, counts issued in
         # arrival order; with --e2e-groups > 1 the unbinned catalogs travel and are counted in patch slices
-        results_e2e, _, _, devs = count_cross_pipelined(eng, host, opi, opj, plan.r2, groups=args.e2e_groups)
+        ci_e2e, cf_e2e, _, devs = count_cross_pipelined(eng, host, opi, opj, plan.r2, groups=args.e2e_groups, fuse=fuse)
+        results_e2e = {tag: (cf_e2e if weighted_tag[tag] else ci_e2e)[tag] for tag in COUNT_TYPES}
+        if dist is not None:
+            for t, tag in enumerate(COUNT_TYPES):
+                red["buf"][tag][0 if weighted_tag[tag] else 1].copy_(torch.from_numpy(results_e2e[tag]))
+            full = reduce_device()
+            torch.cuda.synchronize()
         dev = {f"{k}{n}": d for k, lst in devs.items() for n, (d, _, _) in enumerate(lst)}
-        results_e2e = reduce_results(results_e2e)
         barrier()
         dt = time.perf_counter() - t0
         for d in dev.values():
@@ -482,6 +607,9 @@ def run_gpu_arm(args):
         if rank == 0:
             log(f"[bench] e2e step {step}: {dt * 1e3:.1f} ms")
             if step == 0:
+                if dist is not None:
+                    full = full.cpu().numpy()
+                    results_e2e = {tag: (full[:, t] if weak else full[0, t]) for t, tag in enumerate(COUNT_TYPES)}
                 for tag in COUNT_TYPES:
                     assert np.array_equal(results_e2e[tag], results[tag]), f"e2e result of {tag} differs"
         if step >= e2e_warm:
@@ -498,14 +626,13 @@ def run_gpu_arm(args):
         h2d_only.append(time.perf_counter() - t0)
         for d in dev.values():
             d.free()
-    h2d_only_ms = 1e3 * min(h2d_only)
+    h2d_only_ms = 1e3 * max_over_ranks(min(h2d_only))
 
-    # statistics of the last timed step, summed over ranks
-    tot_stats = np.array([sum(s[k] for s in stats_last.values()) for k in ("pair_tests", "pair_tests_naive", "rechecks")],
+    # statistics of the last timed step, summed over ranks; kernel time: the slowest rank's
+    tot_stats = np.array([sum(s[k] for s in stats_last.values()) for k in ("pair_tests", "pair_tests_naive", "rechecks", "work_items")],
                          dtype=np.float64)
+    t_kernel_max = max_over_ranks(float(np.mean(kernel_ms)))
     if dist is not None:
-        import torch
-
         t = torch.from_numpy(tot_stats).cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         tot_stats = t.cpu().numpy()
@@ -525,10 +652,10 @@ def run_gpu_arm(args):
     sms = eng.num_sms
     peak_tests = sms * 128 * sm_max_mhz * 1e6 / FP32_INSTR_PER_TEST
     t_step = float(np.mean(step_ms)) / 1e3
-    t_kernel = float(np.mean(kernel_ms)) / 1e3
+    t_kernel = t_kernel_max / 1e3
     executed = float(tot_stats[0])
-    achieved = executed / max(t_kernel, 1e-12) / world  # per GPU: rank 0's kernel time, 1/world of the tests
-    in_scale = {tag: int(results[tag].sum()) for tag in COUNT_TYPES}
+    achieved = executed / max(t_kernel, 1e-12) / world  # per GPU: the slowest rank's kernel time, 1/world of the tests
+    in_scale = {tag: float(results[tag].sum()) for tag in COUNT_TYPES}
     clk = clocks.summary()
 
     line = dict(
@@ -542,30 +669,29 @@ def run_gpu_arm(args):
                         if weak else ""),
             linked_patch_pairs=int(len(pi)), naive_pair_tests=wl["naive"], pairs_in_scale=in_scale,
             l2="inputs (>= 1 GB of catalog rows) exceed the 126 MB L2; every step rebuilds the index from the raw rows",
-            parallelism=(f"{world} fields of {wl['n_patch']} patches, one per GPU (no patch links between fields), one NCCL "
-                         f"reduce of the count tensor" if weak else
-                         f"second-catalog patches dealt to {world} GPU(s) as compact equal-cost groups, each rank holds only "
-                         f"the rows of its patches and of the first-catalog patches linked to them, one NCCL reduce of the counts"),
+            parallelism=("1 GPU" if world == 1 else
+                         f"{world} fields of {wl['n_patch']} patches, one per GPU (no patch links between fields), one NCCL "
+                         f"reduce of the count tensor inside the timed region" if weak else
+                         f"the ONE job split over {world} GPUs: second-catalog patches dealt as compact equal-cost groups, each rank "
+                         f"holds only the rows of its patches and of the first-catalog patches linked to them; ONE NCCL sum-reduce "
+                         f"of the (4, n_pairs, n_bins, n_sub) count tensor to rank 0 inside the timed region"),
+            fused_counts=bool(fuse),
         ),
-        breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=t_kernel * 1e3,
-                          per_count={tag: stats_last[tag]["kernel_ms"] for tag in COUNT_TYPES},
-                          work_items={tag: int(stats_last[tag]["work_items"]) for tag in COUNT_TYPES},
-                          executed_tests={tag: int(stats_last[tag]["pair_tests"]) for tag in COUNT_TYPES},
+        breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=float(np.mean(kernel_ms)),
+                          per_launch={tag: s["kernel_ms"] for tag, s in stats_last.items()},
+                          work_items={tag: int(s["work_items"]) for tag, s in stats_last.items()},
+                          executed_tests={tag: int(s["pair_tests"]) for tag, s in stats_last.items()},
                           host_prep_s=wl["t_host_prep"], catalogs_s=wl["t_catalogs"]),
         roofline=dict(
             bound="fp32", achieved=achieved / 1e9, peak=peak_tests / 1e9, unit="Gtests/s",
             frac=achieved / peak_tests,
-            # dram__bytes_read.sum + dram__bytes_write.sum of the dominant (RR) launch, one `ncu --set full`
-            # capture of this workload (profiles/r01_h_ncu_full_k_count_uni.txt); not an HBM-bound kernel
-            traffic=1.0075e9 if (args.workload == "C3" and args.scale == 1.0 and (world == 1 or weak)) else None,
-            traffic_unit="bytes per RR launch (algorithmic minimum 4.8e8: 1e7 tile rows + 1e7 candidate rows, 24 B each)",
-            note=f"pair-count kernels of rank 0; executed (non-pruned) tests / kernel time vs {sms} SMs x 128 lanes x "
+            traffic=None,  # dram bytes per launch come from the ncu captures under profiles/, not from a timed run
+            note=f"pair-count kernels (slowest rank); executed (non-pruned) tests / kernel time vs {sms} SMs x 128 lanes x "
                  f"{sm_max_mhz:.0f} MHz / {FP32_INSTR_PER_TEST} FP32 instr per test (MEASURED_PEAKS.json sm_max_mhz)",
             executed_pair_tests=int(executed), prune_efficiency=1.0 - executed / max(float(tot_stats[1]), 1.0),
             useful_fraction=sum(in_scale.values()) / max(executed, 1),
-            fp64_rechecks=int(tot_stats[2]),
-            per_launch_frac={tag: (stats_last[tag]["pair_tests"] / max(stats_last[tag]["kernel_ms"], 1e-9) * 1e3) / peak_tests
-                             for tag in COUNT_TYPES},
+            fp64_rechecks=int(tot_stats[2]), work_items=int(tot_stats[3]),
+            per_launch_frac={tag: (s["pair_tests"] / max(s["kernel_ms"], 1e-9) * 1e3) / peak_tests for tag, s in stats_last.items()},
         ),
         e2e=dict(value=total_naive / float(np.mean(e2e_s)) / 1e9, unit="Gpairs/s", ms_per_step=float(np.mean(e2e_s)) * 1e3,
                  h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=int(d2h_bytes),
@@ -573,7 +699,9 @@ def run_gpu_arm(args):
         gpu_launches=int(launches),
         clocks=clk,
     )
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and not weak:
+        # the CPU port of the reference's algorithm on a bounded sample of THIS job: timing baseline and, at the
+        # full size of the workload, the parity check of the GPU result (bit-exact / 1e-12 with weights)
         cpu = cpu_sample(wl, args.cpu_budget)
         t_cpu = cpu["t_build"] + cpu["t_count"]
         line["cpu_baseline"] = dict(
@@ -582,6 +710,9 @@ def run_gpu_arm(args):
                    f"x 4 count types): tree build {cpu['t_build']:.2f}s + count {cpu['t_count']:.2f}s",
             extrapolated_full_job_s=t_cpu * total_naive / max(cpu["naive"], 1),
         )
+        line["parity_checked_pairs"] = check_parity(wl, results, cpu)
+        line["parity"] = ("GPU counts of the full job == CPU reference algorithm (scipy cKDTree) on every sampled patch pair, "
+                          + ("1e-12 relative" if any_weighted or wl["config"].scales.rweight is not None else "bit-exact"))
     emit(line)
     eng.close()
     if dist is not None:
@@ -598,10 +729,13 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every catalog (development only)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="count DD, RD, DR, RR in four passes instead of two fused ones")
+    ap.add_argument("--full-reference", action="store_true", help="--impl reference: also time the full job once")
     ap.add_argument("--e2e-groups", type=int, default=1,
                     help="patch slices per unbinned catalog in the end-to-end schedule (1 = whole catalogs)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = one C3-sized field per GPU (default), strong = the one field split over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the ONE job split over the GPUs (default, the north-star case), "
+                         "weak = one independent field of the workload's size per GPU")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

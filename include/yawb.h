@@ -43,7 +43,7 @@ typedef struct {
     uint64_t pair_tests;       /* pair tests executed (after sky-cell / tile pruning)                     */
     uint64_t pair_tests_naive; /* sum over requested patch pairs and z-bins of n1 * n2                    */
     uint64_t rechecks;         /* tests re-evaluated in exact FP64                                        */
-    uint64_t work_items;       /* (tile, patch) work items that survived the bounding-sphere test         */
+    uint64_t work_items;       /* work items written by the planner (tile x linked patch, non-empty)      */
     uint64_t launches;         /* kernels launched by this call                                           */
     uint64_t reserved;
 } yawb_stats;
@@ -133,6 +133,20 @@ int yawb_sum_weights(const yawb_cat *cat, double *out);
 int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pair_i,
                const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges,
                uint32_t flags, double *out_f64, int64_t *out_i64, yawb_stats *stats);
+
+/* Two first catalogs against the same second catalog in ONE pass: results identical to
+ *     yawb_count(ctx, cat1a, cat2, ...) -> out_*_a   and   yawb_count(ctx, cat1b, cat2, ...) -> out_*_b.
+ *
+ * This is how crosscorrelate's DD + RD (reference sample and its randoms against the unknown sample) and
+ * DR + RR (the same two against the unknown sample's randoms) are counted,
+ * src/yaw/correlation/measurements.py:623-626: both first catalogs share the patches, the z-binning and the
+ * thresholds, so their rows are indexed together (one fused sky-cell index, cached until either catalog is
+ * dropped or freed) and every register tile of the second catalog is loaded, rotated and matched against the
+ * sky cells once instead of twice.  cat1a and cat1b need the same n_patch / n_bins; YAWB_FLAG_EXACT_BRUTEFORCE
+ * is not supported here.  stats cover both counts. */
+int yawb_count2(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2, const int32_t *pair_i,
+                const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
+                double *out_f64_a, int64_t *out_i64_a, double *out_f64_b, int64_t *out_i64_b, yawb_stats *stats);
 
 /* Pinned host memory helpers so callers can stage inputs for async copies. */
 int yawb_host_alloc(void **ptr, uint64_t bytes);

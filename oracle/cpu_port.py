@@ -14,12 +14,13 @@ reference's algorithm exactly -- same third-party kernel, same work decompositio
   * a task farm over patch pairs with `multiprocessing.Pool.imap_unordered`
     (src/yaw/utils/parallel.py:318-343), diagonal pairs first (measurements.py:258-289).
 
-Differences from the reference that do not change the arithmetic: trees are kept in the
-worker processes' memory (fork-inherited) instead of being pickled to disk and re-read
-per pair, and the scale->angle conversion is evaluated once per z-bin instead of once per
-pair.  Both make this port slightly FASTER than the reference, i.e. a conservative baseline.
+Differences from the reference that do not change the arithmetic: trees are built on the
+worker pool like the reference's, but kept in the worker processes' memory (fork-inherited)
+instead of being pickled to disk and re-read per pair, and the scale->angle conversion is
+evaluated once per z-bin instead of once per pair.  Both make this port slightly FASTER than
+the reference, i.e. a conservative baseline.
 
-Pinned against the live reference in `tests/test_vs_reference.py::test_cpu_port_*`.
+Pinned against the live reference in `tests/test_vs_reference.py::test_cpu_port_counts_equal_reference`.
 """
 
 from __future__ import annotations
@@ -119,10 +120,17 @@ def _build_one(args):
 
 
 def build_catalog_trees(patch_rows, n_bins: int | None, workers: int = 1):
-    """`Catalog.build_trees` (catalog.py:1406-1460): `patch_rows[p] = (xyz, weights, zbin)`.
-    Built in the parent so the forked count workers inherit them (the reference pickles them to disk)."""
+    """`Catalog.build_trees` (catalog.py:1406-1460): `patch_rows[p] = (xyz, weights, zbin)`, one task per
+    patch on the worker pool (`parallel.iter_unordered(BinnedTrees.build, patches)`, catalog.py:1450-1456).
+    The reference's workers pickle their trees to disk (trees.py:529-543); here they travel back to the parent
+    pickled through the pool's pipe, so that the forked count workers inherit them."""
     t0 = time.perf_counter()
-    trees = [build_patch_trees(x, w, z, n_bins) for (x, w, z) in patch_rows]
+    args = [(x, w, z, n_bins) for (x, w, z) in patch_rows]
+    if workers <= 1 or len(args) <= 1:
+        trees = [_build_one(a) for a in args]
+    else:
+        with mp.get_context("fork").Pool(min(workers, len(args))) as pool:
+            trees = pool.map(_build_one, args, chunksize=1)
     return trees, time.perf_counter() - t0
 
 

@@ -85,6 +85,26 @@ class _Planck15Like:
         return self.comoving_distance(z) / (1.0 + np.asarray(z))
 
 
+class FLRW:
+    """stand-in for `astropy.cosmology.FLRW` (module level so that instances pickle: the reference ships its
+    `Configuration` to `multiprocessing` workers)"""
+
+
+class _P15(_Planck15Like, FLRW):
+    pass
+
+
+class StrEnum(str, enum.Enum):
+    """`strenum.StrEnum`: case preserving, unlike `enum.StrEnum`"""
+
+    def __str__(self) -> str:
+        return self.value
+
+    @staticmethod
+    def _generate_next_value_(name, start, count, last_values):
+        return name
+
+
 def _install_stubs() -> None:
     # 1. yaw._version
     ver = types.ModuleType("yaw._version")
@@ -93,14 +113,6 @@ def _install_stubs() -> None:
     sys.modules.setdefault("yaw._version", ver)
 
     # 2. strenum (case preserving, unlike enum.StrEnum)
-    class StrEnum(str, enum.Enum):
-        def __str__(self) -> str:
-            return self.value
-
-        @staticmethod
-        def _generate_next_value_(name, start, count, last_values):
-            return name
-
     strenum = types.ModuleType("strenum")
     strenum.StrEnum = StrEnum
     sys.modules.setdefault("strenum", strenum)
@@ -136,12 +148,6 @@ def _install_stubs() -> None:
     units.Quantity = Quantity
     units.Mpc = 1.0
     cosmology = types.ModuleType("astropy.cosmology")
-
-    class FLRW:
-        pass
-
-    class _P15(_Planck15Like, FLRW):
-        pass
 
     planck15 = _P15()
     cosmology.FLRW = FLRW

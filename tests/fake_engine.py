@@ -67,3 +67,8 @@ class OracleEngine:
                 else:
                     out_f[k, b] = h
         return out_i, out_f, dict(kernel_ms=0.0, pair_tests=0, pair_tests_naive=0, rechecks=0, launches=0)
+
+    def count2(self, cat1a, cat1b, cat2, pair_i, pair_j, r2_edges):
+        ia, fa, st = self.count(cat1a, cat2, pair_i, pair_j, r2_edges)
+        ib, fb, _ = self.count(cat1b, cat2, pair_i, pair_j, r2_edges)
+        return (ia, fa), (ib, fb), st

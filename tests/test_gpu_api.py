@@ -73,7 +73,8 @@ def test_pipelined_schedule_gpu(engine):
         for tag, kind in (("DD", "dd"), ("DR", "dr"), ("RD", "rd"), ("RR", "rr")):
             got = plan.finish(counts[tag])[0]
             assert np.array_equal(got, g[f"cross_{kind}_counts_s0"][:, pair_i, pair_j].T), (groups, tag)
-            assert stats[tag]["pair_tests"] > 0
+        assert all(st["pair_tests"] > 0 for st in stats.values())
+        assert set("+".join(stats).split("+")) == {"DD", "DR", "RD", "RR"}  # fused passes report under joined tags
         for lst in devs.values():
             for dev, _, _ in lst:
                 dev.free()

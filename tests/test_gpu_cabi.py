@@ -237,6 +237,52 @@ def test_random_dense_fast_vs_exact(engine):
             d1.free(); d2.free()
 
 
+def test_fused_count_equals_two_counts(engine):
+    """`yawb_count2` (two first catalogs in one pass over a fused sky-cell index) must return exactly what two
+    `yawb_count` calls return: different sizes, weights on one side only, dropped z-bins, several edge counts,
+    and a patch that is empty in the larger catalog"""
+    rng = np.random.default_rng(11)
+    n_patch, n_bins = 6, 4
+
+    def cat(n, binned, weighted, empty_patch=None):
+        ra = rng.uniform(0.0, 0.06, n); dec = np.arcsin(rng.uniform(-0.02, 0.02, n))
+        patch = np.minimum((ra / 0.06 * n_patch).astype(int), n_patch - 1)
+        if empty_patch is not None:
+            keep = patch != empty_patch
+            ra, dec, patch = ra[keep], dec[keep], patch[keep]
+        order = np.argsort(patch, kind="stable")
+        xyz = oracle.radec_to_xyz(ra, dec)[order]
+        off = np.concatenate([[0], np.cumsum(np.bincount(patch, minlength=n_patch))])
+        zbin = rng.integers(-1, n_bins + 1, len(ra)).astype(np.int32) if binned else None
+        w = rng.uniform(0.5, 1.5, len(ra)) if weighted else None
+        return xyz, off, w, zbin
+
+    pi, pj = np.meshgrid(np.arange(n_patch), np.arange(n_patch), indexing="ij")
+    pi, pj = pi.ravel(), pj.ravel()
+    for wa, wb, w2, n_edges in ((False, False, False, 2), (True, False, False, 2), (False, False, True, 5), (True, True, False, 12)):
+        r2 = np.sort(rng.uniform(1e-8, 4e-6, (n_bins, n_edges)), axis=1)
+        xa, oa, wwa, za = cat(3000, True, wa)
+        xb, ob, wwb, zb = cat(40000, True, wb, empty_patch=2)
+        x2, o2, ww2, _ = cat(30000, False, w2)
+        da = engine.upload_catalog(xa, oa, weights=wwa, zbin=za, n_bins=n_bins)
+        db = engine.upload_catalog(xb, ob, weights=wwb, zbin=zb, n_bins=n_bins)
+        d2 = engine.upload_catalog(x2, o2, weights=ww2)
+        (ia, fa), (ib, fb), st = engine.count2(da, db, d2, pi, pj, r2)
+        sa_i, sa_f, _ = engine.count(da, d2, pi, pj, r2)
+        sb_i, sb_f, _ = engine.count(db, d2, pi, pj, r2)
+        assert_array_equal(ia, sa_i)
+        assert_array_equal(ib, sb_i)
+        assert_allclose(fa, sa_f, rtol=RTOL_WEIGHTED, atol=0)
+        assert_allclose(fb, sb_f, rtol=RTOL_WEIGHTED, atol=0)
+        assert sa_i.sum() > 100 and sb_i.sum() > 1000 and st["pair_tests"] > 0
+        # the other order of the two catalogs (the smaller one supplies the frames where the larger is empty)
+        (ib2, _), (ia2, _), _ = engine.count2(db, da, d2, pi, pj, r2)
+        assert_array_equal(ia2, sa_i)
+        assert_array_equal(ib2, sb_i)
+        for d in (da, db, d2):
+            d.free()
+
+
 @pytest.mark.parametrize("variant", ["sat", "pred"])
 def test_pair_test_variants_exact(engine, variant, monkeypatch):
     """both FP32 pair-test formulations (7-instruction saturating ramp / 8-instruction predicated) must

@@ -13,7 +13,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libyawb.so")
+# YAWB_LIB: development override (kernel variants built side by side)
+LIB_PATH = os.environ.get("YAWB_LIB") or os.path.join(_HERE, "csrc", "libyawb.so")
 
 FLAG_EXACT_BRUTEFORCE = 1
 FLAG_OUT_DEVICE = 2
@@ -25,7 +26,7 @@ EXPORTS = (
     "yawb_last_error", "yawb_create", "yawb_destroy", "yawb_upload_catalog", "yawb_free_catalog",
     "yawb_build_index", "yawb_drop_index", "yawb_catalog_info", "yawb_sum_weights", "yawb_count",
     "yawb_host_alloc", "yawb_host_free", "yawb_sync", "yawb_version", "yawb_device_sms",
-    "yawb_timer_start", "yawb_timer_stop", "yawb_assign_patches", "yawb_upload_catalog_u8",
+    "yawb_timer_start", "yawb_timer_stop", "yawb_assign_patches", "yawb_upload_catalog_u8", "yawb_count2",
 )
 
 
@@ -91,6 +92,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.yawb_count.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_uint32,
         c_void_p, c_void_p, POINTER(YawbStats),
+    ]
+    lib.yawb_count2.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_uint32,
+        c_void_p, c_void_p, c_void_p, c_void_p, POINTER(YawbStats),
     ]
     for name in EXPORTS:
         if name not in ("yawb_last_error",):

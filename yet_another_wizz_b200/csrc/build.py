@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ["yawb_api.cu", "yawb_alloc.cu", "yawb_index.cu", "yawb_count.cu"]
 HEADERS = ["yawb_internal.cuh", "yawb_count_stream.cuh", os.path.join(ROOT, "include", "yawb.h")]
-OUT = os.path.join(HERE, "libyawb.so")
+OUT = os.environ.get("YAWB_BUILD_OUT") or os.path.join(HERE, "libyawb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -163,6 +163,52 @@ class Engine:
         )
         return out_i, out_f, stats.as_dict()
 
+    def count2(
+        self,
+        cat1a: DeviceCatalog,
+        cat1b: DeviceCatalog,
+        cat2: DeviceCatalog,
+        pair_i: np.ndarray,
+        pair_j: np.ndarray,
+        r2_edges: np.ndarray,
+        *,
+        out_device: tuple[int, int, int, int] | None = None,
+    ) -> tuple[tuple[np.ndarray, np.ndarray], tuple[np.ndarray, np.ndarray], dict]:
+        """`count(cat1a, cat2)` and `count(cat1b, cat2)` in one pass over a fused index of the two first
+        catalogs (`yawb_count2`): returns `((counts_a, sums_a), (counts_b, sums_b), stats)`.
+
+        `out_device = (sums_a, counts_a, sums_b, counts_b)`: raw device pointers (0 = not wanted) of
+        caller-owned buffers shaped `(n_pairs, n_bins, n_edges - 1)`; the results stay on the device
+        (`YAWB_FLAG_OUT_DEVICE`, e.g. for an NCCL reduce) and the arrays returned are `None`."""
+        pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+        r2_edges = np.ascontiguousarray(r2_edges, dtype=np.float64)
+        n_bins = cat1a.n_bins
+        if r2_edges.ndim == 1:
+            r2_edges = np.ascontiguousarray(np.broadcast_to(r2_edges, (n_bins, len(r2_edges))))
+        if r2_edges.shape[0] != n_bins:
+            raise ValueError(f"r2_edges must have shape (n_bins={n_bins}, n_edges)")
+        n_edges = r2_edges.shape[1]
+        shape = (len(pair_i), n_bins, n_edges - 1)
+        stats = _lib.YawbStats()
+        if out_device is not None:
+            ptrs = [c_void_p(p) if p else None for p in out_device]
+            _lib.check(
+                self.lib.yawb_count2(
+                    self._h, cat1a._h, cat1b._h, cat2._h, _ptr(pair_i), _ptr(pair_j), len(pair_i), _ptr(r2_edges), n_edges,
+                    _lib.FLAG_OUT_DEVICE, *ptrs, byref(stats),
+                )
+            )
+            return (None, None), (None, None), stats.as_dict()
+        out = [(np.zeros(shape, dtype=np.int64), np.zeros(shape, dtype=np.float64)) for _ in range(2)]
+        _lib.check(
+            self.lib.yawb_count2(
+                self._h, cat1a._h, cat1b._h, cat2._h, _ptr(pair_i), _ptr(pair_j), len(pair_i), _ptr(r2_edges), n_edges, 0,
+                _ptr(out[0][1]), _ptr(out[0][0]), _ptr(out[1][1]), _ptr(out[1][0]), byref(stats),
+            )
+        )
+        return out[0], out[1], stats.as_dict()
+
     def count_into_device(self, cat1, cat2, pair_i, pair_j, r2_edges, out_f64_ptr: int, out_i64_ptr: int):
         """Variant writing into caller-owned device buffers (raw pointers)."""
         pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)

@@ -365,22 +365,36 @@ class PatchLinkage:
             sw1_all = (uploads.get(main_catalog, binning) if kappa1 else dev1).sum_weights()
             sw2_all = (uploads.get(second, bins2) if kappa2 else dev2).sum_weights()
 
-            own = np.arange(len(pair_i))
-            if shard.active:
-                costs = pair_costs(pair_i, pair_j, main_catalog.get_num_records(), second.get_num_records())
-                own = assign_pairs_lpt(costs, shard.world_size)[shard.rank]
+            own = self._own_pairs(shard, pair_i, pair_j, main_catalog, second)
             hist_i, hist_f, stats = engine.count(dev1, dev2, pair_i[own], pair_j[own], plan.r2)
-            weighted = dev1.weighted or dev2.weighted
-            hist = hist_f if weighted else hist_i
-            if shard.active:
-                full = np.zeros((len(pair_i), *hist.shape[1:]), dtype=hist.dtype)
-                full[own] = hist
-                hist = shard.reduce_to_root(full)
+            hist = hist_f if (dev1.weighted or dev2.weighted) else hist_i
+            hist = self._gather_shards(shard, hist, own, len(pair_i))
             _last_stats[count_type_info or ("auto" if auto else "cross")] = stats
         finally:
             if self._uploads is None:
                 uploads.free()
+        return self._package(hist, plan, binning, num_patches, pair_i, pair_j, sw1_all, sw2_all, auto)
 
+    @staticmethod
+    def _own_pairs(shard, pair_i, pair_j, cat1, cat2) -> np.ndarray:
+        """patch pairs counted by this rank (all of them without sharding)"""
+        if not shard.active:
+            return np.arange(len(pair_i))
+        costs = pair_costs(pair_i, pair_j, cat1.get_num_records(), cat2.get_num_records())
+        return assign_pairs_lpt(costs, shard.world_size)[shard.rank]
+
+    @staticmethod
+    def _gather_shards(shard, hist: np.ndarray, own: np.ndarray, n_pairs: int) -> np.ndarray:
+        if not shard.active:
+            return hist
+        full = np.zeros((n_pairs, *hist.shape[1:]), dtype=hist.dtype)
+        full[own] = hist
+        return shard.reduce_to_root(full)
+
+    @staticmethod
+    def _package(hist, plan, binning, num_patches, pair_i, pair_j, sw1_all, sw2_all, auto) -> list[NormalisedCounts]:
+        """sub-bin histograms of the patch pairs -> one `NormalisedCounts` per scale (`measurements.py:354-367`)"""
+        num_bins = len(binning)
         counts = plan.finish(hist)  # (n_scales, n_pairs, n_bins)
         sum_weights1 = np.zeros((num_bins, num_patches))
         sum_weights2 = np.zeros((num_bins, num_patches))
@@ -400,6 +414,36 @@ class PatchLinkage:
             patched.counts[:, pair_i, pair_j] = vals.T
             result.append(NormalisedCounts(patched, sum_weights))
         return result
+
+    def count_pairs_fused(self, main_a, main_b, second, *, count_type_info: tuple[str, str] = ("DD", "RD")
+                          ) -> tuple[list[NormalisedCounts], list[NormalisedCounts]]:
+        """`count_pairs(main_a, second)` and `count_pairs(main_b, second)` of a cross-correlation in ONE pass of
+        the engine (`yawb_count2`: the two z-binned catalogs share one sky-cell index, every register tile of
+        the unbinned `second` catalog is set up once).  Same results as the two separate calls."""
+        logger.info("counting %s and %s from patch pairs", *count_type_info)
+        engine = self.engine or get_default_engine()
+        shard = self.shard or current_shard()
+        uploads = self._uploads or _Uploads(engine)
+        binning = _as_binning(self.config)
+        num_patches = len(main_a)
+        plan = self._get_plan()
+        pair_i, pair_j = self.get_patch_id_pairs(auto=False)
+        try:
+            dev_a, dev_b = uploads.get(main_a, binning), uploads.get(main_b, binning)
+            dev2 = uploads.get(second, None)
+            sw_a, sw_b, sw2 = dev_a.sum_weights(), dev_b.sum_weights(), dev2.sum_weights()
+            larger = main_a if sum(main_a.get_num_records()) >= sum(main_b.get_num_records()) else main_b
+            own = self._own_pairs(shard, pair_i, pair_j, larger, second)
+            (ia, fa), (ib, fb), stats = engine.count2(dev_a, dev_b, dev2, pair_i[own], pair_j[own], plan.r2)
+            weighted = dev_a.weighted or dev_b.weighted or dev2.weighted
+            hist_a = self._gather_shards(shard, fa if weighted else ia, own, len(pair_i))
+            hist_b = self._gather_shards(shard, fb if weighted else ib, own, len(pair_i))
+            _last_stats["+".join(count_type_info)] = stats
+        finally:
+            if self._uploads is None:
+                uploads.free()
+        return (self._package(hist_a, plan, binning, num_patches, pair_i, pair_j, sw_a, sw2, False),
+                self._package(hist_b, plan, binning, num_patches, pair_i, pair_j, sw_b, sw2, False))
 
     def count_pairs_optional(self, main_catalog, *optional_catalog, **kwargs):
         if any(cat is None for cat in (main_catalog, *optional_catalog)):
@@ -487,10 +531,21 @@ def crosscorrelate(config, reference, unknown, *, ref_rand=None, unk_rand=None, 
         # `pipeline.count_cross_pipelined`)
         binning = _as_binning(config)
         links._uploads.enqueue(((reference, binning), (unknown, None), (ref_rand, binning), (unk_rand, None)))
-        DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
-        RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
-        DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
-        RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
+        # the reference sample and its randoms share patches, z-bins and thresholds: counted together against
+        # each unbinned catalog (one pass instead of two) unless only one of them carries weights
+        fuse = (ref_rand is not None and bool(reference.has_weights) == bool(ref_rand.has_weights)
+                and hasattr(links.engine or get_default_engine(), "count2") and os.environ.get("YAWB_FUSE", "1") != "0")
+        if fuse:
+            DD, RD = links.count_pairs_fused(reference, ref_rand, unknown, count_type_info=("DD", "RD"))
+            if unk_rand is not None:
+                DR, RR = links.count_pairs_fused(reference, ref_rand, unk_rand, count_type_info=("DR", "RR"))
+            else:
+                DR = RR = [None for _ in range(config.scales.num_scales)]
+        else:
+            DD = links.count_pairs(reference, unknown, count_type_info="DD", **kw)
+            RD = links.count_pairs_optional(ref_rand, unknown, count_type_info="RD", **kw)
+            DR = links.count_pairs_optional(reference, unk_rand, count_type_info="DR", **kw)
+            RR = links.count_pairs_optional(ref_rand, unk_rand, count_type_info="RR", **kw)
     finally:
         links._uploads.free()
         links._uploads = None

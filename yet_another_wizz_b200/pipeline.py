@@ -70,12 +70,17 @@ def upload_patch_slices(engine, arrays: dict, n_groups: int) -> list[tuple[objec
 
 
 def count_cross_pipelined(engine, host: dict, pair_i: np.ndarray, pair_j: np.ndarray, r2: np.ndarray, *,
-                          groups: int = 4):
+                          groups: int = 4, fuse: bool = True):
     """DD / DR / RD / RR (as far as the catalogs in `host` allow) between the patches listed in
     `(pair_i, pair_j)`.  `host[name]` = upload arguments of catalog `name` in ("ref", "ref_rand", "unk",
     "unk_rand") or None.  Returns `(counts_i64, sums_f64, stats, devices)`: per count type the
     `(n_pairs, n_bins, n_sub)` arrays, the merged kernel statistics, and the device catalogs (whole
-    first-role catalogs and the slices of the second-role ones) for the caller to query and free."""
+    first-role catalogs and the slices of the second-role ones) for the caller to query and free.
+
+    With `fuse` (default) and two first-role catalogs of the same kind (both weighted or both unweighted) the
+    reference sample and its randoms are counted against each second-role catalog in ONE pass
+    (`Engine.count2`: DD + RD, then DR + RR); the statistics of such a pass are reported under the joined tag,
+    e.g. `stats["DD+RD"]`."""
     pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
     pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
     def rows(k):
@@ -86,10 +91,14 @@ def count_cross_pipelined(engine, host: dict, pair_i: np.ndarray, pair_j: np.nda
     # time it arrives; what is left then is its index and the counts against it
     first = sorted((k for k in ("ref", "ref_rand") if host.get(k) is not None), key=rows)
     second = sorted((k for k in ("unk", "unk_rand") if host.get(k) is not None), key=rows)
-    order = []  # upload order: F0, S0, F1, S1
-    for f, s2 in zip(first, second):
-        order += [f, s2]
-    order += first[len(second):] + second[len(first):]
+    fused = fuse and len(first) == 2 and (host[first[0]].get("weights") is None) == (host[first[1]].get("weights") is None)
+    if fused:  # both first-role catalogs are needed by the first count: F0, F1, S0, S1
+        order = first + second
+    else:  # upload order: F0, S0, F1, S1
+        order = []
+        for f, s2 in zip(first, second):
+            order += [f, s2]
+        order += first[len(second):] + second[len(first):]
 
     # enqueue every copy up front
     devices: dict[str, list] = {}
@@ -107,21 +116,47 @@ def count_cross_pipelined(engine, host: dict, pair_i: np.ndarray, pair_j: np.nda
     n_bins = max(host[k].get("n_bins", 1) for k in first) if first else 1
     shape = (len(pair_i), n_bins, r2.shape[1] - 1)
     counts, sums, stats = {}, {}, {}
+    def tag_of(k1, k2):
+        return next(t for t, (a, b) in COUNT_TYPES.items() if (a, b) == (k1, k2))
+
+    def ensure(tag):
+        if tag not in counts:
+            counts[tag] = np.zeros(shape, dtype=np.int64)
+            sums[tag] = np.zeros(shape, dtype=np.float64)
+
+    def add_stats(tag, st):
+        acc = stats.setdefault(tag, {})
+        for key, val in st.items():
+            acc[key] = acc.get(key, 0) + val
+
+    if fused:
+        # one pass per second-role slice: (F0, F1) x S, in arrival order of the slices
+        for k2 in second:
+            tags = [tag_of(k1, k2) for k1 in first]
+            for n, (dev2, lo, hi) in enumerate(devices[k2]):
+                for tag in tags:
+                    ensure(tag)
+                sel = np.flatnonzero((pair_j >= lo) & (pair_j < hi))
+                if len(sel) == 0:
+                    continue
+                (ia, fa), (ib, fb), st = engine.count2(devices[first[0]][0][0], devices[first[1]][0][0], dev2,
+                                                       pair_i[sel], pair_j[sel], r2)
+                counts[tags[0]][sel], sums[tags[0]][sel] = ia, fa
+                counts[tags[1]][sel], sums[tags[1]][sel] = ib, fb
+                add_stats("+".join(tags), st)
+        return counts, sums, stats, devices
     # counts in the order in which their inputs are complete
     jobs = sorted(((max(arrival[(k1, 0)], arrival[(k2, n)]), arrival[(k2, n)], k1, k2, n)
                    for k1 in first for k2 in second for n in range(len(devices[k2]))))
     for _, _, k1, k2, n in jobs:
-        tag = next(t for t, (a, b) in COUNT_TYPES.items() if (a, b) == (k1, k2))
-        if tag not in counts:
-            counts[tag] = np.zeros(shape, dtype=np.int64)
-            sums[tag] = np.zeros(shape, dtype=np.float64)
-            stats[tag] = {}
+        tag = tag_of(k1, k2)
+        ensure(tag)
+        stats.setdefault(tag, {})
         dev2, lo, hi = devices[k2][n]
         sel = np.flatnonzero((pair_j >= lo) & (pair_j < hi))
         if len(sel) == 0:
             continue
         ci, cf, st = engine.count(devices[k1][0][0], dev2, pair_i[sel], pair_j[sel], r2)
         counts[tag][sel], sums[tag][sel] = ci, cf
-        for key, val in st.items():
-            stats[tag][key] = stats[tag].get(key, 0) + val
+        add_stats(tag, st)
     return counts, sums, stats, devices
