@@ -64,6 +64,7 @@ struct FastParams {
     int lg_cells;
     int acc_global;               // general sub-bin path: segment histograms go straight to global atomics
     const BinPar *binpar;
+    double rmax_all;              // largest search radius over the z-bins
     unsigned long long *out_cnt;  // [n_types][n_pairs][n_bins][n_edges - 1]
     double *out_w;
     size_t type_stride;           // n_pairs * n_bins * (n_edges - 1)
@@ -80,8 +81,8 @@ __device__ __forceinline__ BinRows bin_rows(const SGrid &G, double ulo, double u
     BinRows r{0, 0, 0, 0};
     if (bp.empty) return r;
     // query box = tile box grown by the search radius (sound: |du|, |dv|, |dt| <= chord)
-    const double fu0 = floor((ulo - bp.rmax - G.u0) * G.inv_c), fu1 = floor((uhi + bp.rmax - G.u0) * G.inv_c);
-    const double fv0 = floor((vlo - bp.rmax - G.v0) * G.inv_c), fv1 = floor((vhi + bp.rmax - G.v0) * G.inv_c);
+    const double fu0 = floor((ulo - bp.rmax - G.u0) * G.inv_cu), fu1 = floor((uhi + bp.rmax - G.u0) * G.inv_cu);
+    const double fv0 = floor((vlo - bp.rmax - G.v0) * G.inv_cv), fv1 = floor((vhi + bp.rmax - G.v0) * G.inv_cv);
     if (fu1 < 0.0 || fv1 < 0.0 || fu0 > (double)(G.gu - 1) || fv0 > (double)(G.gv - 1)) return r;
     r.iu0 = (int)fmax(fu0, 0.0);
     r.iu1 = (int)fmin(fu1, (double)(G.gu - 1));
@@ -248,6 +249,54 @@ __device__ __forceinline__ void test_candidate(const Cand c, double swt, const f
             }
         }
     }
+}
+
+// One candidate against ONE row pair of the lane (SAT form), for the sub-tile test loop.
+__device__ __forceinline__ void test_pair(const float2 sx, const float2 sy, const float2 sz, const float2 sw,
+                                          const float2 rxk, const float2 ryk, const float2 rzk, const float2 rnk,
+                                          float ta, float tb, float2 &acc_a, float2 &acc_b) {
+    float2 u = __fadd2_rn(rnk, sw);
+    u = __ffma2_rn(rxk, sx, u);
+    u = __ffma2_rn(ryk, sy, u);
+    u = __ffma2_rn(rzk, sz, u);
+    float2 v;
+    v.x = __saturatef(fmaf(fabsf(u.x), ta, tb));
+    v.y = __saturatef(fmaf(fabsf(u.y), ta, tb));
+    acc_a = __fadd2_rn(acc_a, v);
+    acc_b = __ffma2_rn(v, v, acc_b);
+}
+
+// Sub-tile form of one candidate: its 4-bit mask (warp-uniform, staged with the candidate in place of the
+// duplicate of -2z) names the row pairs (64-row sub-tiles of the Hilbert-ordered tile) it can reach; the others
+// are skipped by a branch, not by predication.
+__device__ __forceinline__ void test_candidate_sub(const Cand c, const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                                   const float2 (&rz)[HPL], const float2 (&rn)[HPL], float ta, float tb,
+                                                   float2 &acc_a, float2 &acc_b) {
+    const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
+    const float2 sz = make_float2(c.b.x, c.b.x), sw = make_float2(c.b.z, c.b.w);
+    const unsigned mask = __float_as_uint(c.b.y);
+#define YAWB_T(k) test_pair(sx, sy, sz, sw, rx[k], ry[k], rz[k], rn[k], ta, tb, acc_a, acc_b)
+    if constexpr (HPL == 4) {
+        switch (mask) {
+            case 1: YAWB_T(0); break;
+            case 2: YAWB_T(1); break;
+            case 3: YAWB_T(0); YAWB_T(1); break;
+            case 4: YAWB_T(2); break;
+            case 5: YAWB_T(0); YAWB_T(2); break;
+            case 6: YAWB_T(1); YAWB_T(2); break;
+            case 7: YAWB_T(0); YAWB_T(1); YAWB_T(2); break;
+            case 8: YAWB_T(3); break;
+            case 9: YAWB_T(0); YAWB_T(3); break;
+            case 10: YAWB_T(1); YAWB_T(3); break;
+            case 11: YAWB_T(0); YAWB_T(1); YAWB_T(3); break;
+            case 12: YAWB_T(2); YAWB_T(3); break;
+            case 13: YAWB_T(0); YAWB_T(2); YAWB_T(3); break;
+            case 14: YAWB_T(1); YAWB_T(2); YAWB_T(3); break;
+            case 15: YAWB_T(0); YAWB_T(1); YAWB_T(2); YAWB_T(3); break;
+            default: break;
+        }
+    }
+#undef YAWB_T
 }
 
 // entries [ea, eb) of the list belong to one z-bin
@@ -706,7 +755,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
     P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
     P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
-    P.r2 = a.d_r2; P.r2f = a.d_r2f; P.binpar = a.d_binpar;
+    P.r2 = a.d_r2; P.r2f = a.d_r2f; P.binpar = a.d_binpar; P.rmax_all = a.rmax_all;
     P.lg_cells = a.n_edges > 2 ? 2 * a.n_edges : 0;
     P.lgpar = a.d_r2f + (size_t)a.n_bins * a.n_edges;
     P.lgT = reinterpret_cast<const unsigned short *>(P.lgpar + 2 * (size_t)a.n_bins);

@@ -28,7 +28,11 @@ constexpr int kThreads = 256;
 #define YAWB_TARGET_PER_CELL 5.5
 #endif
 constexpr double kTargetPerCell = YAWB_TARGET_PER_CELL;  // rows per sky cell and z-bin the grid is sized for
-constexpr long long kMaxCellsPerPatchBin = 1ll << 22;
+constexpr long long kMaxCellsPerPatchBin = 1ll << 24;
+#ifndef YAWB_CELL_ASPECT
+#define YAWB_CELL_ASPECT 4.0
+#endif
+constexpr double kCellAspect = YAWB_CELL_ASPECT;  // cell height / cell width
 
 inline int blocks_for(int64_t n, int per_block = kThreads) {
     return (int)std::min<int64_t>((n + per_block - 1) / per_block, 1 << 30);
@@ -322,8 +326,8 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
     local_uv(frames[p], x[i], y[i], z[i], u, v);
     const SGrid g = grids[p];
     // clamp in double first: the product can exceed the int range for degenerate patches
-    int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_c), 0.0), (double)(g.gu - 1));
-    int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_c), 0.0), (double)(g.gv - 1));
+    int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_cu), 0.0), (double)(g.gu - 1));
+    int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_cv), 0.0), (double)(g.gv - 1));
     keys[i] = (K)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
 }
 
@@ -821,20 +825,26 @@ static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
         double du = std::max(f.umax - f.umin, 0.0), dv = std::max(f.vmax - f.vmin, 0.0);
         double per_bin = std::max((double)np / B, 1.0);
         double area = std::max(du * dv, 1e-30);
+        // cells of height c (the spacing of the cell rows, sized for kTargetPerCell rows of one z-bin per c x c
+        // square) and width c / kCellAspect: a query is one contiguous run of rows per cell row, so narrow cells
+        // trim the run to the query box at no cost in the number of runs
         double c = std::sqrt(kTargetPerCell * area / per_bin);
         double span = std::max(du, dv);
         if (!(c > 0.0) || span <= 0.0) c = 1.0;
-        c = std::max(c, span / 2048.0);  // bound the grid, <= 2048 x 2048 cells
+        c = std::max(c, span / 2048.0);  // bound the grid, <= 8192 x 2048 cells
         SGrid &g = fi->h_sgrid[p];
         g.u0 = f.umin;
         g.v0 = f.vmin;
-        g.inv_c = 1.0 / c;
-        g.gu = std::max(1, (int)std::floor(du / c) + 1);
-        g.gv = std::max(1, (int)std::floor(dv / c) + 1);
-        while ((long long)g.gu * g.gv > kMaxCellsPerPatchBin) {  // defensive; unreachable with the bound above
-            c *= 2.0; g.inv_c = 1.0 / c;
-            g.gu = std::max(1, (int)std::floor(du / c) + 1);
-            g.gv = std::max(1, (int)std::floor(dv / c) + 1);
+        auto dims = [&]() {
+            g.inv_cv = 1.0 / c;
+            g.inv_cu = kCellAspect / c;
+            g.gu = std::max(1, (int)std::floor(du * g.inv_cu) + 1);
+            g.gv = std::max(1, (int)std::floor(dv * g.inv_cv) + 1);
+        };
+        dims();
+        while ((long long)g.gu * g.gv > kMaxCellsPerPatchBin || g.gu > 32767) {
+            c *= 1.5;
+            dims();
         }
         g.cell_base = base;
         base += (long long)B * g.gu * g.gv;

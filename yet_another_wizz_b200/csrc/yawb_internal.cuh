@@ -47,7 +47,8 @@ struct PatchFrame {
 // 0.5001 / qscale (a few 1e-11 for a 5-degree patch: finer than the float rounding of a tile-local
 // vector), and the exact doubles stay available for the FP64 recheck.
 struct SGrid {
-    double u0, v0, inv_c;  // cell (iu, iv) covers u0 + iu/inv_c ...
+    double u0, v0;         // cell (iu, iv) covers u0 + iu / inv_cu ..., v0 + iv / inv_cv ...
+    double inv_cu, inv_cv; // cells are narrower along u, the direction of the contiguous runs (YAWB_CELL_ASPECT)
     int gu, gv;            // cells per row / number of rows
     long long cell_base;   // global cell id of (bin 0, iv 0, iu 0); bin stride = gu * gv
     double t0;             // origin of the third coordinate (t = (P - c).c <= 0)
