@@ -9,7 +9,7 @@ import json, sys
 name = sys.argv[1]
 try:
     d = json.load(open(f"gpurun_out/sweep_{name}.json"))
-    pc = d["breakdown_ms"]["per_count"]
+    pc = d["breakdown_ms"]["per_launch"]
     print(name, "step %.2f" % d["ms_per_step"], "kernels %.2f" % d["breakdown_ms"]["count_kernels"], {k: round(v, 3) for k, v in pc.items()},
           "frac %.3f" % d["roofline"]["frac"], "e2e %.1f" % d["e2e"]["ms_per_step"])
 except Exception as e:

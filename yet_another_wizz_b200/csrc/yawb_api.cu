@@ -153,6 +153,8 @@ int yawb_create(int device, yawb_ctx **out) {
     YAWB_CUDA(cudaEventCreate(&ctx->ev1));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_i0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_i1));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_f0));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_f1));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_t1));
     YAWB_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
@@ -178,6 +180,8 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_i0);
     cudaEventDestroy(ctx->ev_i1);
+    cudaEventDestroy(ctx->ev_f0);
+    cudaEventDestroy(ctx->ev_f1);
     cudaEventDestroy(ctx->ev_t0);
     cudaEventDestroy(ctx->ev_t1);
     cudaStreamDestroy(ctx->stream);
@@ -357,24 +361,18 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     if (cat1b && yawb_cat_finalize(cat1b)) return 1;
     float t_idx = 0.f;
     FIndex *fi = nullptr;
+    bool first_built = false;
     {
         const bool need = cat1b ? true : cat1->findex == nullptr;
-        bool built = false;
-        if (need) YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
+        if (need) YAWB_CUDA(cudaEventRecord(ctx->ev_f0, st));
         if (cat1b) {
-            if (yawb_findex_get_fused(ctx, cat1, cat1b, &fi, &built)) return 1;
+            if (yawb_findex_get_fused(ctx, cat1, cat1b, &fi, &first_built)) return 1;
         } else {
             if (yawb_index_build_first(cat1)) return 1;
             fi = cat1->findex;
-            built = need;
+            first_built = need;
         }
-        if (built) {
-            float t = 0.f;
-            YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
-            YAWB_CUDA(cudaEventSynchronize(ctx->ev_i1));
-            YAWB_CUDA(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
-            t_idx += t;
-        }
+        if (first_built) YAWB_CUDA(cudaEventRecord(ctx->ev_f1, st));  // read after the final synchronisation
     }
     if (yawb_cat_finalize(cat2)) return 1;
     const bool second_built = !cat2->has_rtiles;
@@ -522,6 +520,9 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
 
     int launches = 0;
     unsigned long long h_counters[8] = {0};
+    const cudaMemcpyKind kind = (flags & YAWB_FLAG_OUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    double *d_tmp = nullptr;
+    if (!weighted && !(flags & YAWB_FLAG_OUT_DEVICE) && n_out && (out_f64[0] || out_f64[1])) DALLOC(d_tmp, n_out * sizeof(double));
     for (int attempt = 0;; ++attempt) {
         TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
         if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
@@ -529,45 +530,49 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         TRY(cudaEventRecord(ctx->ev0, st));
         int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
                                                       : yawb_launch_count_fast(ctx, a, &launches);
-        if (rc) { cleanup(); return rc; }
+        if (rc) { cleanup(); if (d_tmp) yawb_dfree(ctx, d_tmp, st); return rc; }
         TRY(cudaEventRecord(ctx->ev1, st));
         TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+        // the results travel right behind the counters (ONE synchronisation per call); should a work-item list have
+        // been too small -- the host only learns that now -- the count is repeated with the exact sizes
+        for (int t = 0; t < n_types && n_out1; ++t) {
+            if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), kind, st));
+            if (out_f64[t]) {
+                if (weighted) {
+                    TRY(cudaMemcpyAsync(out_f64[t], d_w + t * n_out1, n_out1 * sizeof(double), kind, st));
+                } else if (flags & YAWB_FLAG_OUT_DEVICE) {
+                    k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, out_f64[t], (long long)n_out1);
+                    launches += 1;
+                } else {
+                    k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, d_tmp + t * n_out1, (long long)n_out1);
+                    launches += 1;
+                    TRY(cudaMemcpyAsync(out_f64[t], d_tmp + t * n_out1, n_out1 * sizeof(double), kind, st));
+                }
+            }
+        }
         TRY(cudaStreamSynchronize(st));
         if (!h_counters[6]) break;
-        YAWB_REQUIRE(attempt == 0, "work-item lists overflowed twice (%llu + %llu items)", h_counters[4], h_counters[5]);
+        if (attempt > 0) {
+            yawb_set_error("work-item lists overflowed twice (%llu + %llu items)", h_counters[4], h_counters[5]);
+            cleanup();
+            if (d_tmp) yawb_dfree(ctx, d_tmp, st);
+            return 2;
+        }
         a.cap_heavy = (long long)h_counters[4] + 1024;
         a.cap_light = (long long)h_counters[5] + 1024;
     }
-
-    // results
-    const cudaMemcpyKind kind = (flags & YAWB_FLAG_OUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    double *d_tmp = nullptr;
-    for (int t = 0; t < n_types && n_out1; ++t) {
-        if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), kind, st));
-        if (out_f64[t]) {
-            if (weighted) {
-                TRY(cudaMemcpyAsync(out_f64[t], d_w + t * n_out1, n_out1 * sizeof(double), kind, st));
-            } else if (flags & YAWB_FLAG_OUT_DEVICE) {
-                k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, out_f64[t], (long long)n_out1);
-                launches += 1;
-            } else {
-                if (!d_tmp) DALLOC(d_tmp, n_out * sizeof(double));
-                k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, d_tmp + t * n_out1, (long long)n_out1);
-                launches += 1;
-                cudaError_t e = cudaMemcpyAsync(out_f64[t], d_tmp + t * n_out1, n_out1 * sizeof(double), kind, st);
-                if (e != cudaSuccess) yawb_dfree(ctx, d_tmp, st);
-                TRY(e);
-            }
-        }
-    }
     if (d_tmp) yawb_dfree(ctx, d_tmp, st);
-    TRY(cudaStreamSynchronize(st));
     TRY(cudaGetLastError());
     float t_k = 0.f;
     TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));
     if (second_built) {
         float t = 0.f;
         TRY(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
+        t_idx += t;
+    }
+    if (first_built) {
+        float t = 0.f;
+        TRY(cudaEventElapsedTime(&t, ctx->ev_f0, ctx->ev_f1));
         t_idx += t;
     }
     s.index_ms = t_idx;

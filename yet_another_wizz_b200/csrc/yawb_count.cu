@@ -251,54 +251,6 @@ __device__ __forceinline__ void test_candidate(const Cand c, double swt, const f
     }
 }
 
-// One candidate against ONE row pair of the lane (SAT form), for the sub-tile test loop.
-__device__ __forceinline__ void test_pair(const float2 sx, const float2 sy, const float2 sz, const float2 sw,
-                                          const float2 rxk, const float2 ryk, const float2 rzk, const float2 rnk,
-                                          float ta, float tb, float2 &acc_a, float2 &acc_b) {
-    float2 u = __fadd2_rn(rnk, sw);
-    u = __ffma2_rn(rxk, sx, u);
-    u = __ffma2_rn(ryk, sy, u);
-    u = __ffma2_rn(rzk, sz, u);
-    float2 v;
-    v.x = __saturatef(fmaf(fabsf(u.x), ta, tb));
-    v.y = __saturatef(fmaf(fabsf(u.y), ta, tb));
-    acc_a = __fadd2_rn(acc_a, v);
-    acc_b = __ffma2_rn(v, v, acc_b);
-}
-
-// Sub-tile form of one candidate: its 4-bit mask (warp-uniform, staged with the candidate in place of the
-// duplicate of -2z) names the row pairs (64-row sub-tiles of the Hilbert-ordered tile) it can reach; the others
-// are skipped by a branch, not by predication.
-__device__ __forceinline__ void test_candidate_sub(const Cand c, const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                                   const float2 (&rz)[HPL], const float2 (&rn)[HPL], float ta, float tb,
-                                                   float2 &acc_a, float2 &acc_b) {
-    const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
-    const float2 sz = make_float2(c.b.x, c.b.x), sw = make_float2(c.b.z, c.b.w);
-    const unsigned mask = __float_as_uint(c.b.y);
-#define YAWB_T(k) test_pair(sx, sy, sz, sw, rx[k], ry[k], rz[k], rn[k], ta, tb, acc_a, acc_b)
-    if constexpr (HPL == 4) {
-        switch (mask) {
-            case 1: YAWB_T(0); break;
-            case 2: YAWB_T(1); break;
-            case 3: YAWB_T(0); YAWB_T(1); break;
-            case 4: YAWB_T(2); break;
-            case 5: YAWB_T(0); YAWB_T(2); break;
-            case 6: YAWB_T(1); YAWB_T(2); break;
-            case 7: YAWB_T(0); YAWB_T(1); YAWB_T(2); break;
-            case 8: YAWB_T(3); break;
-            case 9: YAWB_T(0); YAWB_T(3); break;
-            case 10: YAWB_T(1); YAWB_T(3); break;
-            case 11: YAWB_T(0); YAWB_T(1); YAWB_T(3); break;
-            case 12: YAWB_T(2); YAWB_T(3); break;
-            case 13: YAWB_T(0); YAWB_T(2); YAWB_T(3); break;
-            case 14: YAWB_T(1); YAWB_T(2); YAWB_T(3); break;
-            case 15: YAWB_T(0); YAWB_T(1); YAWB_T(2); YAWB_T(3); break;
-            default: break;
-        }
-    }
-#undef YAWB_T
-}
-
 // entries [ea, eb) of the list belong to one z-bin
 template <bool WEIGHTED, bool SAT>
 __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,

@@ -23,10 +23,6 @@
 #ifndef YAWB_LB
 #define YAWB_LB 192
 #endif
-#ifndef YAWB_SUBTILE
-#define YAWB_SUBTILE 0  // per-candidate sub-tile switch in k_count_stream: measured SLOWER (4.5 vs 3.5 ms per fused C3
-                        // launch: the dispatch serialises the warp); sub-tile culling lives in k_count_flip instead
-#endif
 #ifndef YAWB_STREAM_WARPS
 #define YAWB_STREAM_WARPS 4
 #endif
@@ -77,8 +73,6 @@ struct StreamSmem {
     SegDesc *seg;              // [n_types * n_bins]
     float4 *binrec;            // [n_bins] half extents of the query box (x, y, z) and mid
     float2 *binthr;            // [n_bins] thresholds of the pair test
-    float *binr;               // [n_bins] search radius of the z-bin, rounded up (sub-tile culling)
-    float4 *subbox;            // [2 * HPL] boxes of the 64-row sub-tiles: (cx, cy, cz, hx), (hy, hz, -, -)
     unsigned long long *acc;   // [n_types][n_bins * nsub]
     double *accw;              // same (WEIGHTED)
     unsigned *hist;            // [nsub] (MULTI)
@@ -120,8 +114,6 @@ __host__ __device__ inline size_t stream_carve(StreamSmem<WEIGHTED> *S, unsigned
     p = take((size_t)n_types * n_bins * sizeof(SegDesc)); if (S) S->seg = (SegDesc *)p;
     p = take(n_bins * sizeof(float4)); if (S) S->binrec = (float4 *)p;
     p = take(n_bins * sizeof(float2)); if (S) S->binthr = (float2 *)p;
-    p = take(n_bins * sizeof(float)); if (S) S->binr = (float *)p;
-    p = take(2 * HPL * sizeof(float4)); if (S) S->subbox = (float4 *)p;
     p = take(nacc * sizeof(unsigned long long)); if (S) S->acc = (unsigned long long *)p;
     p = take(WEIGHTED ? nacc * sizeof(double) : 0); if (S) S->accw = WEIGHTED ? (double *)p : nullptr;
     p = take(multi ? nsub * sizeof(unsigned) : 0); if (S) S->hist = multi ? (unsigned *)p : nullptr;
@@ -319,7 +311,6 @@ __device__ __forceinline__ void stream_begin(const FastParams &P, const StreamSm
         // a displaced candidate changes d2 by at most |delta| (2 |d| + |delta|) <= 0.87 q (4 M + q) < 4 M q + q^2
         const float eps = (EPS32 * (32.0f * m2 + 8.0f * bp.mid) + 4.0f * sqrtf(m2) * 1.0001f * q + q * q) * 1.0001f;
         S.binrec[b] = make_float4(hx, hy, hz, bp.mid);
-        S.binr[b] = r;
         if (MULTI && SAT) {
             // cumulative counts per edge: v_k = sat(K (e_k - mid - u) + 1/2); the float copy of
             // e_k - mid adds at most eps32 |e_k - mid| to the error of u
@@ -341,8 +332,8 @@ __device__ __forceinline__ void stream_begin(const FastParams &P, const StreamSm
 }
 
 // ---- convert the landed raw chunk into the staged list; returns (entries of type 0, entries of type 1) ----
-template <bool WEIGHTED, bool SUBTILE>
-__device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, int slot, int cnt, int lane, unsigned &n_sub) {
+template <bool WEIGHTED>
+__device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, int slot, int cnt, int lane) {
     const ItemAux &ax = S.aux[slot];
     const int k0 = ax.ko[0], k1 = ax.ko[1], k2 = ax.ko[2];
     const float qinv = ax.qinv;
@@ -351,7 +342,7 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
         const int i = base + lane;
         bool ok = i < cnt;
         float fx = 0.f, fy = 0.f, fz = 0.f, mid = 0.f;
-        unsigned aux = 0u, mask = 0xfu;
+        unsigned aux = 0u;
         int b = 0;
         if (ok) {
             const SRec r = S.raw[i];
@@ -364,18 +355,6 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
             const float4 rec4 = S.binrec[b];
             mid = rec4.w;
             ok = fabsf(fx) <= rec4.x && fabsf(fy) <= rec4.y && fabsf(fz) <= rec4.z;
-            if (SUBTILE && ok) {
-                // which 64-row sub-tiles can hold a partner: box of the sub-tile grown by the search radius
-                // (sound for the same reason as the query box: |dx|, |dy|, |dz| <= chord)
-                const float rb = S.binr[b];
-                mask = 0u;
-#pragma unroll
-                for (int k = 0; k < HPL; ++k) {
-                    const float4 sc = S.subbox[2 * k], sh = S.subbox[2 * k + 1];
-                    if (fabsf(fx - sc.x) <= sc.w + rb && fabsf(fy - sc.y) <= sh.x + rb && fabsf(fz - sc.z) <= sh.y + rb) mask |= 1u << k;
-                }
-                ok = mask != 0u;
-            }
         }
         const bool second = (aux >> 31) != 0u;
         const unsigned m0 = __ballot_sync(FULL, ok && !second), m1 = __ballot_sync(FULL, ok && second);
@@ -385,8 +364,7 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
             const float sn = fx * fx + fy * fy + fz * fz;
             const float axx = -2.0f * fx, ayy = -2.0f * fy, azz = -2.0f * fz, aw = sn - mid;
             S.list[pos].a = make_float4(axx, axx, ayy, ayy);
-            S.list[pos].b = make_float4(azz, SUBTILE ? __uint_as_float(mask) : azz, aw, aw);
-            if (SUBTILE) n_sub += __popc(mask);  // (candidate, row pair) blocks this lane staged
+            S.list[pos].b = make_float4(azz, azz, aw, aw);
             S.lidx[pos] = (int)(aux & 0x7fffffffu);
             S.lbin[pos] = (unsigned short)b;
             if (WEIGHTED) S.lw[pos] = S.rawlw[i];
@@ -428,7 +406,6 @@ __device__ __forceinline__ int stream_segments(const StreamSmem<WEIGHTED> &S, in
 // Per z-bin segment: groups of four candidates fully unrolled plus a fall-through tail, the decided /
 // undecided check once per <= 16 candidates, the warp total of a segment added to the accumulator while the
 // next segment is already running.
-template <bool SUBTILE>
 __device__ __forceinline__ void stream_test_sat(const FastParams &P, const StreamSmem<false> &S, int n_seg,
                                                 const float2 (&rx)[HPL], const float2 (&ry)[HPL], const float2 (&rz)[HPL],
                                                 const float2 (&rn)[HPL], const Tile &tl, int lane, unsigned &n_recheck) {
@@ -449,21 +426,17 @@ __device__ __forceinline__ void stream_test_sat(const FastParams &P, const Strea
             float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
             double ws[YAWB_RPL];
             int e = c0;
-            if (SUBTILE) {
-                for (; e < c1; ++e) test_candidate_sub(S.list[e], rx, ry, rz, rn, ta, tb, acc_a, acc_b);
-            } else {
 #define YAWB_T(idx) test_candidate<false, true>(S.list[idx], 0.0, rx, ry, rz, rn, ta, tb, acc_a, acc_b, ws)
-                for (; e + 4 <= c1; e += 4) {
-                    YAWB_T(e); YAWB_T(e + 1); YAWB_T(e + 2); YAWB_T(e + 3);
-                }
-                switch (c1 - e) {
-                    case 3: YAWB_T(e + 2);
-                    case 2: YAWB_T(e + 1);
-                    case 1: YAWB_T(e);
-                    default: break;
-                }
-#undef YAWB_T
+            for (; e + 4 <= c1; e += 4) {
+                YAWB_T(e); YAWB_T(e + 1); YAWB_T(e + 2); YAWB_T(e + 3);
             }
+            switch (c1 - e) {
+                case 3: YAWB_T(e + 2);
+                case 2: YAWB_T(e + 1);
+                case 1: YAWB_T(e);
+                default: break;
+            }
+#undef YAWB_T
             const float sa = acc_a.x + acc_a.y, sb = acc_b.x + acc_b.y;
             unsigned c = (unsigned)(sa + 0.5f);
             unsigned flagged = __ballot_sync(FULL, sa != sb);
@@ -546,7 +519,6 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    constexpr bool SUBTILE = YAWB_SUBTILE && HPL == 4 && SAT && !WEIGHTED && !MULTI;  // the headline kernel
     const int nsub = P.n_edges - 1;
     const bool acc_global = MULTI && P.acc_global;
     const int nacc = acc_global ? 0 : P.n_types * P.n_bins * nsub;  // accumulators kept in shared memory
@@ -561,7 +533,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
     const long long n_heavy = min((long long)P.counters[4], P.cap_heavy);
     const long long n_live = n_heavy + min((long long)P.counters[5], P.cap_light);
     unsigned long long n_tests = 0;
-    unsigned n_recheck = 0, n_subtests = 0;
+    unsigned n_recheck = 0;
 
     // ---- prologue: two records, the plan of the first item, the index of a third ----
     long long next_idx = 0;
@@ -645,40 +617,11 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
                     if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; rn[r >> 1].y = n; }
                     else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; rn[r >> 1].x = n; }
                 }
-                if (SUBTILE) {
-                    // boxes of the row pairs (pair k = rows 64 k .. 64 k + 63 of the tile, Hilbert-contiguous): warp-wide
-                    // min / max of the rounded coordinates, padded by more than the rounding of rows and candidates
-                    const float slack = 4.0e-7f * (sqrtf(ax.eu * ax.eu + ax.ev * ax.ev + ax.et * ax.et) + (float)P.rmax_all);
-#pragma unroll
-                    for (int k = 0; k < HPL; ++k) {
-                        const bool v0 = lane + 64 * k < it.count, v1 = lane + 64 * k + 32 < it.count;
-                        const float c0x[3] = {rx[k].x, ry[k].x, rz[k].x}, c1x[3] = {rx[k].y, ry[k].y, rz[k].y};
-                        float ctr[3], hlf[3];
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            float mn = fminf(v0 ? c0x[d] : FLT_MAX, v1 ? c1x[d] : FLT_MAX);
-                            float mx = fmaxf(v0 ? c0x[d] : -FLT_MAX, v1 ? c1x[d] : -FLT_MAX);
-#pragma unroll
-                            for (int o = 16; o; o >>= 1) {
-                                mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
-                                mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
-                            }
-                            const bool any = mn <= mx;  // an empty row pair gets a box nothing can reach
-                            ctr[d] = any ? 0.5f * (mn + mx) : FAR;
-                            hlf[d] = any ? 0.5f * (mx - mn) * 1.00002f + slack : 0.f;
-                        }
-                        if (lane == 0) {
-                            S.subbox[2 * k] = make_float4(ctr[0], ctr[1], ctr[2], hlf[0]);
-                            S.subbox[2 * k + 1] = make_float4(hlf[1], hlf[2], 0.f, 0.f);
-                        }
-                    }
-                    __syncwarp();
-                }
             }
-            const int2 L = stream_convert<WEIGHTED, SUBTILE>(S, c_slot, c_cnt, lane, n_subtests);
+            const int2 L = stream_convert<WEIGHTED>(S, c_slot, c_cnt, lane);
             __syncwarp();
             n_seg = stream_segments<WEIGHTED>(S, L.x, L.y, lane);
-            if (!SUBTILE) n_tests += (unsigned long long)(L.x + L.y) * (unsigned long long)it.count;
+            n_tests += (unsigned long long)(L.x + L.y) * (unsigned long long)it.count;
         }
 
         // ---- produce: request the next raw chunk; at an item boundary advance the stages behind it ----
@@ -722,7 +665,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
         if (c_cnt >= 0) {
             if (n_seg > 0) {
                 if constexpr (!WEIGHTED && !MULTI && SAT)
-                    stream_test_sat<SUBTILE>(P, S, n_seg, rx, ry, rz, rn, tl, lane, n_recheck);
+                    stream_test_sat(P, S, n_seg, rx, ry, rz, rn, tl, lane, n_recheck);
                 else
                     stream_test_generic<WEIGHTED, MULTI, SAT>(P, S, n_seg, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair, rwt);
             }
@@ -751,7 +694,6 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
         }
         __syncwarp();
     }
-    if (SUBTILE) n_tests = 64ull * __reduce_add_sync(FULL, n_subtests);  // executed tests: 64 rows per staged block
     if (lane == 0 && n_tests) atomicAdd(&P.counters[1], n_tests);
     const unsigned rc = __reduce_add_sync(FULL, n_recheck);
     if (lane == 0 && rc) atomicAdd(&P.counters[2], (unsigned long long)rc);

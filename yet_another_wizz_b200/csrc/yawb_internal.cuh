@@ -121,7 +121,8 @@ struct yawb_ctx {
     cudaStream_t stream = nullptr;       // all kernels and result copies
     cudaStream_t copy_stream = nullptr;  // host-to-device copies of catalog uploads (overlap with kernels)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_i0 = nullptr, ev_i1 = nullptr;  // lazy index builds inside yawb_count
+    cudaEvent_t ev_i0 = nullptr, ev_i1 = nullptr;  // lazy index builds inside yawb_count (second role)
+    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;  // ... (first role)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user stopwatch
     unsigned long long *d_counters = nullptr;  // [8] work counter + statistics
     // pinned arena for the meta data of in-flight uploads (bump allocated, reset when none is pending)
