@@ -11,7 +11,8 @@ Parity status: PINNED.  The restatement is checked against
     (restated in `tests/test_oracle.py`),
   * golden vectors produced by running the unmodified reference in the build
     container (`tests/golden/make_golden.py` -> `tests/golden/*.npz`),
-  * the live reference when `/root/reference` is present (`tests/test_oracle_vs_reference.py`).
+  * the live reference when `/root/reference` is present
+    (`tests/test_vs_reference.py::test_oracle_against_live_reference`).
 
 The arithmetic that the reference delegates to scipy's compiled
 `cKDTree.count_neighbors` (scipy 1.18.1 in this image; unpinned in the

@@ -144,3 +144,47 @@ def test_medium_synthetic_vs_oracle(engine):
     assert_array_equal(corr.dd.sum_weights.sum_weights1, sw1)
     assert_array_equal(corr.dd.sum_weights.sum_weights2, sw2)
     assert counts.sum() > 1e4
+
+
+def test_resident_catalogs_across_calls():
+    """the engine keeps device catalogs and their indexes between measurement calls (the reference's tree cache,
+    `trees.py:515-526`): same numbers, no re-indexing on the second call, a rebuild when the z-binning changes"""
+    import yet_another_wizz_b200 as yb
+    from yet_another_wizz_b200 import measurements
+
+    g = golden_io.load("cross_unweighted")
+    config = golden_cases.config_from_golden(g)
+    cats = {k: golden_cases.catalog_from_golden(g, k) for k in ("ref", "unk", "ref_rand", "unk_rand")}
+    eng = yb.Engine(0, cache_catalogs=True)
+    try:
+        kw = dict(ref_rand=cats["ref_rand"], unk_rand=cats["unk_rand"], engine=eng)
+        first = yb.crosscorrelate(config, cats["ref"], cats["unk"], **kw)
+        assert sum(s["index_ms"] for s in measurements.last_stats().values()) > 0
+        assert len(eng._cat_cache) == 4
+        second = yb.crosscorrelate(config, cats["ref"], cats["unk"], **kw)
+        assert sum(s["index_ms"] for s in measurements.last_stats().values()) == 0  # nothing was rebuilt
+        golden_cases.check_corrfunc(g, "cross", second, ("dd", "dr", "rd", "rr"), exact=True)
+        for a, b in zip(first, second):
+            assert a == b
+        # another z-binning: the binned catalogs are rebuilt (their cache entries replaced), the unbinned ones are reused
+        cfg = golden_io.config_of(g)
+        edges = np.asarray(cfg["zedges"])
+        config2 = yb.Configuration.create(rmin=cfg["rmin"], rmax=cfg["rmax"], edges=edges[: len(edges) // 2 + 1], closed=cfg["closed"])
+        third = yb.crosscorrelate(config2, cats["ref"], cats["unk"], **kw)
+        assert third[0].dd.counts.num_bins == len(edges) // 2
+        assert len(eng._cat_cache) == 4
+        ref_only = yb.Engine(0, cache_catalogs=False)
+        try:
+            want = yb.crosscorrelate(config2, cats["ref"], cats["unk"], ref_rand=cats["ref_rand"], unk_rand=cats["unk_rand"], engine=ref_only)
+        finally:
+            ref_only.close()
+        for a, b in zip(third, want):
+            assert a == b
+        eng.cache_clear()
+        assert len(eng._cat_cache) == 0
+        fourth = yb.crosscorrelate(config, cats["ref"], cats["unk"], **kw)  # everything uploaded and indexed again
+        assert sum(s["index_ms"] for s in measurements.last_stats().values()) > 0
+        for a, b in zip(first, fourth):
+            assert a == b
+    finally:
+        eng.close()

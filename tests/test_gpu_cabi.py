@@ -364,3 +364,33 @@ def test_assign_patches_matches_scipy_vq(engine):
     assert a.get_num_records() == b.get_num_records()
     for pid in a.keys():
         assert_array_equal(a[pid].load_data()["ra"], b[pid].load_data()["ra"])
+
+
+def test_more_than_65535_patch_pairs(engine):
+    """a densely linked catalog of 300 patches: 90 000 patch pairs in one call (the planner runs on a flat grid, so
+    the number of pairs is not limited by a grid dimension)"""
+    rng = np.random.default_rng(5)
+    n_patch, n = 300, 6000
+    ra = rng.uniform(0.0, 0.003, n); dec = np.arcsin(rng.uniform(-0.0015, 0.0015, n))
+    patch = rng.integers(0, n_patch, n)
+    order = np.argsort(patch, kind="stable")
+    xyz = oracle.radec_to_xyz(ra, dec)[order]
+    off = np.concatenate([[0], np.cumsum(np.bincount(patch, minlength=n_patch))])
+    zbin = rng.integers(0, 2, n).astype(np.int32)[order]
+    pi, pj = np.meshgrid(np.arange(n_patch), np.arange(n_patch), indexing="ij")
+    pi, pj = pi.ravel(), pj.ravel()
+    assert len(pi) > 65535
+    r2 = np.tile(oracle.chord_sq_edges(np.array([1e-4, 8e-4])), (2, 1))
+    d1 = engine.upload_catalog(xyz, off, zbin=zbin, n_bins=2)
+    d2 = engine.upload_catalog(xyz, off)
+    fi, _, _ = engine.count(d1, d2, pi, pj, r2)
+    ei, _, _ = engine.count(d1, d2, pi, pj, r2, exact=True)
+    assert_array_equal(fi, ei)
+    # the total over all patch pairs is the single-patch count of the same rows
+    whole1 = engine.upload_catalog(xyz, np.array([0, n]), zbin=zbin, n_bins=2)
+    whole2 = engine.upload_catalog(xyz, np.array([0, n]))
+    wi, _, _ = engine.count(whole1, whole2, [0], [0], r2)
+    assert_array_equal(fi.sum(axis=0), wi[0])
+    assert wi.sum() > 10000
+    for d in (d1, d2, whole1, whole2):
+        d.free()

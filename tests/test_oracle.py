@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 from numpy.testing import assert_allclose, assert_array_equal
 
+import golden_cases
 import golden_io
 import oracle
 
@@ -198,3 +199,49 @@ def test_c_and_numpy_agree_weighted():
     assert_allclose(h_c, h_np, rtol=1e-13)
     assert_array_equal(oracle.pair_histogram(a, b, None, None, r2, use_c=False),
                        oracle.pair_histogram(a, b, None, None, r2, use_c=True))
+
+
+@pytest.mark.parametrize("name,workers", [("cross_unweighted", 1), ("cross_weighted_multiscale", 2)])
+def test_cpu_port_counts_equal_reference(name, workers):
+    """`oracle/cpu_port.py` (the CPU arm of bench.py when the reference itself is not installed: scipy cKDTree per
+    patch and z-bin + a task farm over patch pairs, trees built on the worker pool) against the per-patch-pair
+    counts the UNMODIFIED reference wrote into the golden vectors -- all four count types, serial and with a pool"""
+    import cpu_port
+    from yet_another_wizz_b200.measurements import PatchLinkage, _angles_per_bin, _as_binning, prepare_catalog_arrays
+
+    g = golden_io.load(name)
+    config = golden_cases.config_from_golden(g)
+    cats = {k: golden_cases.catalog_from_golden(g, k) for k in ("ref", "unk", "ref_rand", "unk_rand")}
+    binning = _as_binning(config)
+    arrays = {k: prepare_catalog_arrays(c, binning if k in ("ref", "ref_rand") else None) for k, c in cats.items()}
+    links = PatchLinkage.from_catalogs(config, *cats.values(), engine=object())
+    pair_i, pair_j = links.get_patch_id_pairs(auto=False)
+    pairs = [(int(i), int(j)) for i, j in zip(pair_i, pair_j)]
+    amin, amax = _angles_per_bin(config)
+    n_bins, n_patch = len(binning), len(cats["ref"])
+
+    def trees_of(key, binned):
+        a = arrays[key]
+        rows = []
+        for p in range(n_patch):
+            s, e = a["patch_off"][p], a["patch_off"][p + 1]
+            rows.append((a["xyz"][s:e], None if a["weights"] is None else a["weights"][s:e],
+                         a["zbin"][s:e].astype(np.int32) if binned else None))
+        built, _ = cpu_port.build_catalog_trees(rows, n_bins if binned else None, workers=workers)
+        return dict(enumerate(built))
+
+    trees = {k: trees_of(k, k in ("ref", "ref_rand")) for k in arrays}
+    weighted = any(a["weights"] is not None for a in arrays.values())
+    for tag, (a, b) in dict(dd=("ref", "unk"), dr=("ref", "unk_rand"), rd=("ref_rand", "unk"), rr=("ref_rand", "unk_rand")).items():
+        counts, _ = cpu_port.count_pairs(trees[a], trees[b], pairs, amin, amax, rweight=config.scales.rweight,
+                                         resolution=config.scales.resolution, workers=workers)
+        for s in range(config.scales.num_scales):
+            want = g[f"cross_{tag}_counts_s{s}"]
+            got = np.zeros_like(want)
+            for (i, j), c in counts.items():
+                got[:, i, j] = c[s]
+            if weighted:
+                assert_allclose(got, want, rtol=1e-12, atol=0)
+            else:
+                assert_array_equal(got, want)
+            assert want.sum() > 0

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from ctypes import byref, c_double, c_int64, c_void_p
 
 import numpy as np
@@ -53,9 +54,10 @@ class DeviceCatalog:
         _lib.check(self.engine.lib.yawb_drop_index(self._h))
 
     def free(self) -> None:
-        if self._h is not None:
+        # a closed engine has already released every device block of its catalogs (and its streams are gone)
+        if self._h is not None and self.engine._h is not None:
             self.engine.lib.yawb_free_catalog(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -67,8 +69,16 @@ class DeviceCatalog:
 class Engine:
     """One context on one CUDA device.  Raises if the device or library is missing."""
 
-    def __init__(self, device: int = 0, *, staging: bool | None = None):
-        """`staging=True` (or YAWB_STAGING=1): measurement calls prepare large catalogs straight into a
+    def __init__(self, device: int = 0, *, staging: bool | None = None, cache_catalogs: bool | None = None,
+                 cache_bytes: int | None = None):
+        """`cache_catalogs` (default on; YAWB_CACHE=0 turns it off): device catalogs uploaded by the measurement
+        functions stay resident, with their indexes, keyed by (catalog, z-binning) -- the counterpart of the
+        reference's on-disk tree cache (`BinnedTrees.build` skips the rebuild while the `binning` file matches,
+        `src/yaw/catalog/trees.py:515-526`).  A loop of `crosscorrelate` calls over tomographic bins then uploads and
+        indexes only the catalogs that changed.  Least recently used entries are dropped beyond `cache_bytes` of
+        device memory (default 64 GB, YAWB_CACHE_GB).
+
+        `staging=True` (or YAWB_STAGING=1): measurement calls prepare large catalogs straight into a
         cache of page-locked buffers, so their copies are asynchronous and run at full PCIe rate.  Worth it
         for loops of many calls (C3: 225 -> 118 ms per call), not for a single one: page-locking the cache
         costs ~1.5 s per GB once."""
@@ -79,6 +89,11 @@ class Engine:
         _lib.check(self.lib.yawb_create(int(device), byref(h)))
         self._h = h
         self.device = int(device)
+        self._catalogs = weakref.WeakSet()  # live device catalogs: freed before the context goes away
+        self.cache_catalogs = (os.environ.get("YAWB_CACHE", "1") != "0") if cache_catalogs is None else bool(cache_catalogs)
+        self.cache_bytes = int(float(os.environ.get("YAWB_CACHE_GB", "64")) * 2**30) if cache_bytes is None else int(cache_bytes)
+        self._cat_cache: dict = {}  # (identity, kappa) -> [signature of the binning, DeviceCatalog, bytes, weakref | None]
+        self._cat_cache_tick = 0
         self._pinned: list[c_void_p] = []
         self._stage_free: list[tuple[c_void_p, int]] = []
         self._stage_used: list[tuple[c_void_p, int]] = []
@@ -125,6 +140,7 @@ class Engine:
                             zbin is not None, weights is not None)
         # the upload is asynchronous: keep the host buffers alive as long as the handle
         cat._keepalive = (xyz, weights, zbin, patch_off)
+        self._catalogs.add(cat)
         return cat
 
     def count(
@@ -235,6 +251,62 @@ class Engine:
                                                 _ptr(out)))
         return out
 
+    # ---- resident catalogs across measurement calls -------------------------------------------------
+    @staticmethod
+    def _cache_identity(catalog):
+        path = getattr(catalog, "cache_directory", None)
+        return ("dir", str(path)) if path is not None else ("id", id(catalog))
+
+    def cache_lookup(self, catalog, signature, kappa: bool):
+        """Device catalog kept for `catalog` with this z-binning, or None.  An entry built for another binning
+        is dropped (the reference rebuilds its trees in that case, `trees.py:519-526`)."""
+        if not self.cache_catalogs:
+            return None
+        key = (self._cache_identity(catalog), bool(kappa))
+        entry = self._cat_cache.get(key)
+        if entry is None:
+            return None
+        if entry[0] != signature or entry[1]._h is None:
+            self._cache_drop(key)
+            return None
+        self._cat_cache_tick += 1
+        entry[4] = self._cat_cache_tick
+        return entry[1]
+
+    def cache_store(self, catalog, signature, kappa: bool, dev: DeviceCatalog) -> bool:
+        if not self.cache_catalogs:
+            return False
+        ident = self._cache_identity(catalog)
+        key = (ident, bool(kappa))
+        ref = None
+        if ident[0] == "id":  # an in-memory catalog: the entry lives as long as the object
+            try:
+                ref = weakref.ref(catalog, lambda _r, k=key: self._cache_drop(k))
+            except TypeError:
+                return False
+        self._cache_drop(key)
+        nbytes = max(dev.info()[1], 0) * 3  # raw rows now, the indexes built later are about twice that
+        self._cat_cache_tick += 1
+        self._cat_cache[key] = [signature, dev, nbytes, ref, self._cat_cache_tick]
+        total = sum(e[2] for e in self._cat_cache.values())
+        while total > self.cache_bytes and len(self._cat_cache) > 1:  # least recently used first, never the new one
+            victim = min((k for k in self._cat_cache if k != key), key=lambda k: self._cat_cache[k][4])
+            total -= self._cat_cache[victim][2]
+            self._cache_drop(victim)
+        return True
+
+    def _cache_drop(self, key) -> None:
+        entry = self._cat_cache.pop(key, None)
+        if entry is not None:
+            try:
+                entry[1].free()
+            except Exception:
+                pass
+
+    def cache_clear(self) -> None:
+        for key in list(self._cat_cache):
+            self._cache_drop(key)
+
     def timer_start(self) -> None:
         _lib.check(self.lib.yawb_timer_start(self._h))
 
@@ -288,6 +360,9 @@ class Engine:
 
     def close(self) -> None:
         if self._h is not None:
+            self.cache_clear()
+            for cat in list(self._catalogs):
+                cat.free()
             for ptr in self._pinned:
                 self.lib.yawb_host_free(ptr)
             self._pinned.clear()

@@ -176,6 +176,7 @@ class _Uploads:
 
     def __init__(self, engine) -> None:
         self.engine = engine
+        self._resident: set = set()  # keys whose device catalog belongs to the engine's cache (not freed here)
         self._cache: dict[tuple[int, bool, bool], object] = {}
         self._pending: dict[tuple[int, bool, bool], object] = {}
         self._pool = None
@@ -183,6 +184,29 @@ class _Uploads:
     @staticmethod
     def _key(catalog, binning, kappa):
         return (id(catalog), binning is not None, bool(kappa))
+
+    @staticmethod
+    def _signature(binning):
+        """what a resident device catalog depends on besides the catalog itself (the reference's `binning` file)"""
+        if binning is None:
+            return None
+        return (tuple(np.asarray(binning.edges, dtype=np.float64).tolist()), str(binning.closed))
+
+    def _resident_lookup(self, key, catalog, binning, kappa) -> bool:
+        lookup = getattr(self.engine, "cache_lookup", None)
+        dev = lookup(catalog, self._signature(binning), kappa) if lookup else None
+        if dev is None:
+            return False
+        self._cache[key] = dev
+        self._resident.add(key)
+        return True
+
+    def _store(self, key, catalog, binning, kappa, dev):
+        self._cache[key] = dev
+        store = getattr(self.engine, "cache_store", None)
+        if store and store(catalog, self._signature(binning), kappa, dev):
+            self._resident.add(key)
+        return dev
 
     def enqueue(self, requests) -> None:
         """`requests`: iterable of (catalog or None, binning or None[, kappa])."""
@@ -193,45 +217,55 @@ class _Uploads:
             catalog, binning, kappa = (*req, False)[:3]
             key = self._key(catalog, binning, kappa)
             if catalog is not None and key not in self._cache and key not in self._pending:
-                todo.append((key, catalog, binning, kappa))
+                if not self._resident_lookup(key, catalog, binning, kappa):
+                    todo.append((key, catalog, binning, kappa))
         if not todo:
             return
         if self._pool is None:
             self._pool = ThreadPoolExecutor(max_workers=1)
         for key, catalog, binning, kappa in todo:
-            self._pending[key] = self._pool.submit(_prepare_for, self.engine, catalog, binning, kappa)
+            self._pending[key] = (self._pool.submit(_prepare_for, self.engine, catalog, binning, kappa), catalog, binning, kappa)
         for key, *_ in todo:  # upload in order; each wait overlaps with the preparation of the next catalog
             self._resolve(key)
 
     def _resolve(self, key):
-        arrays = self._pending.pop(key).result()
-        self._cache[key] = self.engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
-        return self._cache[key]
+        fut, catalog, binning, kappa = self._pending.pop(key)
+        arrays = fut.result()
+        dev = self.engine.upload_catalog(arrays.pop("xyz"), arrays.pop("patch_off"), **arrays)
+        return self._store(key, catalog, binning, kappa, dev)
 
     def get(self, catalog, binning: Binning | None, kappa: bool = False):
         key = self._key(catalog, binning, kappa)
         if key in self._pending:
             return self._resolve(key)
-        if key not in self._cache:
-            self._cache[key] = upload_catalog(self.engine, catalog, binning, kappa=kappa)
+        if key not in self._cache and not self._resident_lookup(key, catalog, binning, kappa):
+            self._store(key, catalog, binning, kappa, upload_catalog(self.engine, catalog, binning, kappa=kappa))
         return self._cache[key]
 
     def free(self) -> None:
-        for fut in self._pending.values():
+        for fut, *_ in self._pending.values():
             fut.cancel()
         self._pending.clear()
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
-        for dev in self._cache.values():
-            dev.free()
+        for key, dev in self._cache.items():
+            if key not in self._resident:  # resident catalogs stay with the engine for the next call
+                dev.free()
         self._cache.clear()
+        self._resident.clear()
         if getattr(self.engine, "staging", False):  # every upload of this call has been consumed or dropped
             self.engine.sync()
             self.engine.staging_release()
 
 
 # ---- patch linkage ----------------------------------------------------------------------------------
+# The functions and methods from here to `PatchLinkage.get_patch_id_pairs` (`check_patch_conistency`,
+# `get_max_angle`, `PatchLinkage.from_catalogs` and its properties, `iter_patch_id_pairs`) restate the reference's
+# decisions step by step (yet_another_wizz v3.1.1, `src/yaw/correlation/measurements.py:131-168, 193-289`,
+# Copyright (C) Jan Luca van den Busch, GPL-3.0-or-later): the engine must visit exactly the reference's set of
+# patch pairs, including the order in which `set.pop()` yields them, so this block follows that code closely
+# and is covered by the same licence terms.
 def check_patch_conistency(catalog, *catalogs, rtol: float = 0.5) -> None:
     centers = AngularCoordinates(_coords_data(catalog.get_centers()))
     radii = _coords_data(catalog.get_radii())
@@ -383,13 +417,14 @@ class PatchLinkage:
         costs = pair_costs(pair_i, pair_j, cat1.get_num_records(), cat2.get_num_records())
         return assign_pairs_lpt(costs, shard.world_size)[shard.rank]
 
-    @staticmethod
-    def _gather_shards(shard, hist: np.ndarray, own: np.ndarray, n_pairs: int) -> np.ndarray:
+    def _gather_shards(self, shard, hist: np.ndarray, own: np.ndarray, n_pairs: int) -> np.ndarray:
         if not shard.active:
             return hist
         full = np.zeros((n_pairs, *hist.shape[1:]), dtype=hist.dtype)
         full[own] = hist
-        return shard.reduce_to_root(full)
+        engine = self.engine or get_default_engine()
+        device = getattr(engine, "device", None)
+        return shard.reduce_to_root(full, device=None if device is None else f"cuda:{device}")
 
     @staticmethod
     def _package(hist, plan, binning, num_patches, pair_i, pair_j, sw1_all, sw2_all, auto) -> list[NormalisedCounts]:

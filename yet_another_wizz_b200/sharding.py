@@ -88,16 +88,23 @@ class Shard:
         return self.world_size > 1
 
     def reduce_to_root(self, array: np.ndarray, device: str | None = None) -> np.ndarray:
-        """Sum-reduce `array` over ranks onto rank 0 (others get their partial back)."""
+        """Sum `array` over the ranks.  Every element has exactly one non-zero contributor, so the sum is exact.
+        The result is delivered to EVERY rank (an all-reduce: the tensors are a few hundred KB), so that
+        `crosscorrelate` / `autocorrelate` return complete counts wherever they are called.  `device`: where the
+        collective runs with the NCCL backend -- the engine's GPU (`cuda:<engine.device>`), not whatever
+        `torch.cuda.current_device()` happens to be; ignored for CPU backends (gloo in the tests)."""
         if not self.active:
             return array
         import torch
         import torch.distributed as dist
 
         backend = dist.get_backend(self.group)
-        dev = device or (f"cuda:{torch.cuda.current_device()}" if backend == "nccl" else "cpu")
+        if backend == "nccl":
+            dev = device or f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+        else:
+            dev = "cpu"
         t = torch.from_numpy(np.ascontiguousarray(array)).to(dev)
-        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
 
