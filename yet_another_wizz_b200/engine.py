@@ -254,8 +254,9 @@ class Engine:
     # ---- resident catalogs across measurement calls -------------------------------------------------
     @staticmethod
     def _cache_identity(catalog):
-        path = getattr(catalog, "cache_directory", None)
-        return ("dir", str(path)) if path is not None else ("id", id(catalog))
+        # the catalog OBJECT (an entry lives exactly as long as it does); a cache directory is only a label for
+        # this package's in-memory catalogs, and on disk it can be overwritten, so paths are not identities
+        return ("id", id(catalog))
 
     def cache_lookup(self, catalog, signature, kappa: bool):
         """Device catalog kept for `catalog` with this z-binning, or None.  An entry built for another binning
@@ -278,12 +279,10 @@ class Engine:
             return False
         ident = self._cache_identity(catalog)
         key = (ident, bool(kappa))
-        ref = None
-        if ident[0] == "id":  # an in-memory catalog: the entry lives as long as the object
-            try:
-                ref = weakref.ref(catalog, lambda _r, k=key: self._cache_drop(k))
-            except TypeError:
-                return False
+        try:
+            ref = weakref.ref(catalog, lambda _r, k=key: self._cache_drop(k))
+        except TypeError:
+            return False
         self._cache_drop(key)
         nbytes = max(dev.info()[1], 0) * 3  # raw rows now, the indexes built later are about twice that
         self._cat_cache_tick += 1

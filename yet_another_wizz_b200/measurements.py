@@ -186,15 +186,17 @@ class _Uploads:
         return (id(catalog), binning is not None, bool(kappa))
 
     @staticmethod
-    def _signature(binning):
-        """what a resident device catalog depends on besides the catalog itself (the reference's `binning` file)"""
+    def _signature(catalog, binning):
+        """what a resident device catalog depends on besides the catalog object: the z-binning (the reference's
+        `binning` file) and, as a guard against catalogs refilled in place, the rows per patch"""
+        rows = tuple(int(n) for n in catalog.get_num_records())
         if binning is None:
-            return None
-        return (tuple(np.asarray(binning.edges, dtype=np.float64).tolist()), str(binning.closed))
+            return (rows, None)
+        return (rows, tuple(np.asarray(binning.edges, dtype=np.float64).tolist()), str(binning.closed))
 
     def _resident_lookup(self, key, catalog, binning, kappa) -> bool:
         lookup = getattr(self.engine, "cache_lookup", None)
-        dev = lookup(catalog, self._signature(binning), kappa) if lookup else None
+        dev = lookup(catalog, self._signature(catalog, binning), kappa) if lookup else None
         if dev is None:
             return False
         self._cache[key] = dev
@@ -204,7 +206,7 @@ class _Uploads:
     def _store(self, key, catalog, binning, kappa, dev):
         self._cache[key] = dev
         store = getattr(self.engine, "cache_store", None)
-        if store and store(catalog, self._signature(binning), kappa, dev):
+        if store and store(catalog, self._signature(catalog, binning), kappa, dev):
             self._resident.add(key)
         return dev
 
