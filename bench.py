@@ -439,13 +439,16 @@ def run_gpu_arm(args):
     # linked to them)
     own = np.arange(len(pi))
     arrays = wl["arrays"]
-    if world > 1 and not weak:
+    part_rank, part_world = rank, world
+    if args.emulate_share:  # development: one GPU runs rank r's share of a w-GPU strong-scaling run ("r/w")
+        part_rank, part_world = (int(v) for v in args.emulate_share.split("/"))
+    if part_world > 1 and not weak:
         n1 = np.diff(arrays["ref_rand"]["patch_off"])
         n2 = np.diff(arrays["unk_rand"]["patch_off"])
         costs = pair_costs(pi, pj, n1, n2)
         patch_cost = np.bincount(pj, weights=costs, minlength=wl["n_patch"])
         centers_xyz = wl["cats"]["unk_rand"].get_centers().to_3d()
-        my_patches = assign_patches_contiguous(patch_cost, centers_xyz, world)[rank]
+        my_patches = assign_patches_contiguous(patch_cost, centers_xyz, part_world)[part_rank]
         own = np.flatnonzero(np.isin(pj, my_patches))
         need = dict(second=np.unique(pj[own]), first=np.unique(pi[own]))
         arrays = {k: subset_patches(a, need["first" if k in ("ref", "ref_rand") else "second"])
@@ -733,6 +736,7 @@ def main():
     ap.add_argument("--full-reference", action="store_true", help="--impl reference: also time the full job once")
     ap.add_argument("--e2e-groups", type=int, default=1,
                     help="patch slices per unbinned catalog in the end-to-end schedule (1 = whole catalogs)")
+    ap.add_argument("--emulate-share", default=None, help="development: 'r/w' = count rank r's share of a w-GPU strong-scaling run")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N > 1: strong = the ONE job split over the GPUs (default, the north-star case), "
                          "weak = one independent field of the workload's size per GPU")

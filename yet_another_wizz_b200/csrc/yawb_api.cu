@@ -512,8 +512,8 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     // work-item lists: a patch with itself needs an item per tile (a few more where items are split), of the
     // tiles of neighbouring patches only the boundary strip survives; if a list turns out too small the
     // count is repeated with the exact sizes
-    a.cap_heavy = 2 * flat_diag + 1024;
-    a.cap_light = (a.n_items - flat_diag) + 1024;
+    a.cap_heavy = 4 * flat_diag + 1024;
+    a.cap_light = 2 * (a.n_items - flat_diag) + 1024;
     a.n_pairs = n_pairs; a.n_bins = B; a.n_edges = n_edges;
     a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp; a.rmax_all = rmax_all;
     a.d_out_cnt = d_cnt; a.d_out_w = d_w; a.weighted = weighted;

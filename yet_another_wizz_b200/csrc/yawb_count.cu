@@ -40,6 +40,12 @@ constexpr float FAR = 1.0e15f;          // coordinates of padding points (never 
 #ifndef YAWB_CCAP
 #define YAWB_CCAP 160
 #endif
+#ifndef YAWB_CCAP_SMALL
+#define YAWB_CCAP_SMALL 48
+#endif
+#ifndef YAWB_SMALL_JOB_ITEMS
+#define YAWB_SMALL_JOB_ITEMS 30
+#endif
 
 struct FastParams {
     // first-role index (one catalog, or two fused)
@@ -496,21 +502,22 @@ struct PlanParams {
     double rmax_all;
     Item *heavy, *light;
     long long cap_heavy, cap_light;
+    int ccap;  // (z-bin, cell row) runs per item: YAWB_CCAP, or less to cut a small job into more, shorter items
     unsigned long long *counters;
 };
 
 template <typename Emit>
 __device__ __forceinline__ void plan_walk(const SGrid &G, const BinPar *__restrict__ binpar, int b_lo, int b_hi, double ulo,
-                                          double uhi, double vlo, double vhi, Emit emit) {
+                                          double uhi, double vlo, double vhi, int ccap, Emit emit) {
     int acc = 0, seg = b_lo;
     for (int b = b_lo; b < b_hi; ++b) {
         const int r = bin_rows(G, ulo, uhi, vlo, vhi, binpar[b], 0, INT_MAX).nrows;
-        if (r > YAWB_CCAP) {
+        if (r > ccap) {
             if (acc > 0) emit(seg, b, 0, INT_MAX);
-            for (int r0 = 0; r0 < r; r0 += YAWB_CCAP) emit(b, b + 1, r0, min(r0 + YAWB_CCAP, r));
+            for (int r0 = 0; r0 < r; r0 += ccap) emit(b, b + 1, r0, min(r0 + ccap, r));
             seg = b + 1;
             acc = 0;
-        } else if (acc + r > YAWB_CCAP) {
+        } else if (acc + r > ccap) {
             emit(seg, b, 0, INT_MAX);
             seg = b;
             acc = r;
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) { it.lo[d] = lo3[d]; it.hi[d] = hi3[d]; }
                 heavy = p1 == p2;
-                plan_walk(G, Q.binpar, it.b_lo, it.b_hi, lo3[0], hi3[0], lo3[1], hi3[1], [&](int, int, int, int) { ++n_emit; });
+                plan_walk(G, Q.binpar, it.b_lo, it.b_hi, lo3[0], hi3[0], lo3[1], hi3[1], Q.ccap, [&](int, int, int, int) { ++n_emit; });
             }
         }
     }
@@ -600,7 +607,7 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
     long long pos = heavy ? (long long)base_h + pre_h - n_emit : (long long)base_l + pre_l - n_emit;
     Item *const out = heavy ? Q.heavy : Q.light;
     const long long cap = heavy ? Q.cap_heavy : Q.cap_light;
-    plan_walk(G, Q.binpar, it.b_lo, it.b_hi, it.lo[0], it.hi[0], it.lo[1], it.hi[1], [&](int b0, int b1, int r0, int r1) {
+    plan_walk(G, Q.binpar, it.b_lo, it.b_hi, it.lo[0], it.hi[0], it.lo[1], it.hi[1], Q.ccap, [&](int b0, int b1, int r0, int r1) {
         if (pos < cap) {
             Item w = it;
             w.b_lo = b0; w.b_hi = b1; w.row_lo = r0; w.row_hi = r1;
@@ -730,6 +737,11 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         Q.n_pairs = a.n_pairs; Q.n_flat = a.n_items; Q.binpar = a.d_binpar; Q.n_bins = a.n_bins; Q.rmax_all = a.rmax_all;
         Q.heavy = d_items; Q.light = d_items + cap_heavy; Q.cap_heavy = cap_heavy; Q.cap_light = cap_light;
         Q.counters = ctx->d_counters;
+        // a small job (a rank's share of a strong-scaling run) is cut into more, shorter items, so that the warps of
+        // the persistent grid finish together: YAWB_SMALL_JOB_ITEMS flat (pair, tile) combinations per warp
+        const long long warps = (long long)ctx->sms * STREAM_CTAS * STREAM_WARPS;
+        Q.ccap = a.n_items < YAWB_SMALL_JOB_ITEMS * warps ? YAWB_CCAP_SMALL : YAWB_CCAP;
+        if (const char *e = getenv("YAWB_CCAP_RUNTIME")) Q.ccap = std::max(8, std::min(YAWB_CCAP, atoi(e)));
         k_plan<<<(unsigned)((a.n_items + 255) / 256), 256, 0, ctx->stream>>>(Q);
         *launches += 1;
     }

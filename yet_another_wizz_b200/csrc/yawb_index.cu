@@ -213,23 +213,6 @@ __global__ void k_init_box(unsigned long long *__restrict__ box, int n_patch) {
     box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
 }
 
-// boxes as they stand in the frames (the starting point when a second catalog's rows are added)
-__global__ void k_box_from_frames(const PatchFrame *__restrict__ frames, int n_patch, unsigned long long *__restrict__ box) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_patch) return;
-    const PatchFrame &f = frames[p];
-    if (f.radius == 0.0 && f.umin == 0.0 && f.umax == 0.0 && f.vmin == 0.0 && f.vmax == 0.0) {  // no rows so far
-        box[5 * p] = box[5 * p + 2] = ~0ull;
-        box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
-        return;
-    }
-    box[5 * p] = enc_double(f.umin);
-    box[5 * p + 1] = enc_double(f.umax);
-    box[5 * p + 2] = enc_double(f.vmin);
-    box[5 * p + 3] = enc_double(f.vmax);
-    box[5 * p + 4] = enc_double(f.radius * f.radius);
-}
-
 __global__ void k_finish_frames(const unsigned long long *__restrict__ box, int n_patch,
                                 PatchFrame *__restrict__ frames) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -751,42 +734,46 @@ int yawb_cat_finalize(yawb_cat *cat) {
 
 // -------------------------------------------------------------------------------------------
 // Frames of a first-role index.  One catalog: its own frames.  Two catalogs: per patch the frame of the
-// catalog with more rows there; the (u, v) box and the radius are then grown over the rows of both.
+// catalog with more rows there; its (u, v) box and radius are then grown -- on the host, without touching the
+// rows -- to contain the other catalog's patch as well: the other patch's bounding box (a box in ITS frame) is
+// carried over as the hull of its eight rotated corners, its bounding sphere by the triangle inequality.
 static int findex_frames(FIndex *fi) {
     yawb_ctx *ctx = fi->ctx;
-    cudaStream_t st = ctx->stream;
     const yawb_cat *a = fi->a, *b = fi->b;
     const int P = fi->n_patch, B = fi->n_bins;
     fi->h_frames = a->h_frames;
     if (fi_alloc(fi, &fi->d_frames, P)) return 1;
-    if (!b) return yawb_h2d_small(ctx, fi->d_frames, fi->h_frames.data(), P * sizeof(PatchFrame));
-    bool a_chosen = false, b_chosen = false;
-    for (int p = 0; p < P; ++p) {
-        const long long ra = a->h_seg_off[(size_t)(p + 1) * B] - a->h_seg_off[(size_t)p * B];
-        const long long rb = b->h_seg_off[(size_t)(p + 1) * B] - b->h_seg_off[(size_t)p * B];
-        if (rb >= ra && rb > 0) {
-            fi->h_frames[p] = b->h_frames[p];
-            b_chosen = true;
-        } else {
-            a_chosen = true;
+    if (b) {
+        for (int p = 0; p < P; ++p) {
+            const long long ra = a->h_seg_off[(size_t)(p + 1) * B] - a->h_seg_off[(size_t)p * B];
+            const long long rb = b->h_seg_off[(size_t)(p + 1) * B] - b->h_seg_off[(size_t)p * B];
+            const bool use_b = rb >= ra && rb > 0;
+            PatchFrame f = use_b ? b->h_frames[p] : a->h_frames[p];
+            const PatchFrame &o = use_b ? a->h_frames[p] : b->h_frames[p];
+            const long long ro = use_b ? ra : rb;
+            if (ro > 0) {
+                // the other patch: rows with (u, v) in its box and t in [-radius^2 / 2, 0] of ITS frame
+                const double tlo = -0.5 * o.radius * o.radius * (1.0 + 1e-9) - 1e-15;
+                double umin = f.umin, umax = f.umax, vmin = f.vmin, vmax = f.vmax;
+                for (int c = 0; c < 8; ++c) {
+                    const double u = (c & 1) ? o.umax : o.umin, v = (c & 2) ? o.vmax : o.vmin, w = (c & 4) ? 0.0 : tlo;
+                    double X[3];
+                    for (int d = 0; d < 3; ++d) X[d] = o.c[d] + u * o.e1[d] + v * o.e2[d] + w * o.c[d] - f.c[d];
+                    const double uu = X[0] * f.e1[0] + X[1] * f.e1[1] + X[2] * f.e1[2];
+                    const double vv = X[0] * f.e2[0] + X[1] * f.e2[1] + X[2] * f.e2[2];
+                    umin = std::min(umin, uu); umax = std::max(umax, uu);
+                    vmin = std::min(vmin, vv); vmax = std::max(vmax, vv);
+                }
+                const double pad = 1e-12 * (1.0 + std::max(std::fabs(umax - umin), std::fabs(vmax - vmin)));
+                f.umin = umin - pad; f.umax = umax + pad; f.vmin = vmin - pad; f.vmax = vmax + pad;
+                const double dc = std::sqrt((o.c[0] - f.c[0]) * (o.c[0] - f.c[0]) + (o.c[1] - f.c[1]) * (o.c[1] - f.c[1]) +
+                                            (o.c[2] - f.c[2]) * (o.c[2] - f.c[2]));
+                f.radius = std::max(f.radius, (dc + o.radius) * (1.0 + 1e-12) + 1e-15);
+            }
+            fi->h_frames[p] = f;
         }
     }
-    if (yawb_h2d_small(ctx, fi->d_frames, fi->h_frames.data(), P * sizeof(PatchFrame))) return 1;
-    Scratch scr(ctx, st);
-    unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
-    YAWB_REQUIRE(d_box != nullptr, "out of device memory (frames)");
-    const int pb = (P + 127) / 128;
-    // a patch that uses the frame of one catalog starts from that catalog's box; the rows of the other
-    // catalog extend it (re-adding a catalog's own rows changes nothing)
-    k_box_from_frames<<<pb, 128, 0, st>>>(fi->d_frames, P, d_box);
-    if (b_chosen && a->n_in > 0)
-        k_patch_bbox<<<blocks_for(a->n_in, kSumRows), kThreads, 0, st>>>(a->x, a->y, a->z, a->patch, a->n_in, fi->d_frames, d_box);
-    if (a_chosen && b->n_in > 0)
-        k_patch_bbox<<<blocks_for(b->n_in, kSumRows), kThreads, 0, st>>>(b->x, b->y, b->z, b->patch, b->n_in, fi->d_frames, d_box);
-    k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, fi->d_frames);
-    YAWB_CUDA(cudaMemcpyAsync(fi->h_frames.data(), fi->d_frames, P * sizeof(PatchFrame), cudaMemcpyDeviceToHost, st));
-    YAWB_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    return yawb_h2d_small(ctx, fi->d_frames, fi->h_frames.data(), P * sizeof(PatchFrame));
 }
 
 static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
