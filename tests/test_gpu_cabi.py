@@ -308,6 +308,27 @@ def test_pair_test_variants_exact(engine, variant, monkeypatch):
     assert ei[0] > 1e6 and fs["rechecks"] > 0
 
 
+@pytest.mark.parametrize("dev", [1e-13, 1e-9, 1e-4])
+def test_rows_off_the_unit_sphere_stay_exact(engine, dev):
+    """The pair test takes |r|^2 of a tile row from the identity for unit vectors; rows that are NOT unit vectors
+    (the C ABI takes any doubles) only widen the band of tests that go through the FP64 recheck: the counts still
+    equal the plain double-precision evaluation of the reference's expression."""
+    rng = np.random.default_rng(11)
+    n = 6000
+    ra = rng.uniform(0.0, 0.01, n); dec = np.arcsin(rng.uniform(-0.005, 0.005, n))
+    xyz = oracle.radec_to_xyz(ra, dec) * (1.0 + dev * rng.uniform(-1.0, 1.0, n))[:, None]
+    a, b = xyz[: n // 2], xyz[n // 2 :]
+    r2 = oracle.chord_sq_edges(np.array([2e-4, 1.5e-3]))
+    want = oracle.pair_histogram(a, b, None, None, r2)
+    ci, _, stats = single_patch_hist(engine, a, None, b, None, r2, False)
+    assert_array_equal(ci, want.astype(np.int64))
+    assert ci[0] > 1e5
+    r2m = oracle.chord_sq_edges(np.array([2e-4, 5e-4, 1.0e-3, 1.5e-3]))
+    want = oracle.pair_histogram(a, b, None, None, r2m)
+    ci, _, _ = single_patch_hist(engine, a, None, b, None, r2m, False)
+    assert_array_equal(ci, want.astype(np.int64))
+
+
 def test_device_memory_is_recycled(engine):
     """upload / count / free cycles of varying size: the context's caching allocator reuses its blocks, the
     footprint on the device stops growing after the first cycles"""

@@ -52,6 +52,25 @@ __device__ __forceinline__ void test_one(const float4 ca, const float4 cb, const
     }
 }
 
+// sphere form: |r|^2 folded into the candidate's operands, no FADD2
+__device__ __forceinline__ void test_one_nf(const float4 ca, const float4 cb, const float2 (&rx)[HPL],
+                                            const float2 (&ry)[HPL], const float2 (&rz)[HPL],
+                                            float ta, float tb, float2 &acc_a, float2 &acc_b) {
+    const float2 sx = make_float2(ca.x, ca.y), sy = make_float2(ca.z, ca.w);
+    const float2 sz = make_float2(cb.x, cb.y), sw = make_float2(cb.z, cb.w);
+#pragma unroll
+    for (int k = 0; k < HPL; ++k) {
+        float2 u = __ffma2_rn(rx[k], sx, sw);
+        u = __ffma2_rn(ry[k], sy, u);
+        u = __ffma2_rn(rz[k], sz, u);
+        float2 v;
+        v.x = __saturatef(fmaf(fabsf(u.x), ta, tb));
+        v.y = __saturatef(fmaf(fabsf(u.y), ta, tb));
+        acc_a = __fadd2_rn(acc_a, v);
+        acc_b = __ffma2_rn(v, v, acc_b);
+    }
+}
+
 // ALU-assisted variant: distance + ramp on the FMA pipe (4 packed + 2 scalar FFMA.SAT per row pair); the hits are
 // counted by adding the bit patterns of v (0 or 0x3f800000) with IADD3, undecided tests (0 < v < 1) are detected
 // with an unsigned running minimum of bits(v) - 1 (VIADDMNMX), both on the integer pipe.
@@ -99,6 +118,48 @@ __device__ __forceinline__ void test_one_sc(const float4 ca, const float4 cb, co
     }
 }
 
+
+constexpr unsigned ONE_BITS = 0x3f800000u;
+__device__ __forceinline__ unsigned lop3_or3(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xfe;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned lop3_or_and(unsigned a, unsigned b, unsigned c) {  // a | (b & c)
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xf8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// Dual-pipe variants: distance + ramp on the FMA pipe (scalar FADD + 3 FFMA + FFMA.SAT per test), everything else on
+// the ALU pipe: an undecided test (0 < v < 1) is detected as min(bits, bits ^ 0x3f800000) != 0 (XOR + VIMNMX), OR-ed
+// into one word (LOP3 per two tests).
+//   MODE 6: hits summed on the FMA pipe (FADD per test)
+//   MODE 7: hits collected as flag bits (bit 23 + row of the 7-bit exponent pattern of 1.0f, LOP3 per test), POPC + IADD per candidate
+//   MODE 8: MODE 7 without the FADD (|r|^2 folded away: points on a sphere)
+template <int MODE, int SLOT>
+__device__ __forceinline__ void test_one_dp(const float4 q, const float2 (&rx)[HPL], const float2 (&ry)[HPL],
+                                            const float2 (&rz)[HPL], const float2 (&rn)[HPL], float ta, float tb, float &sum,
+                                            unsigned &det, unsigned &cnt, unsigned &w8) {
+    unsigned w = 0u, zprev = 0u;
+#pragma unroll
+    for (int k = 0; k < 2 * HPL; ++k) {
+        const float x_ = (k & 1) ? rx[k >> 1].y : rx[k >> 1].x, y_ = (k & 1) ? ry[k >> 1].y : ry[k >> 1].x;
+        const float z_ = (k & 1) ? rz[k >> 1].y : rz[k >> 1].x, n_ = (k & 1) ? rn[k >> 1].y : rn[k >> 1].x;
+        float u = MODE == 8 ? q.w : n_ + q.w;
+        u = fmaf(x_, q.x, u);
+        u = fmaf(y_, q.y, u);
+        u = fmaf(z_, q.z, u);
+        const float v = __saturatef(fmaf(fabsf(u), ta, tb));
+        const unsigned b = __float_as_uint(v);
+        const unsigned z = min(b, b ^ ONE_BITS);
+        if (k & 1) det = lop3_or3(det, zprev, z); else zprev = z;
+        if (MODE == 6) sum += v;
+        else if (k < 7) w = lop3_or_and(w, b, 1u << (23 + k));
+        else w8 = lop3_or_and(w8, b, 1u << (23 + SLOT));
+    }
+    if (MODE != 6) cnt += __popc(w);
+}
+
 __device__ __noinline__ unsigned slow_recheck(const float *g, int e0, int lane) {
     return (unsigned)g[e0 * 32 + lane];  // stands for the FP64 recheck (never taken in the probe)
 }
@@ -131,7 +192,7 @@ __global__ void __launch_bounds__(128) k_probe(const float *__restrict__ init, i
     for (int e = lane; e < LB; e += 32) {
         const float x = init[(e * 7 + warp) & 1023] * 2e-3f, y = init[(e * 13 + 5) & 1023] * 2e-3f, z = 1e-5f;
         const float sn = x * x + y * y + z * z;
-        if (VARIANT == 2) {
+        if (VARIANT == 2 || (VARIANT >= 6 && VARIANT != 9)) {
             list16[e] = make_float4(-2.f * x, -2.f * y, -2.f * z, sn - mid);
         } else {
             list[e].a = make_float4(-2.f * x, -2.f * x, -2.f * y, -2.f * y);
@@ -193,8 +254,31 @@ __global__ void __launch_bounds__(128) k_probe(const float *__restrict__ init, i
                     float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
                     unsigned icnt = 0u, iumin = 0xffffffffu;
                     int e = c0;
+                    float dsum = 0.f;
+                    unsigned ddet = 0u, dcnt = 0u, dw8 = 0u;
+                    if (VARIANT >= 6 && VARIANT < 9) {
+#define TD(idx, slot) test_one_dp<VARIANT, slot>(list16[idx], rx, ry, rz, rn, cur.K, cur.C, dsum, ddet, dcnt, dw8)
+                        for (; e + 4 <= c1; e += 4) {
+                            TD(e, 0); TD(e + 1, 1); TD(e + 2, 2); TD(e + 3, 3);
+                            if (VARIANT != 6) { dcnt += __popc(dw8); dw8 = 0u; }
+                        }
+                        switch (c1 - e) {
+                            case 3: TD(e + 2, 2);
+                            case 2: TD(e + 1, 1);
+                            case 1: TD(e, 0);
+                            default: break;
+                        }
+                        if (VARIANT != 6) dcnt += __popc(dw8);
+#undef TD
+                        e = c1;
+                    }
                     auto T = [&](int idx) {
-                        if (VARIANT == 4) {
+                        if (VARIANT == 9) {
+                            test_one_nf(list[idx].a, list[idx].b, rx, ry, rz, cur.K, cur.C, acc_a, acc_b);
+                        } else if (VARIANT == 10) {
+                            const float4 q = list16[idx];
+                            test_one_nf(make_float4(q.x, q.x, q.y, q.y), make_float4(q.z, q.z, q.w, q.w), rx, ry, rz, cur.K, cur.C, acc_a, acc_b);
+                        } else if (VARIANT == 4) {
                             test_one_sc<false>(list[idx].a, list[idx].b, rx, ry, rz, rn, cur.K, cur.C, acc_a, acc_b, icnt, iumin);
                         } else if (VARIANT == 5) {
                             test_one_sc<true>(list[idx].a, list[idx].b, rx, ry, rz, rn, cur.K, cur.C, acc_a, acc_b, icnt, iumin);
@@ -220,6 +304,10 @@ __global__ void __launch_bounds__(128) k_probe(const float *__restrict__ init, i
                     const float sa = acc_a.x + acc_a.y, sb = acc_b.x + acc_b.y;
                     unsigned c = (unsigned)(sa + 0.5f);
                     bool bad = sa != sb;
+                    if (VARIANT >= 6 && VARIANT < 9) {
+                        c = VARIANT == 6 ? (unsigned)(dsum + 0.5f) : dcnt;
+                        bad = ddet != 0u;
+                    }
                     if (VARIANT == 3 || VARIANT == 5) {
                         c = ((icnt >> 23) * 383u) & 511u;  // icnt = 127 * n << 23 (mod 2^32), 127 * 383 = 1 (mod 512)
                         bad = iumin < 0x3f7fffffu;          // some v strictly between 0 and 1
@@ -306,11 +394,9 @@ int main(int argc, char **argv) {
         CK(cudaDeviceSynchronize());
         return 0;
     }
-    run<0>(d_init, d_out, sms, peak);
     run<1>(d_init, d_out, sms, peak);
     run<2>(d_init, d_out, sms, peak);
-    run<3>(d_init, d_out, sms, peak);
-    run<4>(d_init, d_out, sms, peak);
-    run<5>(d_init, d_out, sms, peak);
+    run<9>(d_init, d_out, sms, peak);
+    run<10>(d_init, d_out, sms, peak);
     return 0;
 }

@@ -36,7 +36,9 @@ constexpr float EPS32 = 5.9604645e-8f;  // 2^-24
 #define YAWB_CHUNK 8
 #endif
 constexpr int CHUNK = YAWB_CHUNK;       // candidates between consistency checks (power of two)
-constexpr float FAR = 1.0e15f;          // coordinates of padding points (never in range)
+// Coordinates of the padding rows of a short tile: NaN.  u = NaN fails |u| < h, and a saturating FMA flushes NaN to +0
+// (PTX: "NaN results are flushed to +0.0f"), so every form of the pair test counts such a row as decided and outside.
+#define PAD_ROW __int_as_float(0x7fffffff)
 #ifndef YAWB_CCAP
 #define YAWB_CCAP 160
 #endif
@@ -55,6 +57,7 @@ struct FastParams {
     const SGrid *sgrid;
     const PatchFrame *sframe;
     int n_types;
+    float zeta;  // max | |P|^2 - 1 | over the rows of the second catalog(s), rounded up: part of the FP32 error bound
     // second catalog (register tiles); rx2.. = second catalog of a joint launch (Item::src == 1)
     const double *rx, *ry, *rz, *rw;
     const double *rx2, *ry2, *rz2, *rw2;
@@ -129,12 +132,11 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// One staged candidate: (-2x, -2y, -2z, |s|^2 - mid), every component duplicated so that it can be
-// used directly as the broadcast operand of the packed f32x2 instructions (FFMA2 / FADD2).
-struct __align__(16) Cand {
-    float4 a;  // (-2x, -2x, -2y, -2y)
-    float4 b;  // (-2z, -2z, |s|^2 - mid, |s|^2 - mid)
-};
+// One staged candidate s, in the tile frame of the item (yawb_count_stream.cuh): (-2 s_x, -2 s_y, -2 (1 + s_z),
+// |s|^2 - mid), so that for a row r of the tile  r . (x, y, z) + w = |r - s|^2 - mid  (the rows are unit vectors,
+// their |r|^2 equals -2 r_z in this frame).  One broadcast LDS.128; the compiler duplicates the components into
+// the register pairs of the packed f32x2 instructions.
+typedef float4 Cand;
 constexpr int HPL = YAWB_RPL / 2;  // row pairs per lane
 
 // ---- view of a warp's staged list for the phase-2 functions --------------------------------------
@@ -223,15 +225,14 @@ __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem
 template <bool WEIGHTED, bool SAT>
 __device__ __forceinline__ void test_candidate(const Cand c, double swt, const float2 (&rx)[HPL],
                                                const float2 (&ry)[HPL], const float2 (&rz)[HPL],
-                                               const float2 (&rn)[HPL], float ta, float tb, float2 &acc_a,
+                                               float ta, float tb, float2 &acc_a,
                                                float2 &acc_b, double (&ws)[YAWB_RPL]) {
     // Blackwell packed FP32: one FFMA2 / FADD2 carries two pair tests (rows 2k and 2k+1 of the lane)
-    const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
-    const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
+    const float2 sx = make_float2(c.x, c.x), sy = make_float2(c.y, c.y);
+    const float2 sz = make_float2(c.z, c.z), sw = make_float2(c.w, c.w);
 #pragma unroll
     for (int k = 0; k < HPL; ++k) {
-        float2 u = __fadd2_rn(rn[k], sw);
-        u = __ffma2_rn(rx[k], sx, u);
+        float2 u = __ffma2_rn(rx[k], sx, sw);
         u = __ffma2_rn(ry[k], sy, u);
         u = __ffma2_rn(rz[k], sz, u);
         if (SAT) {
@@ -261,7 +262,7 @@ __device__ __forceinline__ void test_candidate(const Cand c, double swt, const f
 template <bool WEIGHTED, bool SAT>
 __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
                                               const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                              const float2 (&rz)[HPL], const float2 (&rn)[HPL],
+                                              const float2 (&rz)[HPL],
                                               float ta, float tb, const Tile &tl, int lane, double lo,
                                               double hi, unsigned &cnt_total, double &w_total,
                                               unsigned &n_recheck, const double (&rwt)[YAWB_RPL]) {
@@ -276,11 +277,11 @@ __device__ __forceinline__ void phase2_single(const FastParams &P, const WarpSme
         if (e1 - e0 == CHUNK) {  // common case: fully unrolled, no loop bookkeeping
 #pragma unroll
             for (int k = 0; k < CHUNK; ++k)
-                test_candidate<WEIGHTED, SAT>(S.list[e0 + k], WEIGHTED ? S.lw[e0 + k] : 0.0, rx, ry, rz, rn, ta, tb,
+                test_candidate<WEIGHTED, SAT>(S.list[e0 + k], WEIGHTED ? S.lw[e0 + k] : 0.0, rx, ry, rz, ta, tb,
                                               acc_a, acc_b, ws);
         } else {
             for (int e = e0; e < e1; ++e)
-                test_candidate<WEIGHTED, SAT>(S.list[e], WEIGHTED ? S.lw[e] : 0.0, rx, ry, rz, rn, ta, tb, acc_a,
+                test_candidate<WEIGHTED, SAT>(S.list[e], WEIGHTED ? S.lw[e] : 0.0, rx, ry, rz, ta, tb, acc_a,
                                               acc_b, ws);
         }
         const float sa = acc_a.x + acc_a.y, sb = acc_b.x + acc_b.y;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
 template <int CUM_GROUP>
 __device__ __forceinline__ void phase2_cumul_g(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
                                              const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL], float nk,
+                                             const float2 (&rz)[HPL], float nk,
                                              const Tile &tl, int lane, int b, unsigned &n_recheck) {
     const int ne = P.n_edges;
     const double *ed = P.r2 + (size_t)b * ne;
@@ -363,12 +364,11 @@ __device__ __forceinline__ void phase2_cumul_g(const FastParams &P, const WarpSm
             for (int g = 0; g < CUM_GROUP; ++g) acc_a[g] = acc_b[g] = make_float2(0.f, 0.f);
             for (int e = e0; e < e1; ++e) {
                 const Cand c = S.list[e];
-                const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
-                const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
+                const float2 sx = make_float2(c.x, c.x), sy = make_float2(c.y, c.y);
+                const float2 sz = make_float2(c.z, c.z), sw = make_float2(c.w, c.w);
 #pragma unroll
                 for (int k = 0; k < HPL; ++k) {
-                    float2 u = __fadd2_rn(rn[k], sw);
-                    u = __ffma2_rn(rx[k], sx, u);
+                    float2 u = __ffma2_rn(rx[k], sx, sw);
                     u = __ffma2_rn(ry[k], sy, u);
                     u = __ffma2_rn(rz[k], sz, u);
 #pragma unroll
@@ -417,19 +417,19 @@ __device__ __forceinline__ void phase2_cumul_g(const FastParams &P, const WarpSm
 
 __device__ __forceinline__ void phase2_cumul(const FastParams &P, const WarpSmem<false> &S, int ea, int eb,
                                              const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL], float nk,
+                                             const float2 (&rz)[HPL], float nk,
                                              const Tile &tl, int lane, int b, unsigned &n_recheck) {
     const int ne = P.n_edges;  // measured on C4 (6 edges): one pass of 6 beats two of 3 beats three of 2
-    if (ne <= 3) phase2_cumul_g<3>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
-    else if (ne == 5 || ne == 6) phase2_cumul_g<6>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
-    else phase2_cumul_g<4>(P, S, ea, eb, rx, ry, rz, rn, nk, tl, lane, b, n_recheck);
+    if (ne <= 3) phase2_cumul_g<3>(P, S, ea, eb, rx, ry, rz, nk, tl, lane, b, n_recheck);
+    else if (ne == 5 || ne == 6) phase2_cumul_g<6>(P, S, ea, eb, rx, ry, rz, nk, tl, lane, b, n_recheck);
+    else phase2_cumul_g<4>(P, S, ea, eb, rx, ry, rz, nk, tl, lane, b, n_recheck);
 }
 
 // ---- phase 2, several sub-bins (r-weights, multi-scale) ------------------------------------
 template <bool WEIGHTED>
 __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem<WEIGHTED> &S, int ea, int eb,
                                              const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                             const float2 (&rz)[HPL], const float2 (&rn)[HPL],
+                                             const float2 (&rz)[HPL],
                                              float h_out, float eps, float mid, const Tile &tl, int lane, int b,
                                              unsigned &n_recheck) {
     const int ne = P.n_edges;
@@ -440,12 +440,11 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
     const unsigned short *lgT = P.lgT + (size_t)b * nc;
     for (int e = ea; e < eb; ++e) {
         const Cand c = S.list[e];
-        const float2 sx = make_float2(c.a.x, c.a.y), sy = make_float2(c.a.z, c.a.w);
-        const float2 sz = make_float2(c.b.x, c.b.y), sw = make_float2(c.b.z, c.b.w);
+        const float2 sx = make_float2(c.x, c.x), sy = make_float2(c.y, c.y);
+        const float2 sz = make_float2(c.z, c.z), sw = make_float2(c.w, c.w);
 #pragma unroll
         for (int r = 0; r < YAWB_RPL; ++r) {
-            float2 u2 = __fadd2_rn(rn[r >> 1], sw);
-            u2 = __ffma2_rn(rx[r >> 1], sx, u2);
+            float2 u2 = __ffma2_rn(rx[r >> 1], sx, sw);
             u2 = __ffma2_rn(ry[r >> 1], sy, u2);
             u2 = __ffma2_rn(rz[r >> 1], sz, u2);
             const float u = (r & 1) ? u2.y : u2.x;  // the compiler merges the two halves of a row pair
@@ -713,6 +712,14 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.cell_start = fi->cell_start; P.sgrid = fi->d_sgrid; P.sframe = fi->d_frames; P.n_types = fi->n_types;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
     P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
+    {
+        // the pair test takes |r|^2 of a tile row from the identity for unit vectors (yawb_count_stream.cuh); rows
+        // off the unit sphere by zeta widen the band of tests that are re-evaluated in FP64 (1e-15: the frames'
+        // own deviation from orthonormality)
+        double zeta = 0.0;
+        for (const PatchFrame &f : a.c2->h_frames) zeta = std::max(zeta, f.norm_dev);
+        P.zeta = (float)(zeta + 1.0e-15) * 1.000001f;
+    }
     P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
     P.r2 = a.d_r2; P.r2f = a.d_r2f; P.binpar = a.d_binpar; P.rmax_all = a.rmax_all;
     P.lg_cells = a.n_edges > 2 ? 2 * a.n_edges : 0;

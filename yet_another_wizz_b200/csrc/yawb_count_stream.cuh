@@ -35,16 +35,23 @@ constexpr int NSLOT = 4;                       // items in flight per warp: cons
 constexpr int STREAM_WARPS = YAWB_STREAM_WARPS;
 constexpr int STREAM_CTAS = YAWB_STREAM_CTAS;
 
+// The staged frame of an item ("tile frame"): origin O = the point of the unit sphere in the direction of the centre of
+// the tile box, axes (t1, t2, n) with n = O - (centre of the sphere).  For a row P of the tile (a unit vector)
+// |P - O|^2 = -2 (P - O).n, so the squared chord to a candidate s needs no |r|^2 term:
+//     |r - s|^2 - mid = (|s|^2 - mid) + r . (-2 s_x, -2 s_y, -2 (1 + s_z))        (three FMAs per test)
 struct __align__(16) ItemAux {
-    double ou, ov, ot;  // origin of the staged frame in the frame of p1, a point of the fixed-point lattice
-    int ko[3];          // ... in lattice units
+    double R[9];        // rows t1, t2, n of the tile frame, in coordinates of the frame of p1
+    double O[3];        // origin of the tile frame, in coordinates of the frame of p1
+    double dq[3];       // lattice origin - O:  (row of the index) - O = (k - ko) * qinv + dq
+    int ko[3];          // lattice origin: the lattice point nearest to the centre of the tile box
     int n_combo;        // runs of the item
     float qinv;         // lattice spacing (a power of two)
-    float eu, ev, et;   // half extents of the tile box about the origin, rounded up
+    float eu, ev, et;   // half extents of the tile box about the lattice origin, rounded up
+    float g;            // |lattice origin - O|, rounded up
     int end;            // 1: the work list is exhausted, this slot holds no item
-    int pad[3];
+    int pad[2];
 };
-static_assert(sizeof(ItemAux) == 80, "ItemAux layout");
+static_assert(sizeof(ItemAux) % 16 == 0, "ItemAux layout");
 
 struct __align__(16) SegDesc {
     short ea, eb;  // entries [ea, eb) of the staged list
@@ -198,7 +205,27 @@ __device__ __forceinline__ void stream_plan(const FastParams &P, const SM &S, in
             const float h = (float)fmax(it.hi[d] - o[d], o[d] - it.lo[d]);
             e[d] = h * 1.000001f + 1.0e-30f;
         }
-        ax.ou = o[0]; ax.ov = o[1]; ax.ot = o[2];
+        // tile frame: the sphere is centred at (0, 0, -1) in the frame of p1
+        double n[3] = {c[0], c[1], c[2] + 1.0};
+        const double nn = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] *= nn; n[1] *= nn; n[2] *= nn;
+        // an axis of the frame of p1 made orthogonal to n: u inside a patch, v for a direction near the u axis
+        // (search radii of tens of degrees)
+        double t1[3] = {1.0 - n[0] * n[0], -n[0] * n[1], -n[0] * n[2]};
+        if (fabs(n[0]) > 0.7) { t1[0] = -n[1] * n[0]; t1[1] = 1.0 - n[1] * n[1]; t1[2] = -n[1] * n[2]; }
+        const double tn = 1.0 / sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+        t1[0] *= tn; t1[1] *= tn; t1[2] *= tn;
+        const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+        double g2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            ax.R[d] = t1[d]; ax.R[3 + d] = t2[d]; ax.R[6 + d] = n[d];
+            const double O = n[d] - (d == 2 ? 1.0 : 0.0);
+            ax.O[d] = O;
+            ax.dq[d] = o[d] - O;
+            g2 += (o[d] - O) * (o[d] - O);
+        }
+        ax.g = (float)sqrt(g2) * 1.000001f + 1.0e-30f;
         ax.eu = e[0]; ax.ev = e[1]; ax.et = e[2];
         ax.qinv = (float)G.qinv;
         ax.n_combo = n_combo;
@@ -305,11 +332,14 @@ __device__ __forceinline__ void stream_begin(const FastParams &P, const StreamSm
         // half extents rounded up; they bound every staged vector, hence the FP32 error of u
         const float r = (float)bp.rmax * 1.000001f + q;
         const float hx = (eu + r) * 1.000001f, hy = (ev + r) * 1.000001f, hz = (et + r) * 1.000001f;
-        const float m2 = hx * hx + hy * hy + hz * hz;
-        // |u_fp32 - (d2_ref - mid)| <= 29 eps32 M^2 + 7 eps32 mid (coordinate rounding 8, |r|^2 3, |s|^2 - mid
-        // 4 + 1, first add 2 + 1, three FMAs 12 + 3, mid/h rounding 2), plus the lattice:
-        // a displaced candidate changes d2 by at most |delta| (2 |d| + |delta|) <= 0.87 q (4 M + q) < 4 M q + q^2
-        const float eps = (EPS32 * (32.0f * m2 + 8.0f * bp.mid) + 4.0f * sqrtf(m2) * 1.0001f * q + q * q) * 1.0001f;
+        // norm bound of every staged vector (rows of the tile, candidates inside the query box) about the origin O
+        const float m1 = (sqrtf(hx * hx + hy * hy + hz * hz) + ax.g) * 1.000001f;
+        const float m2 = m1 * m1;
+        // |u_fp32 - (d2_ref - mid)| <= zeta + eps32 (19 M^2 + 6 mid) (rounding of the rows 3, of
+        // the candidate's operands 3, of |s|^2 - mid 1 + 1, three FMAs 12 + 3, mid/h rounding 2; zeta = how far the
+        // rows are from the unit sphere), plus the lattice: a displaced candidate changes d2 by at most
+        // |delta| (2 |d| + |delta|) <= 0.87 q (4 M + q) < 4 M q + q^2
+        const float eps = (EPS32 * (24.0f * m2 + 8.0f * bp.mid) + 4.0f * m1 * 1.0001f * q + q * q + P.zeta) * 1.0001f;
         S.binrec[b] = make_float4(hx, hy, hz, bp.mid);
         if (MULTI && SAT) {
             // cumulative counts per edge: v_k = sat(K (e_k - mid - u) + 1/2); the float copy of
@@ -337,11 +367,13 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
     const ItemAux &ax = S.aux[slot];
     const int k0 = ax.ko[0], k1 = ax.ko[1], k2 = ax.ko[2];
     const float qinv = ax.qinv;
+    const double qd = (double)qinv;
     int L0 = 0, L1 = 0;
     for (int base = 0; base < cnt; base += 32) {
         const int i = base + lane;
         bool ok = i < cnt;
         float fx = 0.f, fy = 0.f, fz = 0.f, mid = 0.f;
+        int kdx = 0, kdy = 0, kdz = 0;
         unsigned aux = 0u;
         int b = 0;
         if (ok) {
@@ -349,9 +381,10 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
             b = S.rawbin[i];
             aux = r.aux;
             // exact integer differences, rounded once to float, times a power of two
-            fx = (float)(r.ku - k0) * qinv;
-            fy = (float)(r.kv - k1) * qinv;
-            fz = (float)(r.kt - k2) * qinv;
+            kdx = r.ku - k0; kdy = r.kv - k1; kdz = r.kt - k2;
+            fx = (float)kdx * qinv;
+            fy = (float)kdy * qinv;
+            fz = (float)kdz * qinv;
             const float4 rec4 = S.binrec[b];
             mid = rec4.w;
             ok = fabsf(fx) <= rec4.x && fabsf(fy) <= rec4.y && fabsf(fz) <= rec4.z;
@@ -361,10 +394,13 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
         if (ok) {
             const unsigned below = (1u << lane) - 1u;
             const int pos = second ? LB - 1 - (L1 + __popc(m1 & below)) : L0 + __popc(m0 & below);
-            const float sn = fx * fx + fy * fy + fz * fz;
-            const float axx = -2.0f * fx, ayy = -2.0f * fy, azz = -2.0f * fz, aw = sn - mid;
-            S.list[pos].a = make_float4(axx, axx, ayy, ayy);
-            S.list[pos].b = make_float4(azz, azz, aw, aw);
+            // into the tile frame in double (exact lattice differences), rounded ONCE to the operands of the test
+            const double qx = (double)kdx * qd + ax.dq[0], qy = (double)kdy * qd + ax.dq[1], qz = (double)kdz * qd + ax.dq[2];
+            const double sx = ax.R[0] * qx + ax.R[1] * qy + ax.R[2] * qz;
+            const double sy = ax.R[3] * qx + ax.R[4] * qy + ax.R[5] * qz;
+            const double sz = ax.R[6] * qx + ax.R[7] * qy + ax.R[8] * qz;
+            const double sn = sx * sx + sy * sy + sz * sz;
+            S.list[pos] = make_float4((float)(-2.0 * sx), (float)(-2.0 * sy), (float)(-2.0 * (1.0 + sz)), (float)(sn - (double)mid));
             S.lidx[pos] = (int)(aux & 0x7fffffffu);
             S.lbin[pos] = (unsigned short)b;
             if (WEIGHTED) S.lw[pos] = S.rawlw[i];
@@ -408,7 +444,7 @@ __device__ __forceinline__ int stream_segments(const StreamSmem<WEIGHTED> &S, in
 // next segment is already running.
 __device__ __forceinline__ void stream_test_sat(const FastParams &P, const StreamSmem<false> &S, int n_seg,
                                                 const float2 (&rx)[HPL], const float2 (&ry)[HPL], const float2 (&rz)[HPL],
-                                                const float2 (&rn)[HPL], const Tile &tl, int lane, unsigned &n_recheck) {
+                                                const Tile &tl, int lane, unsigned &n_recheck) {
     WarpSmem<false> W{};
     W.list = S.list;
     W.lidx = S.lidx;
@@ -426,7 +462,7 @@ __device__ __forceinline__ void stream_test_sat(const FastParams &P, const Strea
             float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
             double ws[YAWB_RPL];
             int e = c0;
-#define YAWB_T(idx) test_candidate<false, true>(S.list[idx], 0.0, rx, ry, rz, rn, ta, tb, acc_a, acc_b, ws)
+#define YAWB_T(idx) test_candidate<false, true>(S.list[idx], 0.0, rx, ry, rz, ta, tb, acc_a, acc_b, ws)
             for (; e + 4 <= c1; e += 4) {
                 YAWB_T(e); YAWB_T(e + 1); YAWB_T(e + 2); YAWB_T(e + 3);
             }
@@ -461,7 +497,7 @@ __device__ __forceinline__ void stream_test_sat(const FastParams &P, const Strea
 template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void stream_test_generic(const FastParams &P, const StreamSmem<WEIGHTED> &S, int n_seg,
                                                     const float2 (&rx)[HPL], const float2 (&ry)[HPL],
-                                                    const float2 (&rz)[HPL], const float2 (&rn)[HPL], const Tile &tl,
+                                                    const float2 (&rz)[HPL], const Tile &tl,
                                                     int lane, int nsub, unsigned &n_recheck, int cur_pair,
                                                     const double (&rwt)[YAWB_RPL]) {
     const size_t nacc1 = (size_t)P.n_bins * nsub;  // accumulators of one type
@@ -475,14 +511,14 @@ __device__ __forceinline__ void stream_test_generic(const FastParams &P, const S
         W.accw = (WEIGHTED && S.accw) ? S.accw + d.type * nacc1 : nullptr;
         const float2 thr = S.binthr[b];
         if (MULTI && SAT && !WEIGHTED) {
-            if constexpr (!WEIGHTED) phase2_cumul(P, W, ea, eb, rx, ry, rz, rn, thr.x, tl, lane, b, n_recheck);
+            if constexpr (!WEIGHTED) phase2_cumul(P, W, ea, eb, rx, ry, rz, thr.x, tl, lane, b, n_recheck);
         } else if (MULTI) {
             for (int k = lane; k < nsub; k += 32) {
                 W.hist[k] = 0u;
                 if (WEIGHTED) W.histw[k] = 0.0;
             }
             __syncwarp();
-            phase2_multi<WEIGHTED>(P, W, ea, eb, rx, ry, rz, rn, thr.x, thr.y, S.binrec[b].w, tl, lane, b, n_recheck);
+            phase2_multi<WEIGHTED>(P, W, ea, eb, rx, ry, rz, thr.x, thr.y, S.binrec[b].w, tl, lane, b, n_recheck);
             __syncwarp();
             if (P.acc_global) {  // straight to the result: one atomic per non-empty sub-bin of the segment
                 const size_t o = (size_t)d.type * P.type_stride + ((size_t)cur_pair * P.n_bins + b) * nsub;
@@ -500,7 +536,7 @@ __device__ __forceinline__ void stream_test_generic(const FastParams &P, const S
         } else {
             unsigned cnt_total = 0;
             double w_total = 0.0;
-            phase2_single<WEIGHTED, SAT && !WEIGHTED>(P, W, ea, eb, rx, ry, rz, rn, thr.x, thr.y, tl, lane,
+            phase2_single<WEIGHTED, SAT && !WEIGHTED>(P, W, ea, eb, rx, ry, rz, thr.x, thr.y, tl, lane,
                                                       P.binpar[b].lo, P.binpar[b].hi, cnt_total, w_total, n_recheck, rwt);
             const unsigned tot = __reduce_add_sync(FULL, cnt_total);
             double wtot = 0.0;
@@ -557,10 +593,10 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
     int raw_cnt = -1, raw_slot = 0;  // the chunk in flight: rows (-1: none), slot of its item
     bool raw_first = false, raw_last = false;
 
-    float2 rx[HPL], ry[HPL], rz[HPL], rn[HPL];  // rows (2k, 2k+1) of the lane share one register pair
+    float2 rx[HPL], ry[HPL], rz[HPL];  // rows (2k, 2k+1) of the lane share one register pair, in the tile frame
     double rwt[YAWB_RPL];                       // their weights (weighted kernels only)
 #pragma unroll
-    for (int r = 0; r < HPL; ++r) rx[r] = ry[r] = rz[r] = rn[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < HPL; ++r) rx[r] = ry[r] = rz[r] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < YAWB_RPL; ++r) rwt[r] = 0.0;
     Tile tl{};
@@ -600,22 +636,23 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
                 const double c0 = F.c[0], c1 = F.c[1], c2 = F.c[2];
                 const double a0 = F.e1[0], a1 = F.e1[1], a2 = F.e1[2];
                 const double g0 = F.e2[0], g1 = F.e2[1], g2 = F.e2[2];
-                const double ou = ax.ou, ov = ax.ov, ot = ax.ot;
 #pragma unroll
                 for (int r = 0; r < YAWB_RPL; ++r) {
                     const int k = lane + 32 * r;
-                    float x = FAR, y = FAR, z = FAR, n = 3.0f * FAR * FAR;  // padding rows are never in range
+                    float x = PAD_ROW, y = PAD_ROW, z = PAD_ROW;  // padding rows: u = NaN, every form of the test rejects it
                     if (k < it.count) {
                         const double ex = dx[r] - c0, ey = dy[r] - c1, ez = dz[r] - c2;
-                        x = (float)(ex * a0 + ey * a1 + ez * a2 - ou);
-                        y = (float)(ex * g0 + ey * g1 + ez * g2 - ov);
-                        z = (float)(ex * c0 + ey * c1 + ez * c2 - ot);
-                        n = x * x + y * y + z * z;
+                        const double qx = ex * a0 + ey * a1 + ez * a2 - ax.O[0];
+                        const double qy = ex * g0 + ey * g1 + ez * g2 - ax.O[1];
+                        const double qz = ex * c0 + ey * c1 + ez * c2 - ax.O[2];
+                        x = (float)(ax.R[0] * qx + ax.R[1] * qy + ax.R[2] * qz);
+                        y = (float)(ax.R[3] * qx + ax.R[4] * qy + ax.R[5] * qz);
+                        z = (float)(ax.R[6] * qx + ax.R[7] * qy + ax.R[8] * qz);
                     } else if (WEIGHTED) {
                         rwt[r] = 0.0;
                     }
-                    if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; rn[r >> 1].y = n; }
-                    else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; rn[r >> 1].x = n; }
+                    if (r & 1) { rx[r >> 1].y = x; ry[r >> 1].y = y; rz[r >> 1].y = z; }
+                    else { rx[r >> 1].x = x; ry[r >> 1].x = y; rz[r >> 1].x = z; }
                 }
             }
             const int2 L = stream_convert<WEIGHTED>(S, c_slot, c_cnt, lane);
@@ -665,9 +702,9 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
         if (c_cnt >= 0) {
             if (n_seg > 0) {
                 if constexpr (!WEIGHTED && !MULTI && SAT)
-                    stream_test_sat(P, S, n_seg, rx, ry, rz, rn, tl, lane, n_recheck);
+                    stream_test_sat(P, S, n_seg, rx, ry, rz, tl, lane, n_recheck);
                 else
-                    stream_test_generic<WEIGHTED, MULTI, SAT>(P, S, n_seg, rx, ry, rz, rn, tl, lane, nsub, n_recheck, cur_pair, rwt);
+                    stream_test_generic<WEIGHTED, MULTI, SAT>(P, S, n_seg, rx, ry, rz, tl, lane, nsub, n_recheck, cur_pair, rwt);
             }
             if (c_last) {  // the item is complete: its counts go to the result of its patch pair
                 __syncwarp();

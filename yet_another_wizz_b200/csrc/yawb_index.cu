@@ -197,6 +197,7 @@ __global__ void k_make_frames(const double *__restrict__ sums, int n_patch, Patc
     f.e2[1] = f.c[2] * f.e1[0] - f.c[0] * f.e1[2];
     f.e2[2] = f.c[0] * f.e1[1] - f.c[1] * f.e1[0];
     f.radius = 0.0;
+    f.norm_dev = 0.0;
     f.umin = f.umax = f.vmin = f.vmax = 0.0;
     frames[p] = f;
 }
@@ -206,23 +207,26 @@ __device__ __forceinline__ double dec_double_dev(unsigned long long b) {
     return __longlong_as_double((long long)b);
 }
 
+constexpr int kBox = 6;  // per patch: min u, max u, min v, max v, max squared chord from the centre, max | |P|^2 - 1 |
+
 __global__ void k_init_box(unsigned long long *__restrict__ box, int n_patch) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_patch) return;
-    box[5 * p] = box[5 * p + 2] = ~0ull;
-    box[5 * p + 1] = box[5 * p + 3] = box[5 * p + 4] = 0ull;
+    box[kBox * p] = box[kBox * p + 2] = ~0ull;
+    box[kBox * p + 1] = box[kBox * p + 3] = box[kBox * p + 4] = box[kBox * p + 5] = 0ull;
 }
 
 __global__ void k_finish_frames(const unsigned long long *__restrict__ box, int n_patch,
                                 PatchFrame *__restrict__ frames) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_patch) return;
-    if (box[5 * p] == ~0ull) return;  // no rows: extents stay zero
-    frames[p].umin = dec_double_dev(box[5 * p]);
-    frames[p].umax = dec_double_dev(box[5 * p + 1]);
-    frames[p].vmin = dec_double_dev(box[5 * p + 2]);
-    frames[p].vmax = dec_double_dev(box[5 * p + 3]);
-    frames[p].radius = sqrt(dec_double_dev(box[5 * p + 4])) * (1.0 + 1e-12) + 1e-15;
+    if (box[kBox * p] == ~0ull) return;  // no rows: extents stay zero
+    frames[p].umin = dec_double_dev(box[kBox * p]);
+    frames[p].umax = dec_double_dev(box[kBox * p + 1]);
+    frames[p].vmin = dec_double_dev(box[kBox * p + 2]);
+    frames[p].vmax = dec_double_dev(box[kBox * p + 3]);
+    frames[p].radius = sqrt(dec_double_dev(box[kBox * p + 4])) * (1.0 + 1e-12) + 1e-15;
+    frames[p].norm_dev = dec_double_dev(box[kBox * p + 5]) * (1.0 + 1e-9) + 4.0e-16;
 }
 
 // per patch: (u, v) bounding box and max squared chord distance from the centre.  Same blocking as
@@ -232,11 +236,11 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
                                                          const double *__restrict__ z, const int *__restrict__ patch,
                                                          long long n, const PatchFrame *__restrict__ frames,
                                                          unsigned long long *__restrict__ box /*[n_patch][5]*/) {
-    __shared__ unsigned long long s_box[5][kThreads / 32];
+    __shared__ unsigned long long s_box[kBox][kThreads / 32];
     const long long row0 = (long long)blockIdx.x * kSumRows;
     const int p_blk = patch[row0];
     const PatchFrame f = frames[p_blk];
-    unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull;
+    unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull, nmax = 0ull;
     for (int k = threadIdx.x; k < kSumRows; k += blockDim.x) {
         const long long i = row0 + k;
         if (i >= n) break;
@@ -246,16 +250,23 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
         const unsigned long long eu = enc_double(dx * g.e1[0] + dy * g.e1[1] + dz * g.e1[2]);
         const unsigned long long ev = enc_double(dx * g.e2[0] + dy * g.e2[1] + dz * g.e2[2]);
         const unsigned long long ed = enc_double(dx * dx + dy * dy + dz * dz);
+        // how far the row is from the unit sphere: | |P|^2 - 1 |, evaluated without cancellation as |d . (P + c)|
+        // plus the deviation of the (normalised) centre itself
+        const unsigned long long en =
+            enc_double(fabs(dx * (x[i] + g.c[0]) + dy * (y[i] + g.c[1]) + dz * (z[i] + g.c[2])) +
+                       fabs(g.c[0] * g.c[0] + g.c[1] * g.c[1] + g.c[2] * g.c[2] - 1.0));
         if (p == p_blk) {
             umin = min(umin, eu); umax = max(umax, eu);
             vmin = min(vmin, ev); vmax = max(vmax, ev);
             dmax = max(dmax, ed);
+            nmax = max(nmax, en);
         } else {
-            atomicMin(&box[5 * p], eu);
-            atomicMax(&box[5 * p + 1], eu);
-            atomicMin(&box[5 * p + 2], ev);
-            atomicMax(&box[5 * p + 3], ev);
-            atomicMax(&box[5 * p + 4], ed);
+            atomicMin(&box[kBox * p], eu);
+            atomicMax(&box[kBox * p + 1], eu);
+            atomicMin(&box[kBox * p + 2], ev);
+            atomicMax(&box[kBox * p + 3], ev);
+            atomicMax(&box[kBox * p + 4], ed);
+            atomicMax(&box[kBox * p + 5], en);
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -264,18 +275,19 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
         vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
         vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
     }
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        s_box[0][w] = umin; s_box[1][w] = umax; s_box[2][w] = vmin; s_box[3][w] = vmax; s_box[4][w] = dmax;
+        s_box[0][w] = umin; s_box[1][w] = umax; s_box[2][w] = vmin; s_box[3][w] = vmax; s_box[4][w] = dmax; s_box[5][w] = nmax;
     }
     __syncthreads();
-    if (threadIdx.x < 5) {
+    if (threadIdx.x < kBox) {
         unsigned long long v = s_box[threadIdx.x][0];
         const bool is_min = threadIdx.x == 0 || threadIdx.x == 2;
         for (int k = 1; k < kThreads / 32; ++k) v = is_min ? min(v, s_box[threadIdx.x][k]) : max(v, s_box[threadIdx.x][k]);
-        if (is_min) atomicMin(&box[5 * p_blk + threadIdx.x], v);  // ~0 / 0 are the neutral initial values
-        else atomicMax(&box[5 * p_blk + threadIdx.x], v);
+        if (is_min) atomicMin(&box[kBox * p_blk + threadIdx.x], v);  // ~0 / 0 are the neutral initial values
+        else atomicMax(&box[kBox * p_blk + threadIdx.x], v);
     }
 }
 
@@ -660,7 +672,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         double *d_sums = scr.get<double>((size_t)P * 3);
         double *d_sumw = scr.get<double>((size_t)B * P);
         unsigned long long *d_counts = scr.get<unsigned long long>((size_t)B * P);
-        unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * 5);
+        unsigned long long *d_box = scr.get<unsigned long long>((size_t)P * kBox);
         YAWB_REQUIRE(d_sums && d_sumw && d_counts && d_box, "out of device memory (upload scratch)");
         YAWB_CUDA(cudaMemsetAsync(d_sums, 0, P * 3 * sizeof(double), st));
         YAWB_CUDA(cudaMemsetAsync(d_sumw, 0, (size_t)B * P * sizeof(double), st));

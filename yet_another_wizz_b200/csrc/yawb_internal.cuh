@@ -38,6 +38,7 @@ struct PatchFrame {
     double e2[3];
     double radius;                    // max chord distance of a patch point from c
     double umin, umax, vmin, vmax;    // bounding box of the patch in (u, v)
+    double norm_dev;                  // max | |P|^2 - 1 | over the rows: how far they are from the unit sphere (rounded up)
 };
 
 // ---- sky-cell grid of one patch (first-role index); identical for every z-bin ------------
