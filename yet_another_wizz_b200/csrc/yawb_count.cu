@@ -189,23 +189,37 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
     if (WEIGHTED) w_out = warp_sum(wsum);
 }
 
-// The same for an arbitrary span [e0, e1) of the list (the streaming kernel checks once per <= 16 candidates).
+// The same for a span [e0, e1) of at most 16 entries (the streaming kernel checks once per <= 16 candidates): lane t
+// takes row t & 7 of lane `src` against candidates t >> 3, t >> 3 + 4, ...; all operands of a lane's (up to four)
+// tests are requested before the first is used, so the warp pays the memory latency once.
 template <bool WEIGHTED>
 __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem<WEIGHTED> &S, int e0, int e1,
                                              const Tile &tl, int lane, int src, double lo, double hi,
                                              unsigned &cnt_out, double &w_out, unsigned &n_recheck) {
+    static_assert(YAWB_RPL == 8, "one lane per row of the flagged lane");
+    constexpr int Q = 4;  // 16 candidates x 8 rows / 32 lanes
     unsigned cnt = 0;
     double wsum = 0.0;
-    const int ne = e1 - e0;
-    for (int t = lane; t < ne * YAWB_RPL; t += 32) {
-        const int e = e0 + t % ne;
-        const int k = src + 32 * (t / ne);
-        if (k < tl.count) {
-            const int i = S.lidx[e], j = tl.start + k;
-            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+    const int k = src + 32 * (lane & 7);
+    const bool row_ok = k < tl.count;
+    const int j = tl.start + (row_ok ? k : 0);
+    const double bx = P.rx[j], by = P.ry[j], bz = P.rz[j];
+    double ax[Q], ay[Q], az[Q];
+    bool ok[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = e0 + (lane >> 3) + 4 * q;
+        ok[q] = row_ok && e < e1;
+        const int i = S.lidx[ok[q] ? e : e0];
+        ax[q] = P.sx[i]; ay[q] = P.sy[i]; az[q] = P.sz[i];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const double d2 = exact_d2(ax[q], ay[q], az[q], bx, by, bz);
+        if (ok[q]) {
             if (d2 > lo && d2 <= hi) {
                 cnt += 1;
-                if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
+                if (WEIGHTED) wsum += S.lw[e0 + (lane >> 3) + 4 * q] * (P.rw ? P.rw[j] : 1.0);
             }
             n_recheck += 1;
         }

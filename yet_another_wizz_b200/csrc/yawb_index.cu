@@ -300,6 +300,19 @@ __device__ __forceinline__ void local_uv(const PatchFrame &f, double X, double Y
     v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
 }
 
+// global sky-cell id of a row of a first-role index, or -1 for a row whose z-bin is out of range
+__device__ __forceinline__ long long key_first(double X, double Y, double Z, int b, int p, int n_bins,
+                                               const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids) {
+    if (b < 0 || b >= n_bins) return -1;
+    double u, v;
+    local_uv(frames[p], X, Y, Z, u, v);
+    const SGrid g = grids[p];
+    // clamp in double first: the product can exceed the int range for degenerate patches
+    int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_cu), 0.0), (double)(g.gu - 1));
+    int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_cv), 0.0), (double)(g.gv - 1));
+    return g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu;
+}
+
 template <typename K>
 __global__ void k_keys_first(const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ z, const int *__restrict__ bin,
@@ -311,19 +324,8 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
     keys += off;  // rows of the second catalog of a fused index follow those of the first
     vals += off;
     vals[i] = (unsigned)(off + i);
-    int b = bin ? bin[i] : 0;
-    if (b < 0 || b >= n_bins) {
-        keys[i] = (K)~(K)0;
-        return;
-    }
-    int p = patch[i];
-    double u, v;
-    local_uv(frames[p], x[i], y[i], z[i], u, v);
-    const SGrid g = grids[p];
-    // clamp in double first: the product can exceed the int range for degenerate patches
-    int iu = (int)fmin(fmax(floor((u - g.u0) * g.inv_cu), 0.0), (double)(g.gu - 1));
-    int iv = (int)fmin(fmax(floor((v - g.v0) * g.inv_cv), 0.0), (double)(g.gv - 1));
-    keys[i] = (K)(g.cell_base + ((long long)b * g.gv + iv) * g.gu + iu);
+    const long long key = key_first(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
+    keys[i] = key < 0 ? (K)~(K)0 : (K)key;
 }
 
 // Hilbert index of a cell on a 65536 x 65536 grid.  Unlike the Morton (Z) curve the Hilbert curve has
@@ -350,7 +352,25 @@ __device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y, int levels
     return d;
 }
 
-// key = (patch * n_bins + bin) << hbits | top `hbits` bits of the Hilbert index
+// key = (patch * n_bins + bin) << hbits | top `hbits` bits of the Hilbert index, or -1 for a row whose z-bin is out of range
+__device__ __forceinline__ long long key_second(double X, double Y, double Z, int b, int p, int n_bins, int hbits,
+                                                const PatchFrame *__restrict__ frames) {
+    if (b < 0 || b >= n_bins) return -1;
+    const PatchFrame &f = frames[p];
+    double u, v;
+    local_uv(f, X, Y, Z, u, v);
+    double su = f.umax > f.umin ? 65535.0 / (f.umax - f.umin) : 0.0;
+    double sv = f.vmax > f.vmin ? 65535.0 / (f.vmax - f.vmin) : 0.0;
+    // The bounding box of the patch is stretched over the whole Hilbert square: an isotropic mapping
+    // would leave part of the square empty, and wherever the curve leaves the populated part and
+    // re-enters elsewhere, 256 consecutive rows straddle the gap (measured: a few tiles per patch with
+    // patch-sized boxes, each worth several average work items -> a 13 % straggler tail).
+    int qu = min(max((int)((u - f.umin) * su), 0), 65535);
+    int qv = min(max((int)((v - f.vmin) * sv), 0), 65535);
+    return (long long)(((unsigned long long)((long long)p * n_bins + b) << hbits) |
+                       (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv, (hbits + 1) / 2) >> (32 - hbits)));
+}
+
 template <typename K>
 __global__ void k_keys_second(const double *__restrict__ x, const double *__restrict__ y,
                               const double *__restrict__ z, const int *__restrict__ bin,
@@ -360,25 +380,164 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     vals[i] = (unsigned)i;
-    int b = bin ? bin[i] : 0;
-    if (b < 0 || b >= n_bins) {
-        keys[i] = (K)~(K)0;
-        return;
+    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    keys[i] = key < 0 ? (K)~(K)0 : (K)key;
+}
+
+// ---- counting sort ------------------------------------------------------------------------------------
+// The sort keys are bounded and dense (sky-cell ids, (patch, z-bin, Hilbert cell) ids: about as many keys as rows),
+// so the rows are put in order by ONE histogram pass, an in-place exclusive scan of the key counts, and ONE
+// scatter pass that recomputes the key, takes the next free slot of its key with an atomic and writes the row's
+// payload straight to its final position.  The order of rows with the same key is arbitrary (it has no meaning:
+// pair counts are sums over all rows of a cell).  cur[k] holds the count of key k after the histogram, the first
+// slot of key k after the scan and the first slot of key k + 1 after the scatter -- which makes (0, cur[0],
+// cur[1], ...) the cell_start table of a first-role index without another pass.
+__global__ void k_hist_first(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                             const int *__restrict__ bin, const int *__restrict__ patch, long long n, int n_bins,
+                             const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
+                             int *__restrict__ cur) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long key = key_first(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
+    if (key >= 0) atomicAdd(&cur[key], 1);
+}
+
+__global__ void k_hist_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                              const int *__restrict__ bin, const int *__restrict__ patch, long long n, int n_bins,
+                              int hbits, const PatchFrame *__restrict__ frames, int *__restrict__ cur) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    if (key >= 0) atomicAdd(&cur[key], 1);
+}
+
+// in-place exclusive scan of `cur[0, n)`: block sums, scan of the block sums (one block), block scans + offsets
+constexpr int kScanPerThread = 16;
+constexpr int kScanBlock = kThreads * kScanPerThread;
+
+__global__ void __launch_bounds__(kThreads) k_scan_sums(const int *__restrict__ cur, long long n, int *__restrict__ sums) {
+    __shared__ int s_w[kThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanBlock;
+    int acc = 0;
+    for (int k = threadIdx.x; k < kScanBlock; k += kThreads)
+        if (base + k < n) acc += cur[base + k];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s_w[w];
+        sums[blockIdx.x] = t;
     }
-    int p = patch[i];
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tops(int *__restrict__ sums, int n_blocks) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const int v = i < n_blocks ? sums[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_w[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            s_w[threadIdx.x] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n_blocks) sums[i] = carry + s_w[threadIdx.x >> 5] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_w[31] + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scan_apply(int *__restrict__ cur, long long n, const int *__restrict__ sums) {
+    __shared__ int s_w[kThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanBlock + (long long)threadIdx.x * kScanPerThread;
+    int v[kScanPerThread];
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        v[k] = base + k < n ? cur[base + k] : 0;
+        tot += v[k];
+    }
+    int incl = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int run = sums[blockIdx.x] + incl - tot;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_w[w];
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        if (base + k < n) cur[base + k] = run;
+        run += v[k];
+    }
+}
+
+// second-role scatter: the row goes to the next free slot of its key
+__global__ void k_scatter_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                                 const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch,
+                                 long long n, int n_bins, int hbits, const PatchFrame *__restrict__ frames,
+                                 int *__restrict__ cur, double *__restrict__ ox, double *__restrict__ oy,
+                                 double *__restrict__ oz, double *__restrict__ ow) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X = x[i], Y = y[i], Z = z[i];
+    const long long key = key_second(X, Y, Z, bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    if (key < 0) return;
+    const int pos = atomicAdd(&cur[key], 1);
+    ox[pos] = X;
+    oy[pos] = Y;
+    oz[pos] = Z;
+    if (w) ow[pos] = w[i];
+}
+
+// first-role scatter (rows of one catalog; called twice for a fused index): the exact row plus its fixed-point
+// record in the frame of the patch (SGrid: origin and power-of-two scale)
+__global__ void k_scatter_first(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                                const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch,
+                                long long n, int n_bins, unsigned type_bit, const PatchFrame *__restrict__ frames,
+                                const SGrid *__restrict__ grids, int *__restrict__ cur, double *__restrict__ ox,
+                                double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ow,
+                                SRec *__restrict__ orec) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double X = x[i], Y = y[i], Z = z[i];
+    const int p = patch[i];
+    const long long key = key_first(X, Y, Z, bin ? bin[i] : 0, p, n_bins, frames, grids);
+    if (key < 0) return;
+    const int pos = atomicAdd(&cur[key], 1);
+    ox[pos] = X;
+    oy[pos] = Y;
+    oz[pos] = Z;
+    if (ow) ow[pos] = w ? w[i] : 1.0;  // fused index of a weighted and an unweighted catalog
     const PatchFrame &f = frames[p];
-    double u, v;
-    local_uv(f, x[i], y[i], z[i], u, v);
-    double su = f.umax > f.umin ? 65535.0 / (f.umax - f.umin) : 0.0;
-    double sv = f.vmax > f.vmin ? 65535.0 / (f.vmax - f.vmin) : 0.0;
-    // The bounding box of the patch is stretched over the whole Hilbert square: an isotropic mapping
-    // would leave part of the square empty, and wherever the curve leaves the populated part and
-    // re-enters elsewhere, 256 consecutive rows straddle the gap (measured: a few tiles per patch with
-    // patch-sized boxes, each worth several average work items -> a 13 % straggler tail).
-    int qu = min(max((int)((u - f.umin) * su), 0), 65535);
-    int qv = min(max((int)((v - f.vmin) * sv), 0), 65535);
-    keys[i] = (K)(((unsigned long long)((long long)p * n_bins + b) << hbits) |
-                  (unsigned long long)(hilbert16((unsigned)qu, (unsigned)qv, (hbits + 1) / 2) >> (32 - hbits)));
+    const SGrid &g = grids[p];
+    const double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
+    const double u = dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2];
+    const double v = dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2];
+    const double t = dx * f.c[0] + dy * f.c[1] + dz * f.c[2];
+    SRec r;
+    r.ku = (int)fmin(fmax(rint((u - g.u0) * g.qscale), 0.0), 2147483647.0);
+    r.kv = (int)fmin(fmax(rint((v - g.v0) * g.qscale), 0.0), 2147483647.0);
+    r.kt = (int)fmin(fmax(rint((t - g.t0) * g.qscale), 0.0), 2147483647.0);
+    r.aux = (unsigned)pos | type_bit;
+    orec[pos] = r;
 }
 
 __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const double *__restrict__ x,
@@ -538,6 +697,60 @@ int fi_alloc(FIndex *fi, T **ptr, size_t count) {
     if (count == 0) count = 1;
     if (yawb_dalloc(fi->ctx, (void **)ptr, count * sizeof(T), fi->ctx->stream)) return 1;
     fi->device_bytes += (int64_t)(count * sizeof(T));
+    return 0;
+}
+
+int exclusive_scan_inplace(yawb_ctx *ctx, Scratch &scr, int *cur, long long n) {
+    if (n <= 0) return 0;
+    const int n_blocks = (int)((n + kScanBlock - 1) / kScanBlock);
+    int *sums = scr.get<int>(n_blocks);
+    YAWB_REQUIRE(sums != nullptr, "out of device memory (scan scratch)");
+    k_scan_sums<<<n_blocks, kThreads, 0, ctx->stream>>>(cur, n, sums);
+    k_scan_tops<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks);
+    k_scan_apply<<<n_blocks, kThreads, 0, ctx->stream>>>(cur, n, sums);
+    return 0;
+}
+
+// keys up to this many go through the counting sort (one int per key); beyond, the radix sort
+constexpr long long kCountingSortMaxKeys = 1ll << 30;
+
+// first-role rows in sky-cell order by counting sort; fills cell_start (base + 1 entries)
+int build_first_counting(FIndex *fi, long long base) {
+    yawb_ctx *ctx = fi->ctx;
+    cudaStream_t st = ctx->stream;
+    const yawb_cat *a = fi->a, *b = fi->b;
+    Scratch scr(ctx, st);
+    int *cur = fi->cell_start + 1;  // see the note on cur[] above: cell_start = (0, cur[0], cur[1], ...) at the end
+    YAWB_CUDA(cudaMemsetAsync(fi->cell_start, 0, (size_t)(base + 1) * sizeof(int), st));
+    for (const yawb_cat *c : {a, b})
+        if (c && c->n_in > 0)
+            k_hist_first<<<blocks_for(c->n_in), kThreads, 0, st>>>(c->x, c->y, c->z, c->bin, c->patch, c->n_in, fi->n_bins,
+                                                                   fi->d_frames, fi->d_sgrid, cur);
+    if (exclusive_scan_inplace(ctx, scr, cur, base)) return 1;
+    for (const yawb_cat *c : {a, b})
+        if (c && c->n_in > 0)
+            k_scatter_first<<<blocks_for(c->n_in), kThreads, 0, st>>>(c->x, c->y, c->z, c->w, c->bin, c->patch, c->n_in,
+                                                                      fi->n_bins, c == b ? 0x80000000u : 0u, fi->d_frames,
+                                                                      fi->d_sgrid, cur, fi->sx, fi->sy, fi->sz, fi->sw,
+                                                                      fi->rec);
+    return 0;
+}
+
+// second-role rows in (patch, z-bin, Hilbert) order by counting sort
+int build_second_counting(yawb_cat *cat, int hbits, long long n_keys) {
+    yawb_ctx *ctx = cat->ctx;
+    cudaStream_t st = ctx->stream;
+    if (cat->n_in <= 0) return 0;
+    Scratch scr(ctx, st);
+    int *cur = scr.get<int>((size_t)n_keys);
+    YAWB_REQUIRE(cur != nullptr, "out of device memory (key counts)");
+    YAWB_CUDA(cudaMemsetAsync(cur, 0, (size_t)n_keys * sizeof(int), st));
+    k_hist_second<<<blocks_for(cat->n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, cat->n_in,
+                                                              cat->n_bins, hbits, cat->d_frames, cur);
+    if (exclusive_scan_inplace(ctx, scr, cur, n_keys)) return 1;
+    k_scatter_second<<<blocks_for(cat->n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin, cat->patch,
+                                                                 cat->n_in, cat->n_bins, hbits, cat->d_frames, cur, cat->rx,
+                                                                 cat->ry, cat->rz, cat->rw);
     return 0;
 }
 
@@ -867,7 +1080,12 @@ static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
     if (fi->weighted && fi_alloc(fi, &fi->sw, n)) return fail();
     if (fi_alloc(fi, &fi->cell_start, base + 1)) return fail();
     // 32-bit sort keys whenever the cell ids fit (they nearly always do): a third less radix-sort traffic
-    if (base < 0xffffffffll ? build_first_sorted<unsigned>(fi, base) : build_first_sorted<unsigned long long>(fi, base)) return fail();
+    // bounded, dense keys: counting sort (the radix sort only for grids with more cells than the key counts may take)
+    if (base <= kCountingSortMaxKeys && !getenv("YAWB_RADIX_SORT")) {
+        if (build_first_counting(fi, base)) return fail();
+    } else if (base < 0xffffffffll ? build_first_sorted<unsigned>(fi, base) : build_first_sorted<unsigned long long>(fi, base)) {
+        return fail();
+    }
     if (cudaGetLastError() != cudaSuccess) {
         yawb_set_error("first-role index build failed");
         return fail();
@@ -939,7 +1157,15 @@ int yawb_index_build_second(yawb_cat *cat) {
             m = std::max<long long>(m, cat->h_seg_off[sgm + 1] - cat->h_seg_off[sgm]);
         int k = 4;
         while (k < 16 && (1ll << (2 * k)) < m + m / 2) ++k;
-        if (hbits32 >= 16) {
+        // counting sort: one count per (patch, bin, Hilbert cell); the Hilbert resolution is capped so that there are
+        // at most about four keys per row (dense segments then hold a few rows per Hilbert cell, in arbitrary order)
+        int kc = k;
+        const long long key_budget = std::max<long long>(4 * cat->n_in, 1 << 16);
+        while (kc > 1 && (((long long)P * B) << (2 * kc)) > key_budget) --kc;
+        const long long n_keys = ((long long)P * B) << (2 * kc);
+        if (n_keys <= kCountingSortMaxKeys && !getenv("YAWB_RADIX_SORT")) {
+            if (build_second_counting(cat, 2 * kc, n_keys)) return 1;
+        } else if (hbits32 >= 16) {
             if (build_second_sorted<unsigned>(cat, std::min(hbits32, 2 * k))) return 1;
         } else {
             if (build_second_sorted<unsigned long long>(cat, 32)) return 1;
