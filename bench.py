@@ -136,12 +136,28 @@ def make_workload(name: str, scale: float = 1.0, field: int = 0):
                 plan=plan, naive=naive, t_catalogs=t_cat, t_host_prep=t_prep, n_patch=nx * ny)
 
 
-def subset_patches(a: dict, keep: np.ndarray) -> dict:
-    """host arrays of one catalog restricted to the patches in `keep` (all others become empty)"""
+def subset_patches(a: dict, keep: np.ndarray, fractions: dict | None = None, reach: list | None = None) -> dict:
+    """host arrays of one catalog restricted to the patches in `keep` (all others become empty); `fractions`:
+    patch -> (f0, f1), the share of a patch that is split between two ranks (`sharding.split_rows`); `reach`:
+    list of (centre, chord radius) -- only rows inside one of these caps are kept"""
+    from yet_another_wizz_b200.sharding import split_rows
+
     off = a["patch_off"]
     sizes = np.zeros(len(off) - 1, dtype=np.int64)
-    sizes[keep] = np.diff(off)[keep]
-    sel = np.concatenate([np.arange(off[p], off[p + 1]) for p in keep]) if len(keep) else np.empty(0, dtype=np.int64)
+    parts = []
+    for p in keep:
+        rows = np.arange(off[p], off[p + 1])
+        if fractions is not None and p in fractions and fractions[p] != (0.0, 1.0):
+            rows = rows[split_rows(a["xyz"][off[p]:off[p + 1]], *fractions[p])]
+        if reach is not None and len(rows):
+            x = a["xyz"][rows]
+            near = np.zeros(len(rows), dtype=bool)
+            for c, r in reach:
+                near |= ((x - c) ** 2).sum(axis=1) <= r * r
+            rows = rows[near]
+        sizes[p] = len(rows)
+        parts.append(rows)
+    sel = np.concatenate(parts) if parts else np.empty(0, dtype=np.int64)
     return dict(
         xyz=np.ascontiguousarray(a["xyz"][sel]), patch_off=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
         weights=None if a["weights"] is None else np.ascontiguousarray(a["weights"][sel]),
@@ -402,7 +418,7 @@ def run_reference_arm(args):
 def run_gpu_arm(args):
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200.pipeline import count_cross_pipelined
-    from yet_another_wizz_b200.sharding import assign_patches_contiguous, pair_costs
+    from yet_another_wizz_b200.sharding import assign_patch_fractions, pair_costs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -448,11 +464,23 @@ def run_gpu_arm(args):
         costs = pair_costs(pi, pj, n1, n2, radii1=np.asarray(wl["cats"]["ref_rand"].get_radii().data))
         patch_cost = np.bincount(pj, weights=costs, minlength=wl["n_patch"])
         centers_xyz = wl["cats"]["unk_rand"].get_centers().to_3d()
-        my_patches = assign_patches_contiguous(patch_cost, centers_xyz, part_world)[part_rank]
-        own = np.flatnonzero(np.isin(pj, my_patches))
+        share = assign_patch_fractions(patch_cost, centers_xyz, part_world)[part_rank]
+        fractions = {p: (f0, f1) for p, f0, f1 in share}
+        own = np.flatnonzero(np.isin(pj, np.array(sorted(fractions), dtype=np.int64)))
         need = dict(second=np.unique(pj[own]), first=np.unique(pi[own]))
-        arrays = {k: subset_patches(a, need["first" if k in ("ref", "ref_rand") else "second"])
-                  for k, a in arrays.items()}
+        second = {k: subset_patches(arrays[k], need["second"], fractions) for k in ("unk", "unk_rand")}
+        # of a first-catalog patch only the rows within reach of this rank's second-catalog rows can form a pair:
+        # chord to the centre of an own patch <= its radius + the largest search radius (triangle inequality)
+        reach = []
+        rmax_chord = float(np.sqrt(np.max(plan.r2)))
+        for p in need["second"]:
+            rows = np.concatenate([a["xyz"][a["patch_off"][p]:a["patch_off"][p + 1]] for a in second.values()])
+            if len(rows):
+                c = rows.sum(axis=0)
+                c /= np.linalg.norm(c)
+                reach.append((c, (np.sqrt(((rows - c) ** 2).sum(axis=1).max()) + rmax_chord) * (1.0 + 1e-9) + 1e-12))
+        first = {k: subset_patches(arrays[k], need["first"], reach=reach) for k in ("ref", "ref_rand")}
+        arrays = {**first, **second}
     opi, opj = pi[own], pj[own]
 
     # pinned host staging of the inputs (what a caller holding host buffers hands to the C ABI)
@@ -675,8 +703,8 @@ def run_gpu_arm(args):
             parallelism=("1 GPU" if world == 1 else
                          f"{world} fields of {wl['n_patch']} patches, one per GPU (no patch links between fields), one NCCL "
                          f"reduce of the count tensor inside the timed region" if weak else
-                         f"the ONE job split over {world} GPUs: second-catalog patches dealt as compact equal-cost groups, each rank "
-                         f"holds only the rows of its patches and of the first-catalog patches linked to them; ONE NCCL sum-reduce "
+                         f"the ONE job split over {world} GPUs: second-catalog patches dealt as compact equal-cost groups (the patch a cut falls into is shared by two ranks), each rank "
+                         f"holds only the rows of its patches and the rows of the linked first-catalog patches within reach of them; ONE NCCL sum-reduce "
                          f"of the (4, n_pairs, n_bins, n_sub) count tensor to rank 0 inside the timed region"),
             fused_counts=bool(fuse),
         ),
@@ -713,9 +741,10 @@ def run_gpu_arm(args):
                    f"x 4 count types): tree build {cpu['t_build']:.2f}s + count {cpu['t_count']:.2f}s",
             extrapolated_full_job_s=t_cpu * total_naive / max(cpu["naive"], 1),
         )
-        line["parity_checked_pairs"] = check_parity(wl, results, cpu)
-        line["parity"] = ("GPU counts of the full job == CPU reference algorithm (scipy cKDTree) on every sampled patch pair, "
-                          + ("1e-12 relative" if any_weighted or wl["config"].scales.rweight is not None else "bit-exact"))
+        if not args.emulate_share:  # one rank's share alone holds partial counts of the patches it shares
+            line["parity_checked_pairs"] = check_parity(wl, results, cpu)
+            line["parity"] = ("GPU counts of the full job == CPU reference algorithm (scipy cKDTree) on every sampled patch pair, "
+                              + ("1e-12 relative" if any_weighted or wl["config"].scales.rweight is not None else "bit-exact"))
     emit(line)
     eng.close()
     if dist is not None:

@@ -81,3 +81,31 @@ def test_contiguous_patch_groups():
     groups = assign_patches_contiguous(costs, xyz, 4)
     loads = np.array([costs[g].sum() for g in groups])
     assert loads.max() - loads.min() <= 2 * costs.max()
+
+
+def test_patch_fractions_balance_exactly():
+    """shares cut at k / world of the cost: every patch is covered once, loads are equal up to the slivers that
+    snap to a patch boundary; the rows of a shared patch are split into disjoint compact strips"""
+    from yet_another_wizz_b200.sharding import assign_patch_fractions, split_rows
+
+    rng = np.random.default_rng(3)
+    ra, dec = rng.uniform(0.0, 0.7, 64), rng.uniform(-0.2, 0.2, 64)
+    xyz = np.column_stack([np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)])
+    costs = rng.uniform(0.5, 1.5, 64)
+    costs[5] = 0.0  # an empty patch still belongs to exactly one rank
+    for world in (1, 2, 3, 8):
+        shares = assign_patch_fractions(costs, xyz, world)
+        cover = np.zeros(64)
+        for share in shares:
+            for p, f0, f1 in share:
+                assert 0.0 <= f0 < f1 <= 1.0
+                cover[p] += f1 - f0
+        np.testing.assert_allclose(cover, 1.0, atol=1e-12)
+        loads = np.array([sum(costs[p] * (f1 - f0) for p, f0, f1 in share) for share in shares])
+        assert loads.max() - loads.min() <= 2 * 0.03 * costs.max() + 1e-9
+        assert sum(1 for share in shares for p, f0, f1 in share if (f0, f1) != (0.0, 1.0)) <= 2 * (world - 1)
+    pts = rng.normal(size=(1000, 3))
+    pts /= np.linalg.norm(pts, axis=1)[:, None]
+    a, b, c = split_rows(pts, 0.0, 0.25), split_rows(pts, 0.25, 0.6), split_rows(pts, 0.6, 1.0)
+    assert sorted(np.concatenate([a, b, c]).tolist()) == list(range(1000))
+    assert (len(a), len(b), len(c)) == (250, 350, 400)

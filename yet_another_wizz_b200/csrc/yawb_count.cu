@@ -43,7 +43,7 @@ constexpr int CHUNK = YAWB_CHUNK;       // candidates between consistency checks
 #define YAWB_CCAP 160
 #endif
 #ifndef YAWB_CCAP_SMALL
-#define YAWB_CCAP_SMALL 48
+#define YAWB_CCAP_SMALL 24
 #endif
 #ifndef YAWB_SMALL_JOB_ITEMS
 #define YAWB_SMALL_JOB_ITEMS 30
@@ -744,7 +744,15 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     if (a.n_items == 0) return 0;
 
     // planner: self-contained work items (patch-diagonal ones first)
-    const long long cap_heavy = a.cap_heavy, cap_light = a.cap_light;
+    // a small job (a rank's share of a strong-scaling run) is cut into more, shorter items, so that the warps of
+    // the persistent grid finish together: below YAWB_SMALL_JOB_ITEMS flat (pair, tile) combinations per warp the
+    // items hold at most YAWB_CCAP_SMALL runs (swept on an eighth of C3: 16 / 24 / 32 / 48 / 72 / 112 runs ->
+    // count kernels 1.02 / 1.01 / 1.05 / 1.10 / 1.18 / 1.17 ms); the lists grow by the same factor
+    const long long warps = (long long)ctx->sms * STREAM_CTAS * STREAM_WARPS;
+    int ccap = a.n_items < YAWB_SMALL_JOB_ITEMS * warps ? YAWB_CCAP_SMALL : YAWB_CCAP;
+    if (const char *e = getenv("YAWB_CCAP_RUNTIME")) ccap = std::max(8, std::min(YAWB_CCAP, atoi(e)));
+    const long long cap_scale = (YAWB_CCAP + ccap - 1) / ccap;
+    const long long cap_heavy = a.cap_heavy * cap_scale, cap_light = a.cap_light * cap_scale;
     Item *d_items = nullptr;
     if (yawb_dalloc(ctx, (void **)&d_items, (size_t)(cap_heavy + cap_light) * sizeof(Item), ctx->stream)) return 1;
     P.items_heavy = d_items;
@@ -758,11 +766,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         Q.n_pairs = a.n_pairs; Q.n_flat = a.n_items; Q.binpar = a.d_binpar; Q.n_bins = a.n_bins; Q.rmax_all = a.rmax_all;
         Q.heavy = d_items; Q.light = d_items + cap_heavy; Q.cap_heavy = cap_heavy; Q.cap_light = cap_light;
         Q.counters = ctx->d_counters;
-        // a small job (a rank's share of a strong-scaling run) is cut into more, shorter items, so that the warps of
-        // the persistent grid finish together: YAWB_SMALL_JOB_ITEMS flat (pair, tile) combinations per warp
-        const long long warps = (long long)ctx->sms * STREAM_CTAS * STREAM_WARPS;
-        Q.ccap = a.n_items < YAWB_SMALL_JOB_ITEMS * warps ? YAWB_CCAP_SMALL : YAWB_CCAP;
-        if (const char *e = getenv("YAWB_CCAP_RUNTIME")) Q.ccap = std::max(8, std::min(YAWB_CCAP, atoi(e)));
+        Q.ccap = ccap;
         k_plan<<<(unsigned)((a.n_items + 255) / 256), 256, 0, ctx->stream>>>(Q);
         *launches += 1;
     }
