@@ -90,6 +90,13 @@ int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const
  * are 5 % of the bytes of a z-binned catalog as int32, 1.3 % as bytes. */
 int yawb_upload_catalog_u8(yawb_ctx *ctx, const double *xyz, const double *w, const uint8_t *zbin,
                            const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);
+/* Same with the raw redshifts: the rows are assigned to z-bins ON THE DEVICE, with the arithmetic of
+ * np.digitize(z, edges, right = closed_right) - 1 (src/yaw/catalog/trees.py:408-414, Binning edges of
+ * src/yaw/binning.py): bin b holds edges[b] < z <= edges[b + 1] (closed_right) or edges[b] <= z < edges[b + 1];
+ * rows outside the binning (and NaN) are dropped.  Comparisons only, so the ids are identical to numpy's.
+ *   z       n redshifts;   edges   n_bins + 1 strictly increasing doubles (copied by the call) */
+int yawb_upload_catalog_z(yawb_ctx *ctx, const double *xyz, const double *w, const double *z, const double *edges,
+                          int closed_right, const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out);
 int yawb_free_catalog(yawb_cat *cat);
 
 /* Build (or rebuild) the device-side index for a role ahead of time; otherwise
@@ -104,6 +111,16 @@ int yawb_catalog_info(const yawb_cat *cat, int64_t *n_rows, int64_t *device_byte
  * unbinned catalog): AngularTree.sum_weights collected by process_patch_pair,
  * src/yaw/correlation/measurements.py:123-124, trees.py:225-234. */
 int yawb_sum_weights(const yawb_cat *cat, double *out);
+
+/* Patch meta data computed on the device from the uploaded rows (all rows of the patch, whatever their z-bin):
+ * the quantities of Metadata.compute, src/yaw/catalog/patch.py:104-147.
+ *   center_xyz[n_patch][3]  normalised mean direction (the reference converts it to RA / Dec)
+ *   radius_chord[n_patch]   largest chord distance of a row from the centre, rounded up by 1e-12 relative
+ *                           (the reference's radius is the angle 2 asin(chord / 2))
+ *   num_records[n_patch]    rows of the patch
+ * Any pointer may be NULL.  The sums run in a different order than numpy's, so centres agree to ~1e-15, not
+ * bit for bit; the reference-exact meta data of this package's Catalog stays on the host. */
+int yawb_patch_metadata(const yawb_cat *cat, double *center_xyz, double *radius_chord, int64_t *num_records);
 
 /* Count pairs for a list of linked patch pairs.
  *

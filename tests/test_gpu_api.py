@@ -99,6 +99,17 @@ def test_staging_cache_engine():
         eng.close()
 
 
+def test_crosscorrelate_with_device_digitize(engine):
+    """z-bins assigned on the device (`Engine.device_digitize`, yawb_upload_catalog_z) give the reference's counts"""
+    g = golden_io.load("cross_unweighted")
+    engine.device_digitize = True
+    try:
+        corrs = golden_cases.run_cross(g, engine)
+    finally:
+        engine.device_digitize = False
+    golden_cases.check_corrfunc(g, "cross", corrs, ("dd", "dr", "rd", "rr"), exact=True)
+
+
 def test_default_engine_and_stats():
     import yet_another_wizz_b200 as yb
     from yet_another_wizz_b200 import measurements

@@ -329,6 +329,64 @@ def test_rows_off_the_unit_sphere_stay_exact(engine, dev):
     assert_array_equal(ci, want.astype(np.int64))
 
 
+@pytest.mark.parametrize("closed", ["right", "left"])
+def test_device_digitize_matches_numpy(engine, closed):
+    """yawb_upload_catalog_z: z-bins assigned on the device == np.digitize on the host (reference
+    src/yaw/catalog/trees.py:408-414), values on the edges, outside the binning and NaN included: the per-(bin, patch)
+    row counts and every pair count agree with an upload of host-assigned ids"""
+    rng = np.random.default_rng(21)
+    n = 40000
+    ra = rng.uniform(0.0, 0.03, n); dec = np.arcsin(rng.uniform(-0.015, 0.015, n))
+    xyz = oracle.radec_to_xyz(ra, dec)
+    edges = np.linspace(0.1, 1.0, 8)
+    z = rng.uniform(0.0, 1.1, n)
+    z[:200] = rng.choice(edges, 200)  # exactly on an edge
+    z[200:210] = np.nan
+    order = np.argsort(ra > 0.015, kind="stable")
+    xyz, z = xyz[order], z[order]
+    off = np.array([0, int((ra <= 0.015).sum()), n], dtype=np.int64)
+    ids = np.digitize(z, edges, right=(closed == "right")).astype(np.int32) - 1
+    a = engine.upload_catalog(xyz, off, zbin=ids, n_bins=len(edges) - 1)
+    b = engine.upload_catalog(xyz, off, redshifts=z, edges=edges, closed=closed)
+    assert_array_equal(a.sum_weights(), b.sum_weights())
+    assert a.info()[0] == b.info()[0] < n
+    unk = engine.upload_catalog(xyz, off)
+    pi = np.array([0, 0, 1, 1], dtype=np.int32); pj = np.array([0, 1, 0, 1], dtype=np.int32)
+    r2 = oracle.chord_sq_edges(np.array([2e-4, 2e-3]))
+    ca, _, _ = engine.count(a, unk, pi, pj, r2)
+    cb, _, _ = engine.count(b, unk, pi, pj, r2)
+    assert_array_equal(ca, cb)
+    assert ca.sum() > 1e5
+    for c in (a, b, unk):
+        c.free()
+
+
+def test_device_patch_metadata(engine):
+    """yawb_patch_metadata == the reference's Metadata.compute (src/yaw/catalog/patch.py:104-147): centre = normalised
+    mean direction, radius = largest angular distance from it, rows per patch"""
+    rng = np.random.default_rng(22)
+    sizes = [5000, 0, 12000, 1]
+    ras, decs = [], []
+    for k, m in enumerate(sizes):
+        ras.append(rng.uniform(0.1 * k, 0.1 * k + 0.08, m)); decs.append(rng.uniform(-0.3, -0.25 + 0.02 * k, m))
+    ra, dec = np.concatenate(ras), np.concatenate(decs)
+    xyz = oracle.radec_to_xyz(ra, dec)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cat = engine.upload_catalog(xyz, off)
+    center, radius, num = cat.patch_metadata()
+    assert_array_equal(num, sizes)
+    for p, m in enumerate(sizes):
+        if m == 0:
+            continue
+        rows = xyz[off[p]:off[p + 1]]
+        c = rows.mean(axis=0)
+        c /= np.linalg.norm(c)
+        np.testing.assert_allclose(center[p], c, rtol=0, atol=1e-14)
+        want = 2.0 * np.arcsin(np.sqrt(((rows - c) ** 2).sum(axis=1).max()) / 2.0)
+        np.testing.assert_allclose(radius[p], want, rtol=1e-9, atol=1e-13)
+    cat.free()
+
+
 def test_device_memory_is_recycled(engine):
     """upload / count / free cycles of varying size: the context's caching allocator reuses its blocks, the
     footprint on the device stops growing after the first cycles"""

@@ -226,11 +226,12 @@ int yawb_host_free(void *ptr) {
 }
 
 static int upload_common(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin, const uint8_t *zbin8,
-                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+                         const double *zred, const double *edges, int closed_right, const int64_t *patch_off,
+                         int n_patch, int n_bins, yawb_cat **out) {
     YAWB_REQUIRE(ctx && out && patch_off, "yawb_upload_catalog: NULL argument");
     *out = nullptr;
     YAWB_REQUIRE(n_patch >= 1 && n_patch <= 65535, "n_patch must be in 1..65535 (got %d)", n_patch);
-    const bool binned = zbin != nullptr || zbin8 != nullptr;
+    const bool binned = zbin != nullptr || zbin8 != nullptr || zred != nullptr;
     if (!binned) n_bins = 1;
     YAWB_REQUIRE(n_bins >= 1 && n_bins <= 4096, "n_bins must be in 1..4096 (got %d)", n_bins);
     YAWB_REQUIRE(!zbin8 || n_bins <= 254, "byte-sized z-bin ids need n_bins <= 254 (got %d)", n_bins);
@@ -250,7 +251,13 @@ static int upload_common(yawb_ctx *ctx, const double *xyz, const double *w, cons
     cat->n_bins = n_bins;
     cat->binned = binned;
     cat->weighted = w != nullptr;
-    if (yawb_index_upload(ctx, cat, xyz, w, zbin8, zbin, patch_off)) {
+    cat->h_rows_per_patch.resize(n_patch);
+    for (int p = 0; p < n_patch; ++p) cat->h_rows_per_patch[p] = patch_off[p + 1] - patch_off[p];
+    if (zred) {
+        cat->h_edges.assign(edges, edges + n_bins + 1);
+        cat->closed_right = closed_right != 0;
+    }
+    if (yawb_index_upload(ctx, cat, xyz, w, zbin8, zbin, zred, patch_off)) {
         yawb_index_free(cat, true);
         delete cat;
         return 1;
@@ -261,12 +268,21 @@ static int upload_common(yawb_ctx *ctx, const double *xyz, const double *w, cons
 
 int yawb_upload_catalog(yawb_ctx *ctx, const double *xyz, const double *w, const int32_t *zbin,
                         const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
-    return upload_common(ctx, xyz, w, zbin, nullptr, patch_off, n_patch, n_bins, out);
+    return upload_common(ctx, xyz, w, zbin, nullptr, nullptr, nullptr, 1, patch_off, n_patch, n_bins, out);
 }
 
 int yawb_upload_catalog_u8(yawb_ctx *ctx, const double *xyz, const double *w, const uint8_t *zbin,
                            const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
-    return upload_common(ctx, xyz, w, nullptr, zbin, patch_off, n_patch, n_bins, out);
+    return upload_common(ctx, xyz, w, nullptr, zbin, nullptr, nullptr, 1, patch_off, n_patch, n_bins, out);
+}
+
+int yawb_upload_catalog_z(yawb_ctx *ctx, const double *xyz, const double *w, const double *z, const double *edges,
+                          int closed_right, const int64_t *patch_off, int n_patch, int n_bins, yawb_cat **out) {
+    YAWB_REQUIRE(z && edges, "yawb_upload_catalog_z: redshifts or edges are NULL");
+    YAWB_REQUIRE(n_bins >= 1, "yawb_upload_catalog_z: n_bins must be >= 1 (got %d)", n_bins);
+    for (int b = 0; b < n_bins; ++b)
+        YAWB_REQUIRE(edges[b] < edges[b + 1], "yawb_upload_catalog_z: z-bin edges must increase (edge %d)", b);
+    return upload_common(ctx, xyz, w, nullptr, nullptr, z, edges, closed_right, patch_off, n_patch, n_bins, out);
 }
 
 int yawb_free_catalog(yawb_cat *cat) {
@@ -316,6 +332,19 @@ int yawb_sum_weights(const yawb_cat *cat, double *out) {
     YAWB_REQUIRE(cat && out, "yawb_sum_weights: NULL argument");
     if (yawb_cat_finalize(const_cast<yawb_cat *>(cat))) return 1;
     std::memcpy(out, cat->h_sumw.data(), cat->h_sumw.size() * sizeof(double));
+    return 0;
+}
+
+int yawb_patch_metadata(const yawb_cat *cat, double *center_xyz, double *radius_chord, int64_t *num_records) {
+    YAWB_REQUIRE(cat != nullptr, "yawb_patch_metadata: NULL catalog");
+    if (yawb_cat_finalize(const_cast<yawb_cat *>(cat))) return 1;
+    for (int p = 0; p < cat->n_patch; ++p) {
+        const PatchFrame &f = cat->h_frames[p];
+        if (center_xyz)
+            for (int d = 0; d < 3; ++d) center_xyz[3 * p + d] = f.c[d];
+        if (radius_chord) radius_chord[p] = f.radius;
+        if (num_records) num_records[p] = cat->h_rows_per_patch[p];
+    }
     return 0;
 }
 

@@ -720,6 +720,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
 
 // -----------------------------------------------------------------------------------------------
 int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
+    YawbRange range("yawb:plan+count");
     const FIndex *fi = a.c1;
     FastParams P{};
     P.sx = fi->sx; P.sy = fi->sy; P.sz = fi->sz; P.sw = fi->sw; P.rec = fi->rec;
@@ -815,6 +816,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
 }
 
 int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches) {
+    YawbRange range("yawb:count_exact");
     ExactParams P{};
     P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw; P.s_seg = a.c1_cat->d_seg_off;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw; P.r_seg = a.c2->d_seg_off;

@@ -90,6 +90,24 @@ __global__ void k_widen_bins(const unsigned char *__restrict__ b8, long long n, 
 }
 
 // AoS (n x 3) -> SoA, plus the patch id of every row from the row offsets
+// z-bin of every row from its redshift: np.digitize(z, edges, right) - 1 (src/yaw/catalog/trees.py:408-414).
+// right: bin b holds edges[b] < z <= edges[b + 1], i.e. (number of edges strictly below z) - 1; otherwise
+// edges[b] <= z < edges[b + 1], i.e. (number of edges <= z) - 1.  Comparisons only: identical to numpy's ids;
+// NaN compares false everywhere and lands in bin -1 (numpy: past the last bin), dropped either way.
+__global__ void k_digitize(const double *__restrict__ z, long long n, const double *__restrict__ edges, int n_edges,
+                           int right, int *__restrict__ bin) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = z[i];
+    int lo = 0, hi = n_edges;  // number of edges e with e < v (right) or e <= v
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double e = edges[mid];
+        if (right ? (e < v) : (e <= v)) lo = mid + 1; else hi = mid;
+    }
+    bin[i] = lo - 1;
+}
+
 __global__ void k_deinterleave(const double *__restrict__ xyz, const long long *__restrict__ patch_off,
                                int n_patch, long long n, double *__restrict__ x, double *__restrict__ y,
                                double *__restrict__ z, int *__restrict__ patch) {
@@ -818,7 +836,8 @@ int build_second_sorted(yawb_cat *cat, int hbits) {
 static constexpr size_t kCopyChunk = (size_t)YAWB_COPY_CHUNK_MB << 20;
 
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w, const uint8_t *zbin8,
-                      const int32_t *zbin, const int64_t *patch_off) {
+                      const int32_t *zbin, const double *zred, const int64_t *patch_off) {
+    YawbRange range("yawb:upload");
     const long long n = cat->n_in;
     const int P = cat->n_patch, B = cat->n_bins;
     // Only allocations and host-to-device copies are issued here, all on the context's copy stream, which
@@ -831,8 +850,9 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
         dev_alloc(cat, &cat->patch, n, st))
         return 1;
     if (w && dev_alloc(cat, &cat->w, n, st)) return 1;
-    if ((zbin || zbin8) && dev_alloc(cat, &cat->bin, n, st)) return 1;
+    if ((zbin || zbin8 || zred) && dev_alloc(cat, &cat->bin, n, st)) return 1;
     if (zbin8 && dev_alloc(cat, &cat->d_stage_bin8, n, st)) return 1;
+    if (zred && dev_alloc(cat, &cat->d_stage_z, n, st)) return 1;
     if (dev_alloc(cat, &cat->d_frames, P, st) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1, st)) return 1;
     if (dev_alloc(cat, &cat->d_stage_xyz, (size_t)n * 3, st) || dev_alloc(cat, &cat->d_stage_poff, P + 1, st)) return 1;
 
@@ -851,6 +871,7 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     if (w && n > 0) YAWB_CUDA(h2d(cat->w, w, n * sizeof(double)));
     if (zbin && n > 0) YAWB_CUDA(h2d(cat->bin, zbin, n * sizeof(int32_t)));
     if (zbin8 && n > 0) YAWB_CUDA(h2d(cat->d_stage_bin8, zbin8, n));
+    if (zred && n > 0) YAWB_CUDA(h2d(cat->d_stage_z, zred, n * sizeof(double)));
     YAWB_CUDA(cudaEventCreateWithFlags(&cat->ev_meta, cudaEventDisableTiming));
     YAWB_CUDA(cudaEventRecord(cat->ev_meta, st));
     YAWB_CUDA(cudaGetLastError());
@@ -875,6 +896,8 @@ static void release_staging(yawb_cat *cat) {
 // their results to pinned staging, then the host-side row tables.
 int yawb_cat_finalize(yawb_cat *cat) {
     if (cat->finalized) return 0;
+    YawbRange range("yawb:finalize");
+    if (cat->finalized) return 0;
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
     const long long n = cat->n_in;
@@ -895,6 +918,13 @@ int yawb_cat_finalize(yawb_cat *cat) {
             k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_xyz, cat->d_stage_poff, P, n, cat->x, cat->y,
                                                                cat->z, cat->patch);
             if (cat->d_stage_bin8) k_widen_bins<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_bin8, n, cat->bin);
+            if (cat->d_stage_z) {
+                double *d_edges = scr.get<double>(cat->h_edges.size());
+                YAWB_REQUIRE(d_edges != nullptr, "out of device memory (z-bin edges)");
+                if (yawb_h2d_small(ctx, d_edges, cat->h_edges.data(), cat->h_edges.size() * sizeof(double))) return 1;
+                k_digitize<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_z, n, d_edges, (int)cat->h_edges.size(),
+                                                               cat->closed_right ? 1 : 0, cat->bin);
+            }
             const bool use_smem = B <= kSumMaxBins;
             const size_t smem =
                 4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (cat->w ? sizeof(double) : 0)) : 0);
@@ -910,6 +940,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         dev_free(cat, cat->d_stage_xyz, (size_t)n * 3);
         dev_free(cat, cat->d_stage_poff, P + 1);
         dev_free(cat, cat->d_stage_bin8, (size_t)n);
+        dev_free(cat, cat->d_stage_z, (size_t)n);
 
         // meta data (frames, row counts, sums of weights) through pinned staging
         const size_t b_frames = (((size_t)std::max(P, 1) * sizeof(PatchFrame)) + 63) & ~(size_t)63;
@@ -1002,6 +1033,7 @@ static int findex_frames(FIndex *fi) {
 }
 
 static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
+    YawbRange range(b ? "yawb:index_first_fused" : "yawb:index_first");
     *out = nullptr;
     if (yawb_cat_finalize(a)) return 1;
     if (b && yawb_cat_finalize(b)) return 1;
@@ -1139,6 +1171,7 @@ void yawb_findex_drop_fused(yawb_ctx *ctx, const yawb_cat *cat) {
 int yawb_index_build_second(yawb_cat *cat) {
     if (yawb_cat_finalize(cat)) return 1;
     if (cat->has_rtiles) return 0;
+    YawbRange range("yawb:index_second");
     yawb_ctx *ctx = cat->ctx;
     cudaStream_t st = ctx->stream;
     const long long n = cat->n;

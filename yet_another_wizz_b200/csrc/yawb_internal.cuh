@@ -9,7 +9,17 @@
 #include <cstdio>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "yawb.h"
+
+// NVTX range over a scope (header-only NVTX 3: a no-op unless a profiler is attached)
+struct YawbRange {
+    explicit YawbRange(const char *name) { nvtxRangePushA(name); }
+    ~YawbRange() { nvtxRangePop(); }
+    YawbRange(const YawbRange &) = delete;
+    YawbRange &operator=(const YawbRange &) = delete;
+};
 
 void yawb_set_error(const char *fmt, ...);
 
@@ -153,6 +163,9 @@ struct yawb_cat {
     double *d_stage_xyz = nullptr;            // interleaved rows as uploaded, until yawb_cat_finalize()
     long long *d_stage_poff = nullptr;        // row offsets of the patches, until yawb_cat_finalize()
     unsigned char *d_stage_bin8 = nullptr;    // z-bin ids uploaded as bytes, widened by yawb_cat_finalize()
+    double *d_stage_z = nullptr;              // raw redshifts, digitized by yawb_cat_finalize()
+    std::vector<double> h_edges;              // ... against these z-bin edges
+    bool closed_right = true;
     unsigned long long *hp_counts = nullptr;  // pinned staging [n_bins][n_patch]
     double *hp_sumw = nullptr;                // pinned staging [n_bins][n_patch]
     PatchFrame *hp_frames = nullptr;          // pinned staging [n_patch]
@@ -169,6 +182,7 @@ struct yawb_cat {
     PatchFrame *d_frames = nullptr;
     // per (bin, patch): number of rows and sum of weights, host copies
     std::vector<long long> h_counts;   // [n_bins][n_patch]
+    std::vector<long long> h_rows_per_patch;  // [n_patch] rows uploaded, whatever their z-bin
     std::vector<double> h_sumw;        // [n_bins][n_patch]
     std::vector<int> h_seg_off;        // [(n_patch * n_bins) + 1], patch-major, bin-minor
     int *d_seg_off = nullptr;
@@ -210,7 +224,7 @@ struct FIndex {
 
 // index construction (yawb_index.cu)
 int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const double *w, const uint8_t *zbin8,
-                      const int32_t *zbin, const int64_t *patch_off);
+                      const int32_t *zbin, const double *zred, const int64_t *patch_off);
 // device memory (yawb_alloc.cu): stream-aware caching allocator on top of cudaMalloc
 int yawb_dalloc(yawb_ctx *ctx, void **out, size_t bytes, cudaStream_t st);
 void yawb_dfree(yawb_ctx *ctx, void *ptr, cudaStream_t st);

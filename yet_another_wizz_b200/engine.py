@@ -40,6 +40,16 @@ class DeviceCatalog:
         _lib.check(self.engine.lib.yawb_sum_weights(self._h, _ptr(out)))
         return out
 
+    def patch_metadata(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """`(center_xyz (n_patch, 3), radius (n_patch,) in radian, num_records (n_patch,))` computed on the device
+        from the uploaded rows: the quantities of the reference's `Metadata.compute`
+        (`src/yaw/catalog/patch.py:104-147`; centres agree with numpy's to ~1e-15, the sums run in another order)."""
+        center = np.empty((self.n_patch, 3), dtype=np.float64)
+        chord = np.empty(self.n_patch, dtype=np.float64)
+        num = np.empty(self.n_patch, dtype=np.int64)
+        _lib.check(self.engine.lib.yawb_patch_metadata(self._h, _ptr(center), _ptr(chord), _ptr(num)))
+        return center, 2.0 * np.arcsin(np.minimum(chord / 2.0, 1.0)), num
+
     def info(self) -> tuple[int, int]:
         n, nbytes = c_int64(), c_int64()
         _lib.check(self.engine.lib.yawb_catalog_info(self._h, byref(n), byref(nbytes)))
@@ -84,6 +94,9 @@ class Engine:
         costs ~1.5 s per GB once."""
         self.staging = bool(int(os.environ.get("YAWB_STAGING", "0"))) if staging is None else bool(staging)
         self.staging_min_rows = 1_000_000  # smaller catalogs are not worth a page-locked detour
+        # YAWB_DEVICE_DIGITIZE=1: measurement calls ship raw redshifts and the device assigns the z-bins
+        # (`yawb_upload_catalog_z`); default: byte-sized ids assigned on the host (1/8 of the PCIe traffic)
+        self.device_digitize = bool(int(os.environ.get("YAWB_DEVICE_DIGITIZE", "0")))
         self.lib = _lib.load()
         h = c_void_p()
         _lib.check(self.lib.yawb_create(int(device), byref(h)))
@@ -110,7 +123,13 @@ class Engine:
         weights: np.ndarray | None = None,
         zbin: np.ndarray | None = None,
         n_bins: int = 1,
+        redshifts: np.ndarray | None = None,
+        edges: np.ndarray | None = None,
+        closed: str = "right",
     ) -> DeviceCatalog:
+        """`zbin` (+ `n_bins`): z-bin ids assigned on the host; or `redshifts` + `edges` (+ `closed`): the raw
+        redshifts travel and the device assigns the bins with np.digitize's comparisons (`yawb_upload_catalog_z`,
+        reference `src/yaw/catalog/trees.py:408-414`)."""
         xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
         patch_off = np.ascontiguousarray(patch_off, dtype=np.int64)
         n = len(xyz)
@@ -130,16 +149,31 @@ class Engine:
             if len(zbin) != n:
                 raise ValueError("shape of 'xyz' and 'zbin' does not match")
         h = c_void_p()
-        _lib.check(
-            upload(
-                self._h, _ptr(xyz), _ptr(weights), _ptr(zbin), _ptr(patch_off),
-                len(patch_off) - 1, int(n_bins), byref(h),
+        if redshifts is not None:
+            if zbin is not None or edges is None:
+                raise ValueError("pass either 'zbin' or 'redshifts' with 'edges'")
+            redshifts = np.ascontiguousarray(redshifts, dtype=np.float64)
+            edges = np.ascontiguousarray(edges, dtype=np.float64)
+            if len(redshifts) != n:
+                raise ValueError("shape of 'xyz' and 'redshifts' does not match")
+            n_bins = len(edges) - 1
+            _lib.check(
+                self.lib.yawb_upload_catalog_z(
+                    self._h, _ptr(xyz), _ptr(weights), _ptr(redshifts), _ptr(edges), int(str(closed) == "right"),
+                    _ptr(patch_off), len(patch_off) - 1, int(n_bins), byref(h),
+                )
             )
-        )
-        cat = DeviceCatalog(self, h, len(patch_off) - 1, int(n_bins) if zbin is not None else 1,
-                            zbin is not None, weights is not None)
+        else:
+            _lib.check(
+                upload(
+                    self._h, _ptr(xyz), _ptr(weights), _ptr(zbin), _ptr(patch_off),
+                    len(patch_off) - 1, int(n_bins), byref(h),
+                )
+            )
+        binned = zbin is not None or redshifts is not None
+        cat = DeviceCatalog(self, h, len(patch_off) - 1, int(n_bins) if binned else 1, binned, weights is not None)
         # the upload is asynchronous: keep the host buffers alive as long as the handle
-        cat._keepalive = (xyz, weights, zbin, patch_off)
+        cat._keepalive = (xyz, weights, zbin, redshifts, patch_off)
         self._catalogs.add(cat)
         return cat
 

@@ -91,7 +91,7 @@ def _angles_per_bin(config) -> tuple[np.ndarray, np.ndarray]:
 
 
 def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = False,
-                           workers: int | None = None, alloc=None) -> dict:
+                           workers: int | None = None, alloc=None, device_digitize: bool = False) -> dict:
     """Host preparation of one catalog for the C ABI: load every patch once, convert to unit
     vectors with the reference's formula (`AngularCoordinates.to_3d`: numpy cos / sin in double, so the
     device sees the doubles the reference's trees hold), digitise the redshifts (`trees.py:408-414`).
@@ -116,9 +116,15 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     n = int(off[-1])
     xyz = alloc((n, 3), np.float64)
     ws = alloc(n, np.float64) if has_w else None
-    # z-bin ids travel as bytes when they fit (255 = outside the binning): a quarter of the PCIe traffic
+    # z-bin ids travel as bytes when they fit (255 = outside the binning): a quarter of the PCIe traffic;
+    # with `device_digitize` the raw redshifts travel instead and the device assigns the bins (same comparisons
+    # as np.digitize, `yawb_upload_catalog_z`): 8 bytes per row over PCIe against a host pass over the redshifts
     small_bins = binning is not None and len(binning) <= 254
-    zb = alloc(n, np.uint8 if small_bins else np.int32) if binning is not None else None
+    zb = zr = None
+    if binning is not None and device_digitize:
+        zr = alloc(n, np.float64)
+    elif binning is not None:
+        zb = alloc(n, np.uint8 if small_bins else np.int32)
 
     def fill(pid: int) -> None:
         ra, dec, weights, redshifts, kappa_vals = _patch_rows(catalog[pid])
@@ -135,7 +141,9 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
             ws[s:e] = kappa_vals if weights is None else kappa_vals * weights
         elif has_w:
             ws[s:e] = weights
-        if binning is not None:
+        if zr is not None:
+            zr[s:e] = redshifts
+        elif binning is not None:
             ids = binning.digitize(redshifts)  # -1 below, len(binning) above the binning
             if small_bins:
                 ids[ids < 0] = 255
@@ -151,14 +159,18 @@ def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = Fa
     else:
         for pid in patch_ids:
             fill(pid)
-    return dict(xyz=xyz, patch_off=off, weights=ws, zbin=zb, n_bins=len(binning) if binning is not None else 1)
+    out = dict(xyz=xyz, patch_off=off, weights=ws, zbin=zb, n_bins=len(binning) if binning is not None else 1)
+    if zr is not None:
+        out.update(redshifts=zr, edges=np.asarray(binning.edges, dtype=np.float64), closed=str(binning.closed))
+    return out
 
 
 def _prepare_for(engine, catalog, binning: Binning | None, kappa: bool) -> dict:
     # opt-in (`Engine(staging=True)`): large catalogs are prepared straight into the engine's page-locked
     # staging cache; the copy is then asynchronous and overlaps with the preparation of the next catalog
     staged = getattr(engine, "staging", False) and sum(catalog.get_num_records()) >= engine.staging_min_rows
-    return prepare_catalog_arrays(catalog, binning, kappa=kappa, alloc=engine.staging_empty if staged else None)
+    return prepare_catalog_arrays(catalog, binning, kappa=kappa, alloc=engine.staging_empty if staged else None,
+                                  device_digitize=bool(getattr(engine, "device_digitize", False)))
 
 
 def upload_catalog(engine, catalog, binning: Binning | None, *, kappa: bool = False):
