@@ -112,6 +112,17 @@ int yawb_catalog_info(const yawb_cat *cat, int64_t *n_rows, int64_t *device_byte
  * src/yaw/correlation/measurements.py:123-124, trees.py:225-234. */
 int yawb_sum_weights(const yawb_cat *cat, double *out);
 
+/* Jackknife by subtraction on the device: the sum over all patch pairs and its leave-one-patch-out samples,
+ *     total[b] = sum_k v[k][b],   samples[p][b] = total[b] - sum_{k : i_k == p or j_k == p} v[k][b]
+ * -- SampledPatchSum of src/yaw/correlation/paircounts.py:113-141 (total - row_p - column_p + diagonal_p) written
+ * on the list of linked patch pairs instead of the dense (n_patch x n_patch) array.
+ *   values[n_pairs][n_bins]  per-pair, per-z-bin counts or products of sums of weights (host)
+ *   total[n_bins], samples[n_patch][n_bins]   (host)
+ * Integer-valued inputs give exact results (sums of integers below 2^53 do not depend on the order); others
+ * agree with numpy's einsum to rounding. */
+int yawb_jackknife(yawb_ctx *ctx, const double *values, const int32_t *pair_i, const int32_t *pair_j, int n_pairs,
+                   int n_patch, int n_bins, double *total, double *samples);
+
 /* Patch meta data computed on the device from the uploaded rows (all rows of the patch, whatever their z-bin):
  * the quantities of Metadata.compute, src/yaw/catalog/patch.py:104-147.
  *   center_xyz[n_patch][3]  normalised mean direction (the reference converts it to RA / Dec)

@@ -387,6 +387,34 @@ def test_device_patch_metadata(engine):
     cat.free()
 
 
+def test_device_jackknife_matches_einsum(engine):
+    """yawb_jackknife == SampledPatchSum of the reference (src/yaw/correlation/paircounts.py:113-141: total - row -
+    column + diagonal), exactly for integer counts, to rounding for weighted sums"""
+    from yet_another_wizz_b200.binning import Binning
+    from yet_another_wizz_b200.paircounts import PatchedCounts, _sample_patch_sum
+
+    rng = np.random.default_rng(31)
+    n_patch, n_bins = 24, 7
+    binning = Binning(np.linspace(0.1, 1.0, n_bins + 1))
+    dense = np.zeros((n_bins, n_patch, n_patch))
+    link = rng.random((n_patch, n_patch)) < 0.25
+    np.fill_diagonal(link, True)
+    dense[:, link] = rng.integers(0, 10**9, size=(n_bins, int(link.sum())))
+    counts = PatchedCounts(binning, dense, auto=False)
+    want = _sample_patch_sum(binning, dense)
+    got = counts.sample_patch_sum(engine)
+    assert_array_equal(got.data, want.data)
+    assert_array_equal(got.samples, want.samples)
+    dense_w = dense * rng.uniform(0.5, 1.5, size=dense.shape)
+    want = _sample_patch_sum(binning, dense_w)
+    got = PatchedCounts(binning, dense_w, auto=False).sample_patch_sum(engine)
+    np.testing.assert_allclose(got.data, want.data, rtol=1e-13)
+    np.testing.assert_allclose(got.samples, want.samples, rtol=1e-12)
+    # no linked pairs at all
+    total, samples = engine.sample_patch_sum(np.zeros((0, n_bins)), np.zeros(0, np.int32), np.zeros(0, np.int32), n_patch)
+    assert not total.any() and samples.shape == (n_patch, n_bins) and not samples.any()
+
+
 def test_device_memory_is_recycled(engine):
     """upload / count / free cycles of varying size: the context's caching allocator reuses its blocks, the
     footprint on the device stops growing after the first cycles"""

@@ -27,7 +27,7 @@ EXPORTS = (
     "yawb_build_index", "yawb_drop_index", "yawb_catalog_info", "yawb_sum_weights", "yawb_count",
     "yawb_host_alloc", "yawb_host_free", "yawb_sync", "yawb_version", "yawb_device_sms",
     "yawb_timer_start", "yawb_timer_stop", "yawb_assign_patches", "yawb_upload_catalog_u8", "yawb_count2",
-    "yawb_upload_catalog_z", "yawb_patch_metadata",
+    "yawb_upload_catalog_z", "yawb_patch_metadata", "yawb_jackknife",
 )
 
 
@@ -88,6 +88,7 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, POINTER(c_void_p),
     ]
     lib.yawb_patch_metadata.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.yawb_jackknife.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.yawb_free_catalog.argtypes = [c_void_p]
     lib.yawb_build_index.argtypes = [c_void_p, c_int, POINTER(c_double)]
     lib.yawb_drop_index.argtypes = [c_void_p]

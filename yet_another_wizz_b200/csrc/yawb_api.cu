@@ -87,6 +87,25 @@ __global__ void k_assign_patches(const double *__restrict__ xyz, long long n, co
     if (i < n) out[i] = arg;
 }
 
+// one thread per (pair, bin): the value joins the total and the "removed with patch p" sums of both patches
+__global__ void k_jackknife(const double *__restrict__ v, const int *__restrict__ pi, const int *__restrict__ pj,
+                            int n_pairs, int n_bins, double *__restrict__ total, double *__restrict__ removed) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)n_pairs * n_bins) return;
+    const int k = (int)(t / n_bins), b = (int)(t % n_bins);
+    const double x = v[t];
+    if (x == 0.0) return;
+    atomicAdd(&total[b], x);
+    const int i = pi[k], j = pj[k];
+    atomicAdd(&removed[(size_t)i * n_bins + b], x);
+    if (j != i) atomicAdd(&removed[(size_t)j * n_bins + b], x);
+}
+__global__ void k_jackknife_finish(const double *__restrict__ total, int n_patch, int n_bins, double *__restrict__ samples) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_patch * n_bins) return;
+    samples[t] = total[t % n_bins] - samples[t];
+}
+
 extern "C" {
 
 int yawb_assign_patches(yawb_ctx *ctx, const double *xyz, int64_t n, const double *centers_xyz, int n_centers,
@@ -332,6 +351,52 @@ int yawb_sum_weights(const yawb_cat *cat, double *out) {
     YAWB_REQUIRE(cat && out, "yawb_sum_weights: NULL argument");
     if (yawb_cat_finalize(const_cast<yawb_cat *>(cat))) return 1;
     std::memcpy(out, cat->h_sumw.data(), cat->h_sumw.size() * sizeof(double));
+    return 0;
+}
+
+int yawb_jackknife(yawb_ctx *ctx, const double *values, const int32_t *pair_i, const int32_t *pair_j, int n_pairs,
+                   int n_patch, int n_bins, double *total, double *samples) {
+    YAWB_REQUIRE(ctx && total && samples, "yawb_jackknife: NULL argument");
+    YAWB_REQUIRE(n_pairs >= 0 && n_patch >= 1 && n_bins >= 1, "yawb_jackknife: bad sizes");
+    YAWB_REQUIRE(n_pairs == 0 || (values && pair_i && pair_j), "yawb_jackknife: NULL input");
+    for (int k = 0; k < n_pairs; ++k)
+        YAWB_REQUIRE(pair_i[k] >= 0 && pair_i[k] < n_patch && pair_j[k] >= 0 && pair_j[k] < n_patch,
+                     "yawb_jackknife: patch pair %d out of range", k);
+    YAWB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nv = (size_t)n_pairs * n_bins, ns = (size_t)n_patch * n_bins;
+    double *d_v = nullptr, *d_out = nullptr;  // d_out = [total | samples]
+    int *d_p = nullptr;
+    auto cleanup = [&]() {
+        for (void *p : {(void *)d_v, (void *)d_out, (void *)d_p})
+            if (p) yawb_dfree(ctx, p, st);
+    };
+    if (yawb_dalloc(ctx, (void **)&d_v, std::max<size_t>(nv, 1) * sizeof(double), st) ||
+        yawb_dalloc(ctx, (void **)&d_out, (n_bins + ns) * sizeof(double), st) ||
+        yawb_dalloc(ctx, (void **)&d_p, std::max<size_t>(2 * (size_t)n_pairs, 1) * sizeof(int), st)) {
+        cleanup();
+        return 1;
+    }
+    cudaError_t e = cudaMemsetAsync(d_out, 0, (n_bins + ns) * sizeof(double), st);
+    if (e == cudaSuccess && n_pairs > 0) {
+        e = cudaMemcpyAsync(d_v, values, nv * sizeof(double), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_p, pair_i, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_p + n_pairs, pair_j, n_pairs * sizeof(int), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            k_jackknife<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(d_v, d_p, d_p + n_pairs, n_pairs, n_bins, d_out, d_out + n_bins);
+    }
+    if (e == cudaSuccess) {
+        k_jackknife_finish<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(d_out, n_patch, n_bins, d_out + n_bins);
+        e = cudaMemcpyAsync(total, d_out, n_bins * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(samples, d_out + n_bins, ns * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) {
+        yawb_set_error("yawb_jackknife: %s", cudaGetErrorString(e));
+        return 1;
+    }
     return 0;
 }
 

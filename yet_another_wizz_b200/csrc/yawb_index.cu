@@ -1125,7 +1125,9 @@ static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
     if (fi_alloc(fi, &fi->cell_start, base + 1)) return fail();
     // 32-bit sort keys whenever the cell ids fit (they nearly always do): a third less radix-sort traffic
     // bounded, dense keys: counting sort (the radix sort only for grids with more cells than the key counts may take)
-    if (base <= kCountingSortMaxKeys && !getenv("YAWB_RADIX_SORT")) {
+    // (weighted rows keep the stable radix sort: the order of the rows of a cell is the order their weights are
+    // summed in, and a counting sort's atomics would make the last bits of the sums vary from run to run)
+    if (base <= kCountingSortMaxKeys && !fi->weighted && !getenv("YAWB_RADIX_SORT")) {
         if (build_first_counting(fi, base)) return fail();
     } else if (base < 0xffffffffll ? build_first_sorted<unsigned>(fi, base) : build_first_sorted<unsigned long long>(fi, base)) {
         return fail();
@@ -1208,7 +1210,7 @@ int yawb_index_build_second(yawb_cat *cat) {
         const long long key_budget = std::max<long long>(4 * cat->n_in, 1 << 16);
         while (kc > 1 && (((long long)P * B) << (2 * kc)) > key_budget) --kc;
         const long long n_keys = ((long long)P * B) << (2 * kc);
-        if (n_keys <= kCountingSortMaxKeys && !getenv("YAWB_RADIX_SORT")) {
+        if (n_keys <= kCountingSortMaxKeys && !cat->weighted && !getenv("YAWB_RADIX_SORT")) {
             if (build_second_counting(cat, 2 * kc, n_keys)) return 1;
         } else if (hbits32 >= 16) {
             if (build_second_sorted<unsigned>(cat, std::min(hbits32, 2 * k))) return 1;

@@ -177,6 +177,21 @@ class Engine:
         self._catalogs.add(cat)
         return cat
 
+    def sample_patch_sum(self, values: np.ndarray, pair_i: np.ndarray, pair_j: np.ndarray,
+                         n_patch: int) -> tuple[np.ndarray, np.ndarray]:
+        """Sum over the linked patch pairs and its leave-one-patch-out jackknife samples on the device
+        (`yawb_jackknife`): `values` is `(n_pairs, n_bins)`; returns `(total (n_bins,), samples (n_patch, n_bins))`,
+        the `data` / `samples` of the reference's `SampledPatchSum` (`src/yaw/correlation/paircounts.py:113-141`)."""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+        n_pairs, n_bins = values.shape
+        total = np.empty(n_bins, dtype=np.float64)
+        samples = np.empty((int(n_patch), n_bins), dtype=np.float64)
+        _lib.check(self.lib.yawb_jackknife(self._h, _ptr(values), _ptr(pair_i), _ptr(pair_j), int(n_pairs), int(n_patch),
+                                           int(n_bins), _ptr(total), _ptr(samples)))
+        return total, samples
+
     def count(
         self,
         cat1: DeviceCatalog,

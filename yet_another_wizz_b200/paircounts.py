@@ -38,7 +38,12 @@ class SampledPatchSum:
     samples: np.ndarray  # (n_patch, n_bins)
 
 
-def _sample_patch_sum(binning: Binning, array: np.ndarray) -> SampledPatchSum:
+def _sample_patch_sum(binning: Binning, array: np.ndarray, engine=None) -> SampledPatchSum:
+    """`engine`: run the sums on the device over the non-zero patch pairs (`Engine.sample_patch_sum`, yawb_jackknife)"""
+    if engine is not None:
+        ids1, ids2 = np.nonzero(np.any(array, axis=0))
+        total, samples = engine.sample_patch_sum(np.moveaxis(array[:, ids1, ids2], 0, -1), ids1, ids2, array.shape[1])
+        return SampledPatchSum(binning, total, samples)
     # jackknife by subtraction: total - row_i - column_i + diagonal_i
     total = np.einsum("bij->b", array)
     samples = total[None, :] - np.einsum("bij->jb", array) - np.einsum("bij->ib", array) + np.einsum("bii->ib", array)
@@ -82,8 +87,8 @@ class PatchedSumWeights:
             np.einsum("bii->bi", array)[:] *= 0.5
         return array
 
-    def sample_patch_sum(self) -> SampledPatchSum:
-        return _sample_patch_sum(self.binning, self.get_array())
+    def sample_patch_sum(self, engine=None) -> SampledPatchSum:
+        return _sample_patch_sum(self.binning, self.get_array(), engine)
 
     def to_hdf(self, dest) -> None:
         write_version_tag(dest)
@@ -135,8 +140,8 @@ class PatchedCounts:
     def set_patch_pair(self, patch_id1: int, patch_id2: int, counts_binned: np.ndarray) -> None:
         self.counts[:, patch_id1, patch_id2] = counts_binned
 
-    def sample_patch_sum(self) -> SampledPatchSum:
-        return _sample_patch_sum(self.binning, self.get_array())
+    def sample_patch_sum(self, engine=None) -> SampledPatchSum:
+        return _sample_patch_sum(self.binning, self.get_array(), engine)
 
     def to_hdf(self, dest) -> None:
         write_version_tag(dest)
@@ -202,8 +207,8 @@ class NormalisedCounts:
         norm = self._weights.sample_patch_sum().data
         return self._counts.get_array() / norm[:, np.newaxis, np.newaxis]
 
-    def sample_patch_sum(self) -> SampledPatchSum:
-        c, w = self._counts.sample_patch_sum(), self._weights.sample_patch_sum()
+    def sample_patch_sum(self, engine=None) -> SampledPatchSum:
+        c, w = self._counts.sample_patch_sum(engine), self._weights.sample_patch_sum(engine)
         return SampledPatchSum(self.binning, c.data / w.data, c.samples / w.samples)
 
     def to_hdf(self, dest) -> None:
@@ -243,8 +248,8 @@ class NormalisedScalarCounts:
             return NotImplemented
         return self._counts == other._counts and self._weights == other._weights
 
-    def sample_patch_sum(self) -> SampledPatchSum:
-        c, w = self._counts.sample_patch_sum(), self._weights.sample_patch_sum()
+    def sample_patch_sum(self, engine=None) -> SampledPatchSum:
+        c, w = self._counts.sample_patch_sum(engine), self._weights.sample_patch_sum(engine)
         return SampledPatchSum(self.binning, c.data / w.data, c.samples / w.samples)
 
     def to_hdf(self, dest) -> None:
