@@ -30,11 +30,12 @@ def wrap(obj, name):
     def g(*a, **k):
         t = time.perf_counter()
         r = f(*a, **k)
-        events.append((name, 1e3 * (t - T0[0]), 1e3 * (time.perf_counter() - t), r[2] if name == "count" else None))
+        events.append((name, 1e3 * (t - T0[0]), 1e3 * (time.perf_counter() - t), r[2] if name in ("count", "count2") else None))
         return r
     setattr(obj, name, g)
 wrap(eng, "upload_catalog")
 wrap(eng, "count")
+wrap(eng, "count2")
 if SYNC_AFTER_UPLOAD:
     _orig_slices = pipeline.upload_patch_slices
     def _slices(engine, arrays, n):

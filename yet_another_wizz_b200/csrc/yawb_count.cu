@@ -50,8 +50,11 @@ constexpr int CHUNK = YAWB_CHUNK;       // candidates between consistency checks
 #endif
 
 struct FastParams {
-    // first-role index (one catalog, or two fused)
-    const double *sx, *sy, *sz, *sw;
+    // first-role index (one catalog, or two fused).  The exact rows of a candidate are only needed by the FP64
+    // recheck (~0.15 % of the tests): they are read from the catalog's own rows (cx / cy / cz of catalog 0 or 1
+    // of the index) through the row id in SRec::aux -- the index holds no sorted copy of the doubles.
+    const double *cx[2], *cy[2], *cz[2];
+    const double *sw;
     const SRec *rec;
     const int *cell_start;
     const SGrid *sgrid;
@@ -102,6 +105,17 @@ __device__ __forceinline__ BinRows bin_rows(const SGrid &G, double ulo, double u
     r.nrows = max(hi - lo, 0);
     return r;
 }
+
+// Exact row of a staged candidate: aux = row of its catalog | catalog bit (SRec::aux).
+#define YAWB_CAND_ROW(P, aux, X, Y, Z)                                         \
+    do {                                                                       \
+        const int cand_t_ = (int)((unsigned)(aux) >> 31);                      \
+        const int cand_i_ = (int)((unsigned)(aux) & 0x7fffffffu);              \
+        const double *cand_x_ = cand_t_ ? (P).cx[1] : (P).cx[0];               \
+        const double *cand_y_ = cand_t_ ? (P).cy[1] : (P).cy[0];               \
+        const double *cand_z_ = cand_t_ ? (P).cz[1] : (P).cz[0];               \
+        X = cand_x_[cand_i_]; Y = cand_y_[cand_i_]; Z = cand_z_[cand_i_];      \
+    } while (0)
 
 // The reference's comparison value: products rounded separately, summed x -> y -> z.
 __device__ __forceinline__ double exact_d2(double ax, double ay, double az, double bx, double by, double bz) {
@@ -177,7 +191,9 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
         const int k = src + 32 * (t / CHUNK);
         if (e < e1 && k < tl.count) {
             const int i = S.lidx[e], j = tl.start + k;
-            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+            double cxx, cyy, czz;
+            YAWB_CAND_ROW(P, i, cxx, cyy, czz);
+            const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
             if (d2 > lo && d2 <= hi) {
                 cnt += 1;
                 if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
@@ -211,7 +227,7 @@ __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem
         const int e = e0 + (lane >> 3) + 4 * q;
         ok[q] = row_ok && e < e1;
         const int i = S.lidx[ok[q] ? e : e0];
-        ax[q] = P.sx[i]; ay[q] = P.sy[i]; az[q] = P.sz[i];
+        YAWB_CAND_ROW(P, i, ax[q], ay[q], az[q]);
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -345,7 +361,9 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
         const int k = src + 32 * (t / CUM_CHUNK);
         if (e < e1 && k < tl.count) {
             const int i = lidx[e], j = tl.start + k;
-            const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+            double cxx, cyy, czz;
+            YAWB_CAND_ROW(P, i, cxx, cyy, czz);
+            const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
 #pragma unroll
             for (int g = 0; g < G; ++g)
                 if (k0 + g < ne && d2 <= ed[k0 + g]) cnt[g] += 1;
@@ -477,7 +495,9 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
                 const int j = tl.start + min(lane + 32 * r, tl.count - 1);
                 if (!(gap > eps)) {
                     const int i = S.lidx[e];
-                    const double d2 = exact_d2(P.sx[i], P.sy[i], P.sz[i], P.rx[j], P.ry[j], P.rz[j]);
+                    double cxx, cyy, czz;
+                    YAWB_CAND_ROW(P, i, cxx, cyy, czz);
+                    const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
                     k = edges_below(ed, ne, d2);
                     n_recheck += 1;
                 }
@@ -636,7 +656,9 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
 
 // ---- exact all-pairs kernel -------------------------------------------------------------------
 struct ExactParams {
-    const double *sx, *sy, *sz, *sw;
+    const double *cx, *cy, *cz;  // rows of the first catalog as uploaded; SRec::aux of a sorted row is its row there
+    const SRec *rec;
+    const double *sw;
     const int *s_seg;  // [(P * B1) + 1]
     const double *rx, *ry, *rz, *rw;
     const int *r_seg;  // [(P * B2) + 1]
@@ -679,7 +701,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
         const bool live = i < a1;
         double ax = 0, ay = 0, az = 0, aw = 1.0;
         if (live) {
-            ax = P.sx[i]; ay = P.sy[i]; az = P.sz[i];
+            const int row = (int)(P.rec[i].aux & 0x7fffffffu);
+            ax = P.cx[row]; ay = P.cy[row]; az = P.cz[row];
             if (WEIGHTED && P.sw) aw = P.sw[i];
         }
         for (int jc = c0; jc < c1; jc += EX_THREADS) {
@@ -723,7 +746,9 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     YawbRange range("yawb:plan+count");
     const FIndex *fi = a.c1;
     FastParams P{};
-    P.sx = fi->sx; P.sy = fi->sy; P.sz = fi->sz; P.sw = fi->sw; P.rec = fi->rec;
+    P.cx[0] = fi->a->x; P.cy[0] = fi->a->y; P.cz[0] = fi->a->z;
+    P.cx[1] = fi->b ? fi->b->x : fi->a->x; P.cy[1] = fi->b ? fi->b->y : fi->a->y; P.cz[1] = fi->b ? fi->b->z : fi->a->z;
+    P.sw = fi->sw; P.rec = fi->rec;
     P.cell_start = fi->cell_start; P.sgrid = fi->d_sgrid; P.sframe = fi->d_frames; P.n_types = fi->n_types;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
     P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
@@ -818,7 +843,8 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
 int yawb_launch_count_exact(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     YawbRange range("yawb:count_exact");
     ExactParams P{};
-    P.sx = a.c1->sx; P.sy = a.c1->sy; P.sz = a.c1->sz; P.sw = a.c1->sw; P.s_seg = a.c1_cat->d_seg_off;
+    P.cx = a.c1_cat->x; P.cy = a.c1_cat->y; P.cz = a.c1_cat->z; P.rec = a.c1->rec;
+    P.sw = a.c1->sw; P.s_seg = a.c1_cat->d_seg_off;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw; P.r_seg = a.c2->d_seg_off;
     P.b1 = a.c1_cat->n_bins; P.b2 = a.c2->n_bins;
     P.pair_i = a.d_pair_i; P.pair_j = a.d_pair_j;

@@ -402,7 +402,7 @@ __device__ __forceinline__ int2 stream_convert(const StreamSmem<WEIGHTED> &S, in
             const double sz = ax.R[6] * qx + ax.R[7] * qy + ax.R[8] * qz;
             const double sn = sx * sx + sy * sy + sz * sz;
             S.list[pos] = make_float4((float)(-2.0 * sx), (float)(-2.0 * sy), (float)(-2.0 * (1.0 + sz)), (float)(sn - (double)mid));
-            S.lidx[pos] = (int)(aux & 0x7fffffffu);
+            S.lidx[pos] = (int)aux;  // row of its catalog | catalog bit
             S.lbin[pos] = (unsigned short)b;
             if (WEIGHTED) S.lw[pos] = S.rawlw[i];
         }

@@ -370,33 +370,61 @@ __device__ __forceinline__ unsigned hilbert16(unsigned x, unsigned y, int levels
     return d;
 }
 
-// key = (patch * n_bins + bin) << hbits | top `hbits` bits of the Hilbert index, or -1 for a row whose z-bin is out of range
-__device__ __forceinline__ long long key_second(double X, double Y, double Z, int b, int p, int n_bins, int hbits,
-                                                const PatchFrame *__restrict__ frames) {
-    if (b < 0 || b >= n_bins) return -1;
+// Map of a patch box onto the Hilbert square(s), per patch and index build (k_hilbert_map).
+// The bounding box of the patch is stretched over the Hilbert square(s): an isotropic mapping would leave part
+// of the square empty, and wherever the curve leaves the populated part and re-enters elsewhere, 256
+// consecutive rows straddle the gap (measured: a few tiles per patch with patch-sized boxes, each worth several
+// average work items -> a 13 % straggler tail).  An elongated box (aspect >= 2, e.g. the strip of a
+// patch that two ranks share) is covered by k = round(aspect) <= 8 squares side by side along its long axis:
+// the curve leaves a square at the corner where it enters the next one, so the order stays continuous and
+// the cells -- hence the tiles -- stay close to square instead of being stretched k : 1 (a 4 : 1 strip in one
+// square: every tile trips the straggler guard and is cut into 32-row sub-tiles).  Below 2 : 1 a single
+// stretched square is better (C3's 5 x 3 degree patches: 3.6 % fewer executed tests than with two squares).
+// The square index takes its bits from the Hilbert resolution.
+struct HMap {
+    double c[3], e_long[3], e_short[3];  // centre of the patch; tangent axes along the long / short side of the box
+    double o_long, o_short;              // lower edge of the box along the two axes
+    double s_long, s_short;              // k / long side; 65535 / short side (0 for a degenerate box)
+    int k, levels;                       // squares side by side; resolved levels of the curve
+};
+
+__global__ void k_hilbert_map(const PatchFrame *__restrict__ frames, int n_patch, int hbits, HMap *__restrict__ maps) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_patch) return;
     const PatchFrame &f = frames[p];
-    double u, v;
-    local_uv(f, X, Y, Z, u, v);
-    // The bounding box of the patch is stretched over the Hilbert square(s): an isotropic mapping would leave part
-    // of the square empty, and wherever the curve leaves the populated part and re-enters elsewhere, 256
-    // consecutive rows straddle the gap (measured: a few tiles per patch with patch-sized boxes, each worth several
-    // average work items -> a 13 % straggler tail).  An elongated box (aspect >= 2, e.g. the strip of a
-    // patch that two ranks share) is covered by k = round(aspect) <= 8 squares side by side along its long axis:
-    // the curve leaves a square at the corner where it enters the next one, so the order stays continuous and
-    // the cells -- hence the tiles -- stay close to square instead of being stretched k : 1 (a 4 : 1 strip in one
-    // square: every tile trips the straggler guard and is cut into 32-row sub-tiles).  Below 2 : 1 a single
-    // stretched square is better (C3's 5 x 3 degree patches: 3.6 % fewer executed tests than with two squares).
-    // The square index takes its bits from the Hilbert resolution.
     const double du = f.umax - f.umin, dv = f.vmax - f.vmin;
     const bool swap = dv > du;  // the long axis is the x of the curve (which runs from (0, 0) to (max, 0))
     const double lng = swap ? dv : du, sht = swap ? du : dv;
     const int k = sht > 0.0 && lng >= 2.0 * sht ? min((int)rint(lng / sht), 8) : 1;
     const int kb = k > 4 ? 3 : k > 2 ? 2 : k > 1 ? 1 : 0;  // bits of the square index
-    const int levels = (hbits - kb) / 2;
-    const double tl = lng > 0.0 ? ((swap ? v - f.vmin : u - f.umin) / lng) * k : 0.0;
+    HMap m;
+    for (int d = 0; d < 3; ++d) {
+        m.c[d] = f.c[d];
+        m.e_long[d] = swap ? f.e2[d] : f.e1[d];
+        m.e_short[d] = swap ? f.e1[d] : f.e2[d];
+    }
+    m.o_long = swap ? f.vmin : f.umin;
+    m.o_short = swap ? f.umin : f.vmin;
+    m.s_long = lng > 0.0 ? (double)k / lng : 0.0;
+    m.s_short = sht > 0.0 ? 65535.0 / sht : 0.0;
+    m.k = k;
+    m.levels = (hbits - kb) / 2;
+    maps[p] = m;
+}
+
+// key = (patch * n_bins + bin) << hbits | square << (2 * levels) | top bits of the Hilbert index, or -1 for a row whose
+// z-bin is out of range
+__device__ __forceinline__ long long key_second(double X, double Y, double Z, int b, int p, int n_bins, int hbits,
+                                                const HMap *__restrict__ maps) {
+    if (b < 0 || b >= n_bins) return -1;
+    const HMap &m = maps[p];
+    const double dx = X - m.c[0], dy = Y - m.c[1], dz = Z - m.c[2];
+    const double tl = (dx * m.e_long[0] + dy * m.e_long[1] + dz * m.e_long[2] - m.o_long) * m.s_long;
+    const double ts = (dx * m.e_short[0] + dy * m.e_short[1] + dz * m.e_short[2] - m.o_short) * m.s_short;
+    const int k = m.k, levels = m.levels;
     const int sq = min(max((int)tl, 0), k - 1);
     const int qx = min(max((int)((tl - sq) * 65535.0), 0), 65535);
-    const int qy = sht > 0.0 ? min(max((int)((swap ? u - f.umin : v - f.vmin) / sht * 65535.0), 0), 65535) : 0;
+    const int qy = min(max((int)ts, 0), 65535);
     const unsigned long long h = levels > 0 ? (unsigned long long)(hilbert16((unsigned)qx, (unsigned)qy, levels) >> (32 - 2 * levels)) : 0ull;
     return (long long)(((unsigned long long)((long long)p * n_bins + b) << hbits) | ((unsigned long long)sq << (2 * levels)) | h);
 }
@@ -405,12 +433,12 @@ template <typename K>
 __global__ void k_keys_second(const double *__restrict__ x, const double *__restrict__ y,
                               const double *__restrict__ z, const int *__restrict__ bin,
                               const int *__restrict__ patch, long long n, int n_bins, int hbits,
-                              const PatchFrame *__restrict__ frames, K *__restrict__ keys,
+                              const HMap *__restrict__ maps, K *__restrict__ keys,
                               unsigned *__restrict__ vals) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     vals[i] = (unsigned)i;
-    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
     keys[i] = key < 0 ? (K)~(K)0 : (K)key;
 }
 
@@ -434,84 +462,100 @@ __global__ void k_hist_first(const double *__restrict__ x, const double *__restr
 
 __global__ void k_hist_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                               const int *__restrict__ bin, const int *__restrict__ patch, long long n, int n_bins,
-                              int hbits, const PatchFrame *__restrict__ frames, int *__restrict__ cur) {
+                              int hbits, const HMap *__restrict__ maps, int *__restrict__ cur, int *__restrict__ keys) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
+    keys[i] = (int)key;  // the scatter pass reads the key back instead of walking the curve again (-1: dropped row)
     if (key >= 0) atomicAdd(&cur[key], 1);
 }
 
-// in-place exclusive scan of `cur[0, n)`: block sums, scan of the block sums (one block), block scans + offsets
+// in-place exclusive scan of `cur[0, n)` in ONE pass over the data (decoupled look-back): a block takes the next
+// tile of kScanBlock counts from a global ticket (tiles are therefore started in order, whatever the hardware's
+// block schedule), publishes the tile total, and its first warp walks back over the descriptors of the tiles
+// before it -- 32 at a time -- adding totals until it meets a tile whose inclusive prefix is already known.
+// A descriptor is one 64-bit word (state << 62 | value), written with a single store, so no fence is needed.
 constexpr int kScanPerThread = 16;
 constexpr int kScanBlock = kThreads * kScanPerThread;
 
-__global__ void __launch_bounds__(kThreads) k_scan_sums(const int *__restrict__ cur, long long n, int *__restrict__ sums) {
+__global__ void __launch_bounds__(kThreads) k_scan_lookback(int *__restrict__ cur, long long n,
+                                                            unsigned long long *__restrict__ desc /*[tiles + 1]: ticket first*/) {
+    constexpr unsigned long long kScanTotal = 1ull << 62, kScanPrefix = 2ull << 62, kScanValue = (1ull << 62) - 1;
     __shared__ int s_w[kThreads / 32];
-    const long long base = (long long)blockIdx.x * kScanBlock;
-    int acc = 0;
-    for (int k = threadIdx.x; k < kScanBlock; k += kThreads)
-        if (base + k < n) acc += cur[base + k];
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __shared__ long long s_tile;
+    __shared__ long long s_prefix;
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(&desc[0], 1ull);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < kThreads / 32; ++w) t += s_w[w];
-        sums[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_scan_tops(int *__restrict__ sums, int n_blocks) {
-    __shared__ int s_w[32];
-    __shared__ int s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < n_blocks; b0 += 1024) {
-        const int i = b0 + threadIdx.x;
-        const int v = i < n_blocks ? sums[i] : 0;
-        int incl = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int w = s_w[threadIdx.x], wi = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (threadIdx.x >= o) wi += t;
-            }
-            s_w[threadIdx.x] = wi - w;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        if (i < n_blocks) sums[i] = carry + s_w[threadIdx.x >> 5] + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_w[31] + incl;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) k_scan_apply(int *__restrict__ cur, long long n, const int *__restrict__ sums) {
-    __shared__ int s_w[kThreads / 32];
-    const long long base = (long long)blockIdx.x * kScanBlock + (long long)threadIdx.x * kScanPerThread;
+    const long long tile = s_tile;
+    volatile unsigned long long *const d = desc + 1;
+    const long long base = tile * kScanBlock + (long long)threadIdx.x * kScanPerThread;
     int v[kScanPerThread];
     int tot = 0;
+    if (base + kScanPerThread <= n) {  // cur is 4-byte aligned only (cell_start + 1): scalar loads, two full sectors per thread
 #pragma unroll
-    for (int k = 0; k < kScanPerThread; ++k) {
-        v[k] = base + k < n ? cur[base + k] : 0;
-        tot += v[k];
+        for (int k = 0; k < kScanPerThread; ++k) v[k] = cur[base + k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanPerThread; ++k) v[k] = base + k < n ? cur[base + k] : 0;
     }
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) tot += v[k];
     int incl = tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += t;
+        if (lane >= o) incl += t;
     }
-    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    int run = sums[blockIdx.x] + incl - tot;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_w[w];
+    int before = 0, block_total = 0;  // rows of the warps before this one; of the whole tile
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        const int t = s_w[w];
+        if (w < warp) before += t;
+        block_total += t;
+    }
+    if (warp == 0) {
+        long long prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) d[0] = kScanPrefix | (unsigned long long)block_total;
+        } else {
+            if (lane == 0) d[tile] = kScanTotal | (unsigned long long)block_total;
+            // Hundreds of tiles are in flight at once and none of them knows its prefix before the oldest one does, so
+            // the walk is long: every lane requests kLook descriptors per round (256 tiles per round trip to L2).
+            constexpr int kLook = 8;
+            long long look = tile - 1;  // nearest tile not yet accounted for
+            bool found = false;
+            while (!found) {
+                unsigned long long w[kLook];
+#pragma unroll
+                for (int j = 0; j < kLook; ++j) {
+                    const long long idx = look - lane - 32 * j;
+                    w[j] = kScanPrefix;  // before the first tile: prefix 0
+                    if (idx >= 0) w[j] = d[idx];
+                }
+#pragma unroll
+                for (int j = 0; j < kLook; ++j) {
+                    if (found) continue;
+                    const long long idx = look - lane - 32 * j;
+                    while ((w[j] >> 62) == 0ull) w[j] = d[idx];
+                    const unsigned has_prefix = __ballot_sync(0xffffffffu, (w[j] >> 62) == 2ull);
+                    const int stop = has_prefix ? __ffs(has_prefix) - 1 : 32;  // nearest tile with a known prefix
+                    long long part = lane <= stop ? (long long)(w[j] & kScanValue) : 0ll;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    prefix += part;
+                    found = has_prefix != 0u;
+                }
+                look -= 32 * kLook;
+            }
+            if (lane == 0) d[tile] = kScanPrefix | (unsigned long long)(prefix + block_total);
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    int run = (int)s_prefix + before + incl - tot;
 #pragma unroll
     for (int k = 0; k < kScanPerThread; ++k) {
         if (base + k < n) cur[base + k] = run;
@@ -521,15 +565,14 @@ __global__ void __launch_bounds__(kThreads) k_scan_apply(int *__restrict__ cur, 
 
 // second-role scatter: the row goes to the next free slot of its key
 __global__ void k_scatter_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-                                 const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch,
-                                 long long n, int n_bins, int hbits, const PatchFrame *__restrict__ frames,
+                                 const double *__restrict__ w, const int *__restrict__ keys, long long n,
                                  int *__restrict__ cur, double *__restrict__ ox, double *__restrict__ oy,
                                  double *__restrict__ oz, double *__restrict__ ow) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double X = x[i], Y = y[i], Z = z[i];
-    const long long key = key_second(X, Y, Z, bin ? bin[i] : 0, patch[i], n_bins, hbits, frames);
+    const int key = keys[i];
     if (key < 0) return;
+    const double X = x[i], Y = y[i], Z = z[i];
     const int pos = atomicAdd(&cur[key], 1);
     ox[pos] = X;
     oy[pos] = Y;
@@ -542,8 +585,7 @@ __global__ void k_scatter_second(const double *__restrict__ x, const double *__r
 __global__ void k_scatter_first(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                                 const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch,
                                 long long n, int n_bins, unsigned type_bit, const PatchFrame *__restrict__ frames,
-                                const SGrid *__restrict__ grids, int *__restrict__ cur, double *__restrict__ ox,
-                                double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ow,
+                                const SGrid *__restrict__ grids, int *__restrict__ cur, double *__restrict__ ow,
                                 SRec *__restrict__ orec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -552,9 +594,6 @@ __global__ void k_scatter_first(const double *__restrict__ x, const double *__re
     const long long key = key_first(X, Y, Z, bin ? bin[i] : 0, p, n_bins, frames, grids);
     if (key < 0) return;
     const int pos = atomicAdd(&cur[key], 1);
-    ox[pos] = X;
-    oy[pos] = Y;
-    oz[pos] = Z;
     if (ow) ow[pos] = w ? w[i] : 1.0;  // fused index of a weighted and an unweighted catalog
     const PatchFrame &f = frames[p];
     const SGrid &g = grids[p];
@@ -566,7 +605,7 @@ __global__ void k_scatter_first(const double *__restrict__ x, const double *__re
     r.ku = (int)fmin(fmax(rint((u - g.u0) * g.qscale), 0.0), 2147483647.0);
     r.kv = (int)fmin(fmax(rint((v - g.v0) * g.qscale), 0.0), 2147483647.0);
     r.kt = (int)fmin(fmax(rint((t - g.t0) * g.qscale), 0.0), 2147483647.0);
-    r.aux = (unsigned)pos | type_bit;
+    r.aux = (unsigned)i | type_bit;  // the exact row stays where it was uploaded (FP64 recheck only)
     orec[pos] = r;
 }
 
@@ -591,7 +630,6 @@ __global__ void k_gather_rec(const unsigned *__restrict__ perm, long long n, lon
                              const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
                              const double *__restrict__ bw, const int *__restrict__ bpatch,
                              const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
-                             double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
                              double *__restrict__ ow, SRec *__restrict__ orec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -599,9 +637,6 @@ __global__ void k_gather_rec(const unsigned *__restrict__ perm, long long n, lon
     const bool second = j >= n_a;
     if (second) j -= n_a;
     const double X = second ? bx[j] : ax[j], Y = second ? by[j] : ay[j], Z = second ? bz[j] : az[j];
-    ox[i] = X;
-    oy[i] = Y;
-    oz[i] = Z;
     if (ow) {
         const double *w = second ? bw : aw;
         ow[i] = w ? w[j] : 1.0;  // fused index of a weighted and an unweighted catalog
@@ -617,7 +652,7 @@ __global__ void k_gather_rec(const unsigned *__restrict__ perm, long long n, lon
     r.ku = (int)fmin(fmax(rint((u - g.u0) * g.qscale), 0.0), 2147483647.0);
     r.kv = (int)fmin(fmax(rint((v - g.v0) * g.qscale), 0.0), 2147483647.0);
     r.kt = (int)fmin(fmax(rint((t - g.t0) * g.qscale), 0.0), 2147483647.0);
-    r.aux = (unsigned)i | (second ? 0x80000000u : 0u);
+    r.aux = (unsigned)j | (second ? 0x80000000u : 0u);  // row of its catalog | catalog bit
     orec[i] = r;
 }
 
@@ -647,12 +682,24 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     const PatchFrame &f = frames[tl.patch];
     double sx = 0, sy = 0, sz = 0;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int k = lane; k < tl.count; k += 32) {
-        const double X = x[tl.start + k], Y = y[tl.start + k], Z = z[tl.start + k];
-        sx += X;
-        sy += Y;
-        sz += Z;
-        const double dx = X - f.c[0], dy = Y - f.c[1], dz = Z - f.c[2];
+    // the lane's rows (k = lane + 32 r) are requested together and kept for the second pass
+    constexpr int kRows = YAWB_TILE / 32;
+    double X[kRows], Y[kRows], Z[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int k = lane + 32 * r;
+        const bool ok = k < tl.count;
+        X[r] = ok ? x[tl.start + k] : 0.0;
+        Y[r] = ok ? y[tl.start + k] : 0.0;
+        Z[r] = ok ? z[tl.start + k] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        if (lane + 32 * r >= tl.count) continue;
+        sx += X[r];
+        sy += Y[r];
+        sz += Z[r];
+        const double dx = X[r] - f.c[0], dy = Y[r] - f.c[1], dz = Z[r] - f.c[2];
         const double q[3] = {dx * f.e1[0] + dy * f.e1[1] + dz * f.e1[2], dx * f.e2[0] + dy * f.e2[1] + dz * f.e2[2],
                              dx * f.c[0] + dy * f.c[1] + dz * f.c[2]};
 #pragma unroll
@@ -680,9 +727,10 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     double inv = 1.0 / (double)tl.count;
     float cx = (float)(sx * inv), cy = (float)(sy * inv), cz = (float)(sz * inv);
     double r2 = 0.0;  // radius about the float-rounded centre, so the stored sphere is sound
-    for (int k = lane; k < tl.count; k += 32) {
-        double dx = x[tl.start + k] - (double)cx, dy = y[tl.start + k] - (double)cy,
-               dz = z[tl.start + k] - (double)cz;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        if (lane + 32 * r >= tl.count) continue;
+        const double dx = X[r] - (double)cx, dy = Y[r] - (double)cy, dz = Z[r] - (double)cz;
         r2 = fmax(r2, dx * dx + dy * dy + dz * dz);
     }
     for (int o = 16; o; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(full, r2, o));
@@ -733,11 +781,10 @@ int fi_alloc(FIndex *fi, T **ptr, size_t count) {
 int exclusive_scan_inplace(yawb_ctx *ctx, Scratch &scr, int *cur, long long n) {
     if (n <= 0) return 0;
     const int n_blocks = (int)((n + kScanBlock - 1) / kScanBlock);
-    int *sums = scr.get<int>(n_blocks);
-    YAWB_REQUIRE(sums != nullptr, "out of device memory (scan scratch)");
-    k_scan_sums<<<n_blocks, kThreads, 0, ctx->stream>>>(cur, n, sums);
-    k_scan_tops<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks);
-    k_scan_apply<<<n_blocks, kThreads, 0, ctx->stream>>>(cur, n, sums);
+    unsigned long long *desc = scr.get<unsigned long long>((size_t)n_blocks + 1);
+    YAWB_REQUIRE(desc != nullptr, "out of device memory (scan scratch)");
+    YAWB_CUDA(cudaMemsetAsync(desc, 0, ((size_t)n_blocks + 1) * sizeof(unsigned long long), ctx->stream));
+    k_scan_lookback<<<n_blocks, kThreads, 0, ctx->stream>>>(cur, n, desc);
     return 0;
 }
 
@@ -761,8 +808,7 @@ int build_first_counting(FIndex *fi, long long base) {
         if (c && c->n_in > 0)
             k_scatter_first<<<blocks_for(c->n_in), kThreads, 0, st>>>(c->x, c->y, c->z, c->w, c->bin, c->patch, c->n_in,
                                                                       fi->n_bins, c == b ? 0x80000000u : 0u, fi->d_frames,
-                                                                      fi->d_sgrid, cur, fi->sx, fi->sy, fi->sz, fi->sw,
-                                                                      fi->rec);
+                                                                      fi->d_sgrid, cur, fi->sw, fi->rec);
     return 0;
 }
 
@@ -773,14 +819,16 @@ int build_second_counting(yawb_cat *cat, int hbits, long long n_keys) {
     if (cat->n_in <= 0) return 0;
     Scratch scr(ctx, st);
     int *cur = scr.get<int>((size_t)n_keys);
-    YAWB_REQUIRE(cur != nullptr, "out of device memory (key counts)");
+    int *keys = scr.get<int>((size_t)cat->n_in);
+    HMap *maps = scr.get<HMap>((size_t)cat->n_patch);
+    YAWB_REQUIRE(cur && keys && maps, "out of device memory (key counts)");
     YAWB_CUDA(cudaMemsetAsync(cur, 0, (size_t)n_keys * sizeof(int), st));
+    k_hilbert_map<<<(cat->n_patch + 127) / 128, 128, 0, st>>>(cat->d_frames, cat->n_patch, hbits, maps);
     k_hist_second<<<blocks_for(cat->n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, cat->n_in,
-                                                              cat->n_bins, hbits, cat->d_frames, cur);
+                                                              cat->n_bins, hbits, maps, cur, keys);
     if (exclusive_scan_inplace(ctx, scr, cur, n_keys)) return 1;
-    k_scatter_second<<<blocks_for(cat->n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin, cat->patch,
-                                                                 cat->n_in, cat->n_bins, hbits, cat->d_frames, cur, cat->rx,
-                                                                 cat->ry, cat->rz, cat->rw);
+    k_scatter_second<<<blocks_for(cat->n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->w, keys, cat->n_in, cur,
+                                                                 cat->rx, cat->ry, cat->rz, cat->rw);
     return 0;
 }
 
@@ -809,8 +857,7 @@ int build_first_sorted(FIndex *fi, long long base) {
     if (n > 0)
         k_gather_rec<<<blocks_for(n), kThreads, 0, st>>>(v1, n, na_in, a->x, a->y, a->z, a->w, a->patch, b ? b->x : nullptr,
                                                          b ? b->y : nullptr, b ? b->z : nullptr, b ? b->w : nullptr,
-                                                         b ? b->patch : nullptr, fi->d_frames, fi->d_sgrid, fi->sx, fi->sy,
-                                                         fi->sz, fi->sw, fi->rec);
+                                                         b ? b->patch : nullptr, fi->d_frames, fi->d_sgrid, fi->sw, fi->rec);
     k_cell_start<K><<<blocks_for(base + 1), kThreads, 0, st>>>(k1, n, base, fi->cell_start);
     return 0;
 }
@@ -827,8 +874,11 @@ int build_second_sorted(yawb_cat *cat, int hbits) {
     unsigned *v0 = scr.get<unsigned>(nn), *v1 = scr.get<unsigned>(nn);
     YAWB_REQUIRE(k0 && k1 && v0 && v1, "out of device memory (sort buffers)");
     if (n_in > 0) {
+        HMap *maps = scr.get<HMap>((size_t)P);
+        YAWB_REQUIRE(maps != nullptr, "out of device memory (sort buffers)");
+        k_hilbert_map<<<(P + 127) / 128, 128, 0, st>>>(cat->d_frames, P, hbits, maps);
         k_keys_second<K><<<blocks_for(n_in), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->bin, cat->patch, n_in, B,
-                                                                hbits, cat->d_frames, k0, v0);
+                                                                hbits, maps, k0, v0);
         const int end_bit = (n == n_in) ? hbits + bits_for((unsigned long long)std::max<long long>((long long)P * B, 1))
                                         : (int)(8 * sizeof(K));
         if (sort_pairs<K>(ctx, scr, k0, k1, v0, v1, n_in, std::min(end_bit, (int)(8 * sizeof(K))))) return 1;
@@ -1120,7 +1170,7 @@ static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
     }
     if (fi_alloc(fi, &fi->d_sgrid, P)) return fail();
     if (yawb_h2d_small(ctx, fi->d_sgrid, fi->h_sgrid.data(), P * sizeof(SGrid))) return fail();
-    if (fi_alloc(fi, &fi->sx, n) || fi_alloc(fi, &fi->sy, n) || fi_alloc(fi, &fi->sz, n) || fi_alloc(fi, &fi->rec, n)) return fail();
+    if (fi_alloc(fi, &fi->rec, n)) return fail();
     if (fi->weighted && fi_alloc(fi, &fi->sw, n)) return fail();
     if (fi_alloc(fi, &fi->cell_start, base + 1)) return fail();
     // 32-bit sort keys whenever the cell ids fit (they nearly always do): a third less radix-sort traffic
@@ -1143,7 +1193,7 @@ static int findex_build(yawb_ctx *ctx, yawb_cat *a, yawb_cat *b, FIndex **out) {
 void yawb_findex_free(FIndex *fi) {
     if (!fi) return;
     yawb_ctx *ctx = fi->ctx;
-    for (void *p : {(void *)fi->rec, (void *)fi->sx, (void *)fi->sy, (void *)fi->sz, (void *)fi->sw, (void *)fi->cell_start,
+    for (void *p : {(void *)fi->rec, (void *)fi->sw, (void *)fi->cell_start,
                     (void *)fi->d_sgrid, (void *)fi->d_frames})
         if (p) yawb_dfree(ctx, p, ctx->stream);
     delete fi;
@@ -1205,9 +1255,12 @@ int yawb_index_build_second(yawb_cat *cat) {
         int k = 4;
         while (k < 16 && (1ll << (2 * k)) < m + m / 2) ++k;
         // counting sort: one count per (patch, bin, Hilbert cell); the Hilbert resolution is capped so that there are
-        // at most about four keys per row (dense segments then hold a few rows per Hilbert cell, in arbitrary order)
+        // at most about ONE key per row (the cells then hold 1-4 rows, in arbitrary order; swept on C3: 4 / 1 / 0.25 /
+        // 0.06 keys per row -> index build 1.80 / 1.60 / 1.57 / 2.89 ms, count kernels 6.05 / 6.07 / 6.11 / 6.31 ms)
         int kc = k;
-        const long long key_budget = std::max<long long>(4 * cat->n_in, 1 << 16);
+        double keys_per_row = 1.0;
+        if (const char *e = getenv("YAWB_KEYS_PER_ROW")) keys_per_row = std::max(0.001, atof(e));
+        const long long key_budget = std::max<long long>((long long)(keys_per_row * (double)cat->n_in), 1 << 16);
         while (kc > 1 && (((long long)P * B) << (2 * kc)) > key_budget) --kc;
         const long long n_keys = ((long long)P * B) << (2 * kc);
         if (n_keys <= kCountingSortMaxKeys && !cat->weighted && !getenv("YAWB_RADIX_SORT")) {

@@ -211,7 +211,6 @@ struct FIndex {
     int n_patch = 0, n_bins = 1, n_types = 1;
     bool weighted = false;
     SRec *rec = nullptr;                                    // fixed-point rows in the frame of their patch
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr;     // the exact rows (FP64 recheck)
     double *sw = nullptr;                                   // weights (1.0 for rows of an unweighted catalog)
     int *cell_start = nullptr;
     long long n_cells = 0;
