@@ -114,7 +114,8 @@ __device__ __forceinline__ BinRows bin_rows(const SGrid &G, double ulo, double u
         const double *cand_x_ = cand_t_ ? (P).cx[1] : (P).cx[0];               \
         const double *cand_y_ = cand_t_ ? (P).cy[1] : (P).cy[0];               \
         const double *cand_z_ = cand_t_ ? (P).cz[1] : (P).cz[0];               \
-        X = cand_x_[cand_i_]; Y = cand_y_[cand_i_]; Z = cand_z_[cand_i_];      \
+        const size_t cand_o_ = 3 * (size_t)cand_i_; /* interleaved rows */     \
+        X = cand_x_[cand_o_]; Y = cand_y_[cand_o_]; Z = cand_z_[cand_o_];      \
     } while (0)
 
 // The reference's comparison value: products rounded separately, summed x -> y -> z.
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
         double ax = 0, ay = 0, az = 0, aw = 1.0;
         if (live) {
             const int row = (int)(P.rec[i].aux & 0x7fffffffu);
-            ax = P.cx[row]; ay = P.cy[row]; az = P.cz[row];
+            ax = P.cx[3 * (size_t)row]; ay = P.cy[3 * (size_t)row]; az = P.cz[3 * (size_t)row];  // interleaved rows
             if (WEIGHTED && P.sw) aw = P.sw[i];
         }
         for (int jc = c0; jc < c1; jc += EX_THREADS) {

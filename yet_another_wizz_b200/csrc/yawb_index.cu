@@ -82,6 +82,9 @@ __device__ __forceinline__ unsigned long long enc_double(double v) {
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 // ---- upload kernels ---------------------------------------------------------------------
+// The rows stay interleaved as uploaded (xyz[3 i + 0 / 1 / 2]): consecutive threads read consecutive rows, so a
+// warp's three loads cover 768 contiguous bytes between them.  k_patch_ids: the patch id of every row from the row
+// offsets.
 
 // z-bin ids that travelled as bytes (a quarter of the PCIe traffic of int32): widen; ids >= n_bins stay out of range
 __global__ void k_widen_bins(const unsigned char *__restrict__ b8, long long n, int *__restrict__ bin) {
@@ -89,7 +92,6 @@ __global__ void k_widen_bins(const unsigned char *__restrict__ b8, long long n, 
     if (i < n) bin[i] = (int)b8[i];
 }
 
-// AoS (n x 3) -> SoA, plus the patch id of every row from the row offsets
 // z-bin of every row from its redshift: np.digitize(z, edges, right) - 1 (src/yaw/catalog/trees.py:408-414).
 // right: bin b holds edges[b] < z <= edges[b + 1], i.e. (number of edges strictly below z) - 1; otherwise
 // edges[b] <= z < edges[b + 1], i.e. (number of edges <= z) - 1.  Comparisons only: identical to numpy's ids;
@@ -108,14 +110,9 @@ __global__ void k_digitize(const double *__restrict__ z, long long n, const doub
     bin[i] = lo - 1;
 }
 
-__global__ void k_deinterleave(const double *__restrict__ xyz, const long long *__restrict__ patch_off,
-                               int n_patch, long long n, double *__restrict__ x, double *__restrict__ y,
-                               double *__restrict__ z, int *__restrict__ patch) {
+__global__ void k_patch_ids(const long long *__restrict__ patch_off, int n_patch, long long n, int *__restrict__ patch) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    x[i] = xyz[3 * i];
-    y[i] = xyz[3 * i + 1];
-    z[i] = xyz[3 * i + 2];
     int lo = 0, hi = n_patch;  // last p with patch_off[p] <= i
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -129,6 +126,7 @@ __global__ void k_deinterleave(const double *__restrict__ xyz, const long long *
 // memory (rows are grouped by patch, so that is nearly all of them) and flushed with one global atomic
 // per z-bin; stragglers of the next patch go to global memory directly.
 constexpr int kSumRows = 4096;
+constexpr int kSumBatch = 4;  // rows in flight per thread
 constexpr int kSumMaxBins = 2048;
 
 __global__ void __launch_bounds__(kThreads) k_patch_sums(
@@ -151,30 +149,45 @@ __global__ void __launch_bounds__(kThreads) k_patch_sums(
         }
     __syncthreads();
     double ax = 0.0, ay = 0.0, az = 0.0;
-    for (int k = threadIdx.x; k < kSumRows; k += blockDim.x) {
-        const long long i = row0 + k;
-        if (i >= n) break;
-        const int p = patch[i];
-        const int b = bin ? bin[i] : 0;
-        const bool in_bin = b >= 0 && b < n_bins;
-        if (p == p_blk) {
-            ax += x[i]; ay += y[i]; az += z[i];
-            if (in_bin) {
-                if (use_smem) {
-                    atomicAdd(&s_cnt[b], 1u);
-                    if (w) atomicAdd(&s_w[b], w[i]);
-                } else {
-                    atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
-                    if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
+    // kSumBatch rows per thread and round, every load of a round requested before the first is used (a loop with one
+    // row in flight per thread is latency-bound: 2.7 TB/s)
+    for (int k0 = threadIdx.x; k0 < kSumRows; k0 += kSumBatch * blockDim.x) {
+        int p[kSumBatch], b[kSumBatch];
+        double X[kSumBatch], Y[kSumBatch], Z[kSumBatch], W[kSumBatch];
+#pragma unroll
+        for (int q = 0; q < kSumBatch; ++q) {
+            const long long i = row0 + k0 + q * (int)blockDim.x;
+            const bool ok = k0 + q * (int)blockDim.x < kSumRows && i < n;
+            p[q] = ok ? patch[i] : -1;
+            b[q] = ok && bin ? bin[i] : 0;
+            X[q] = ok ? x[3 * i] : 0.0;
+            Y[q] = ok ? y[3 * i] : 0.0;
+            Z[q] = ok ? z[3 * i] : 0.0;
+            W[q] = ok && w ? w[i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < kSumBatch; ++q) {
+            if (p[q] < 0) continue;
+            const bool in_bin = b[q] >= 0 && b[q] < n_bins;
+            if (p[q] == p_blk) {
+                ax += X[q]; ay += Y[q]; az += Z[q];
+                if (in_bin) {
+                    if (use_smem) {
+                        atomicAdd(&s_cnt[b[q]], 1u);
+                        if (w) atomicAdd(&s_w[b[q]], W[q]);
+                    } else {
+                        atomicAdd(&counts[(size_t)b[q] * n_patch + p[q]], 1ull);
+                        if (w) atomicAdd(&sumw[(size_t)b[q] * n_patch + p[q]], W[q]);
+                    }
                 }
-            }
-        } else {
-            atomicAdd(&sums[3 * p], x[i]);
-            atomicAdd(&sums[3 * p + 1], y[i]);
-            atomicAdd(&sums[3 * p + 2], z[i]);
-            if (in_bin) {
-                atomicAdd(&counts[(size_t)b * n_patch + p], 1ull);
-                if (w) atomicAdd(&sumw[(size_t)b * n_patch + p], w[i]);
+            } else {
+                atomicAdd(&sums[3 * p[q]], X[q]);
+                atomicAdd(&sums[3 * p[q] + 1], Y[q]);
+                atomicAdd(&sums[3 * p[q] + 2], Z[q]);
+                if (in_bin) {
+                    atomicAdd(&counts[(size_t)b[q] * n_patch + p[q]], 1ull);
+                    if (w) atomicAdd(&sumw[(size_t)b[q] * n_patch + p[q]], W[q]);
+                }
             }
         }
     }
@@ -259,32 +272,45 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
     const int p_blk = patch[row0];
     const PatchFrame f = frames[p_blk];
     unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull, nmax = 0ull;
-    for (int k = threadIdx.x; k < kSumRows; k += blockDim.x) {
-        const long long i = row0 + k;
-        if (i >= n) break;
-        const int p = patch[i];
-        const PatchFrame &g = p == p_blk ? f : frames[p];
-        const double dx = x[i] - g.c[0], dy = y[i] - g.c[1], dz = z[i] - g.c[2];
-        const unsigned long long eu = enc_double(dx * g.e1[0] + dy * g.e1[1] + dz * g.e1[2]);
-        const unsigned long long ev = enc_double(dx * g.e2[0] + dy * g.e2[1] + dz * g.e2[2]);
-        const unsigned long long ed = enc_double(dx * dx + dy * dy + dz * dz);
-        // how far the row is from the unit sphere: | |P|^2 - 1 |, evaluated without cancellation as |d . (P + c)|
-        // plus the deviation of the (normalised) centre itself
-        const unsigned long long en =
-            enc_double(fabs(dx * (x[i] + g.c[0]) + dy * (y[i] + g.c[1]) + dz * (z[i] + g.c[2])) +
-                       fabs(g.c[0] * g.c[0] + g.c[1] * g.c[1] + g.c[2] * g.c[2] - 1.0));
-        if (p == p_blk) {
-            umin = min(umin, eu); umax = max(umax, eu);
-            vmin = min(vmin, ev); vmax = max(vmax, ev);
-            dmax = max(dmax, ed);
-            nmax = max(nmax, en);
-        } else {
-            atomicMin(&box[kBox * p], eu);
-            atomicMax(&box[kBox * p + 1], eu);
-            atomicMin(&box[kBox * p + 2], ev);
-            atomicMax(&box[kBox * p + 3], ev);
-            atomicMax(&box[kBox * p + 4], ed);
-            atomicMax(&box[kBox * p + 5], en);
+    for (int k0 = threadIdx.x; k0 < kSumRows; k0 += kSumBatch * blockDim.x) {
+        int pq[kSumBatch];
+        double X[kSumBatch], Y[kSumBatch], Z[kSumBatch];
+#pragma unroll
+        for (int q = 0; q < kSumBatch; ++q) {  // all loads of the round first
+            const long long i = row0 + k0 + q * (int)blockDim.x;
+            const bool ok = k0 + q * (int)blockDim.x < kSumRows && i < n;
+            pq[q] = ok ? patch[i] : -1;
+            X[q] = ok ? x[3 * i] : 0.0;
+            Y[q] = ok ? y[3 * i] : 0.0;
+            Z[q] = ok ? z[3 * i] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < kSumBatch; ++q) {
+            const int p = pq[q];
+            if (p < 0) continue;
+            const PatchFrame &g = p == p_blk ? f : frames[p];
+            const double dx = X[q] - g.c[0], dy = Y[q] - g.c[1], dz = Z[q] - g.c[2];
+            const unsigned long long eu = enc_double(dx * g.e1[0] + dy * g.e1[1] + dz * g.e1[2]);
+            const unsigned long long ev = enc_double(dx * g.e2[0] + dy * g.e2[1] + dz * g.e2[2]);
+            const unsigned long long ed = enc_double(dx * dx + dy * dy + dz * dz);
+            // how far the row is from the unit sphere: | |P|^2 - 1 |, evaluated without cancellation as |d . (P + c)|
+            // plus the deviation of the (normalised) centre itself
+            const unsigned long long en =
+                enc_double(fabs(dx * (X[q] + g.c[0]) + dy * (Y[q] + g.c[1]) + dz * (Z[q] + g.c[2])) +
+                           fabs(g.c[0] * g.c[0] + g.c[1] * g.c[1] + g.c[2] * g.c[2] - 1.0));
+            if (p == p_blk) {
+                umin = min(umin, eu); umax = max(umax, eu);
+                vmin = min(vmin, ev); vmax = max(vmax, ev);
+                dmax = max(dmax, ed);
+                nmax = max(nmax, en);
+            } else {
+                atomicMin(&box[kBox * p], eu);
+                atomicMax(&box[kBox * p + 1], eu);
+                atomicMin(&box[kBox * p + 2], ev);
+                atomicMax(&box[kBox * p + 3], ev);
+                atomicMax(&box[kBox * p + 4], ed);
+                atomicMax(&box[kBox * p + 5], en);
+            }
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -342,7 +368,7 @@ __global__ void k_keys_first(const double *__restrict__ x, const double *__restr
     keys += off;  // rows of the second catalog of a fused index follow those of the first
     vals += off;
     vals[i] = (unsigned)(off + i);
-    const long long key = key_first(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
+    const long long key = key_first(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
     keys[i] = key < 0 ? (K)~(K)0 : (K)key;
 }
 
@@ -438,7 +464,7 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     vals[i] = (unsigned)i;
-    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
+    const long long key = key_second(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
     keys[i] = key < 0 ? (K)~(K)0 : (K)key;
 }
 
@@ -456,7 +482,7 @@ __global__ void k_hist_first(const double *__restrict__ x, const double *__restr
                              int *__restrict__ cur) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long key = key_first(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
+    const long long key = key_first(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
     if (key >= 0) atomicAdd(&cur[key], 1);
 }
 
@@ -465,7 +491,7 @@ __global__ void k_hist_second(const double *__restrict__ x, const double *__rest
                               int hbits, const HMap *__restrict__ maps, int *__restrict__ cur, int *__restrict__ keys) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long key = key_second(x[i], y[i], z[i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
+    const long long key = key_second(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
     keys[i] = (int)key;  // the scatter pass reads the key back instead of walking the curve again (-1: dropped row)
     if (key >= 0) atomicAdd(&cur[key], 1);
 }
@@ -572,7 +598,7 @@ __global__ void k_scatter_second(const double *__restrict__ x, const double *__r
     if (i >= n) return;
     const int key = keys[i];
     if (key < 0) return;
-    const double X = x[i], Y = y[i], Z = z[i];
+    const double X = x[3 * i], Y = y[3 * i], Z = z[3 * i];
     const int pos = atomicAdd(&cur[key], 1);
     ox[pos] = X;
     oy[pos] = Y;
@@ -589,7 +615,7 @@ __global__ void k_scatter_first(const double *__restrict__ x, const double *__re
                                 SRec *__restrict__ orec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double X = x[i], Y = y[i], Z = z[i];
+    const double X = x[3 * i], Y = y[3 * i], Z = z[3 * i];
     const int p = patch[i];
     const long long key = key_first(X, Y, Z, bin ? bin[i] : 0, p, n_bins, frames, grids);
     if (key < 0) return;
@@ -616,9 +642,9 @@ __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const d
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned j = perm[i];
-    ox[i] = x[j];
-    oy[i] = y[j];
-    oz[i] = z[j];
+    ox[i] = x[3 * (size_t)j];
+    oy[i] = y[3 * (size_t)j];
+    oz[i] = z[3 * (size_t)j];
     if (w) ow[i] = w[j];
 }
 
@@ -636,7 +662,7 @@ __global__ void k_gather_rec(const unsigned *__restrict__ perm, long long n, lon
     long long j = perm[i];
     const bool second = j >= n_a;
     if (second) j -= n_a;
-    const double X = second ? bx[j] : ax[j], Y = second ? by[j] : ay[j], Z = second ? bz[j] : az[j];
+    const double X = second ? bx[3 * j] : ax[3 * j], Y = second ? by[3 * j] : ay[3 * j], Z = second ? bz[3 * j] : az[3 * j];
     if (ow) {
         const double *w = second ? bw : aw;
         ow[i] = w ? w[j] : 1.0;  // fused index of a weighted and an unweighted catalog
@@ -908,15 +934,17 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
     // copies behind it).  The per-patch reductions run on the main stream when the catalog is first used
     // (yawb_cat_finalize), which joins the copies through `ev_meta`.
     cudaStream_t st = ctx->copy_stream;
-    if (dev_alloc(cat, &cat->x, n, st) || dev_alloc(cat, &cat->y, n, st) || dev_alloc(cat, &cat->z, n, st) ||
-        dev_alloc(cat, &cat->patch, n, st))
-        return 1;
+    // the rows stay interleaved, as uploaded: x / y / z are views of `xyz` with stride 3
+    if (dev_alloc(cat, &cat->xyz, (size_t)n * 3, st) || dev_alloc(cat, &cat->patch, n, st)) return 1;
+    cat->x = cat->xyz;
+    cat->y = cat->xyz + 1;
+    cat->z = cat->xyz + 2;
     if (w && dev_alloc(cat, &cat->w, n, st)) return 1;
     if ((zbin || zbin8 || zred) && dev_alloc(cat, &cat->bin, n, st)) return 1;
     if (zbin8 && dev_alloc(cat, &cat->d_stage_bin8, n, st)) return 1;
     if (zred && dev_alloc(cat, &cat->d_stage_z, n, st)) return 1;
     if (dev_alloc(cat, &cat->d_frames, P, st) || dev_alloc(cat, &cat->d_seg_off, (size_t)P * B + 1, st)) return 1;
-    if (dev_alloc(cat, &cat->d_stage_xyz, (size_t)n * 3, st) || dev_alloc(cat, &cat->d_stage_poff, P + 1, st)) return 1;
+    if (dev_alloc(cat, &cat->d_stage_poff, P + 1, st)) return 1;
 
     // Bulk copies go out in pieces so that other users of the copy engine never wait behind a whole
     // catalog (the small tables of a concurrent pair count avoid the engine altogether: yawb_h2d_small).
@@ -928,7 +956,7 @@ int yawb_index_upload(yawb_ctx *ctx, yawb_cat *cat, const double *xyz, const dou
         }
         return cudaSuccess;
     };
-    if (n > 0) YAWB_CUDA(h2d(cat->d_stage_xyz, xyz, n * 3 * sizeof(double)));
+    if (n > 0) YAWB_CUDA(h2d(cat->xyz, xyz, n * 3 * sizeof(double)));
     YAWB_CUDA(cudaMemcpyAsync(cat->d_stage_poff, patch_off, (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     if (w && n > 0) YAWB_CUDA(h2d(cat->w, w, n * sizeof(double)));
     if (zbin && n > 0) YAWB_CUDA(h2d(cat->bin, zbin, n * sizeof(int32_t)));
@@ -954,7 +982,7 @@ static void release_staging(yawb_cat *cat) {
     cat->hp_sumw = nullptr;
 }
 
-// Completion of an upload at first use: SoA split, per-patch reductions and frames on the main stream,
+// Completion of an upload at first use: patch ids, per-patch reductions and frames on the main stream,
 // their results to pinned staging, then the host-side row tables.
 int yawb_cat_finalize(yawb_cat *cat) {
     if (cat->finalized) return 0;
@@ -977,8 +1005,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
         YAWB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)B * P * sizeof(unsigned long long), st));
         const int pb = (P + 127) / 128;
         if (n > 0) {
-            k_deinterleave<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_xyz, cat->d_stage_poff, P, n, cat->x, cat->y,
-                                                               cat->z, cat->patch);
+            k_patch_ids<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_poff, P, n, cat->patch);
             if (cat->d_stage_bin8) k_widen_bins<<<blocks_for(n), kThreads, 0, st>>>(cat->d_stage_bin8, n, cat->bin);
             if (cat->d_stage_z) {
                 double *d_edges = scr.get<double>(cat->h_edges.size());
@@ -999,7 +1026,6 @@ int yawb_cat_finalize(yawb_cat *cat) {
             k_patch_bbox<<<blocks_for(n, kSumRows), kThreads, 0, st>>>(cat->x, cat->y, cat->z, cat->patch, n,
                                                                        cat->d_frames, d_box);
         k_finish_frames<<<pb, 128, 0, st>>>(d_box, P, cat->d_frames);
-        dev_free(cat, cat->d_stage_xyz, (size_t)n * 3);
         dev_free(cat, cat->d_stage_poff, P + 1);
         dev_free(cat, cat->d_stage_bin8, (size_t)n);
         dev_free(cat, cat->d_stage_z, (size_t)n);
@@ -1395,10 +1421,10 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
         if (cat->ev_meta) cudaEventDestroy(cat->ev_meta);
         cat->ev_meta = nullptr;
         const size_t ni = (size_t)cat->n_in;
-        dev_free(cat, cat->d_stage_xyz, ni * 3);
         dev_free(cat, cat->d_stage_poff, P + 1);
         dev_free(cat, cat->d_stage_bin8, ni);
-        dev_free(cat, cat->x, ni); dev_free(cat, cat->y, ni); dev_free(cat, cat->z, ni);
+        dev_free(cat, cat->xyz, ni * 3);
+        cat->x = cat->y = cat->z = nullptr;
         dev_free(cat, cat->w, ni);
         dev_free(cat, cat->bin, ni);
         dev_free(cat, cat->patch, ni);

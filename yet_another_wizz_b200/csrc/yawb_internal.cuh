@@ -160,7 +160,6 @@ struct yawb_cat {
     // uploads are asynchronous: the host-side tables below are filled by yawb_cat_finalize() on first use
     bool finalized = false;
     cudaEvent_t ev_meta = nullptr;            // recorded on the copy stream after the last host-to-device copy
-    double *d_stage_xyz = nullptr;            // interleaved rows as uploaded, until yawb_cat_finalize()
     long long *d_stage_poff = nullptr;        // row offsets of the patches, until yawb_cat_finalize()
     unsigned char *d_stage_bin8 = nullptr;    // z-bin ids uploaded as bytes, widened by yawb_cat_finalize()
     double *d_stage_z = nullptr;              // raw redshifts, digitized by yawb_cat_finalize()
@@ -173,7 +172,9 @@ struct yawb_cat {
     void *hp_block = nullptr;                 // or in its own pinned block
 
     // raw rows in upload order (grouped by patch)
-    double *x = nullptr, *y = nullptr, *z = nullptr, *w = nullptr;
+    double *xyz = nullptr;                    // the rows as uploaded, interleaved (n x 3)
+    double *x = nullptr, *y = nullptr, *z = nullptr;  // views of xyz: row i is x[3 i], y[3 i], z[3 i]
+    double *w = nullptr;
     int32_t *bin = nullptr;    // nullptr if unbinned
     int32_t *patch = nullptr;
 
