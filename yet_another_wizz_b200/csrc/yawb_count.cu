@@ -194,7 +194,7 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
             const int i = S.lidx[e], j = tl.start + k;
             double cxx, cyy, czz;
             YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-            const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
+            const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
             if (d2 > lo && d2 <= hi) {
                 cnt += 1;
                 if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
@@ -220,7 +220,7 @@ __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem
     const int k = src + 32 * (lane & 7);
     const bool row_ok = k < tl.count;
     const int j = tl.start + (row_ok ? k : 0);
-    const double bx = P.rx[j], by = P.ry[j], bz = P.rz[j];
+    const double bx = P.rx[(size_t)YAWB_RSTRIDE * j], by = P.ry[(size_t)YAWB_RSTRIDE * j], bz = P.rz[(size_t)YAWB_RSTRIDE * j];
     double ax[Q], ay[Q], az[Q];
     bool ok[Q];
 #pragma unroll
@@ -364,7 +364,7 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
             const int i = lidx[e], j = tl.start + k;
             double cxx, cyy, czz;
             YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-            const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
+            const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
 #pragma unroll
             for (int g = 0; g < G; ++g)
                 if (k0 + g < ne && d2 <= ed[k0 + g]) cnt[g] += 1;
@@ -498,7 +498,7 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
                     const int i = S.lidx[e];
                     double cxx, cyy, czz;
                     YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-                    const double d2 = exact_d2(cxx, cyy, czz, P.rx[j], P.ry[j], P.rz[j]);
+                    const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
                     k = edges_below(ed, ne, d2);
                     n_recheck += 1;
                 }
@@ -711,9 +711,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_count_exact(const ExactParams P)
             __syncthreads();
             if ((int)threadIdx.x < nj) {
                 const int j = jc + threadIdx.x;
-                tile[threadIdx.x] = P.rx[j];
-                tile[EX_THREADS + threadIdx.x] = P.ry[j];
-                tile[2 * EX_THREADS + threadIdx.x] = P.rz[j];
+                tile[threadIdx.x] = P.rx[(size_t)YAWB_RSTRIDE * j];
+                tile[EX_THREADS + threadIdx.x] = P.ry[(size_t)YAWB_RSTRIDE * j];
+                tile[2 * EX_THREADS + threadIdx.x] = P.rz[(size_t)YAWB_RSTRIDE * j];
                 tile[3 * EX_THREADS + threadIdx.x] = (WEIGHTED && P.rw) ? P.rw[j] : 1.0;
             }
             __syncthreads();

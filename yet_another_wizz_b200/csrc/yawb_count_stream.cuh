@@ -248,12 +248,9 @@ __device__ __forceinline__ void stream_plan(const FastParams &P, const SM &S, in
         S.csbin[k] = (unsigned short)b;
     }
     // the rows of the tile: towards L2 now, into registers when the item is consumed
-    const double *const rxs = it.src ? P.rx2 : P.rx, *const rys = it.src ? P.ry2 : P.ry, *const rzs = it.src ? P.rz2 : P.rz;
-    for (int k = lane * 16; k < it.count; k += 512) {
-        prefetch_l2(rxs + it.start + k);
-        prefetch_l2(rys + it.start + k);
-        prefetch_l2(rzs + it.start + k);
-    }
+    const double *const rxs = it.src ? P.rx2 : P.rx;
+    for (int k = lane * 4; k < it.count; k += 128)  // 32-byte row records: one 128-byte line per four rows
+        prefetch_l2(rxs + (size_t)YAWB_RSTRIDE * (it.start + k));
 }
 
 // ---- run table of the item whose cell boundaries have landed; returns the number of candidate rows -------
@@ -616,15 +613,16 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
             if (c_first) {
                 // rows of the tile: loads issued now, used after the conversion of the raw chunk
                 tl.start = it.start; tl.count = it.count; tl.patch = 0; tl.bin = 0;
-                const double *const rxs = it.src ? P.rx2 : P.rx, *const rys = it.src ? P.ry2 : P.ry,
-                                    *const rzs = it.src ? P.rz2 : P.rz, *const rws = it.src ? P.rw2 : P.rw;
+                const double *const rxs = it.src ? P.rx2 : P.rx, *const rws = it.src ? P.rw2 : P.rw;
 #pragma unroll
                 for (int r = 0; r < YAWB_RPL; ++r) {
                     const int k = lane + 32 * r;
                     dx[r] = dy[r] = dz[r] = 0.0;
                     if (k < it.count) {
                         const int j = it.start + k;
-                        dx[r] = rxs[j]; dy[r] = rys[j]; dz[r] = rzs[j];
+                        const double2 *const row = reinterpret_cast<const double2 *>(rxs + (size_t)YAWB_RSTRIDE * j);
+                        const double2 ra = row[0], rb = row[1];  // 32-byte row record
+                        dx[r] = ra.x; dy[r] = ra.y; dz[r] = rb.x;
                         if (WEIGHTED) rwt[r] = rws ? rws[j] : 1.0;
                     }
                 }

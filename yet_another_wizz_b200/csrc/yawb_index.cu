@@ -600,9 +600,10 @@ __global__ void k_scatter_second(const double *__restrict__ x, const double *__r
     if (key < 0) return;
     const double X = x[3 * i], Y = y[3 * i], Z = z[3 * i];
     const int pos = atomicAdd(&cur[key], 1);
-    ox[pos] = X;
-    oy[pos] = Y;
-    oz[pos] = Z;
+    // one 32-byte record per row: a full sector per scattered store (three separate arrays cost three partial ones)
+    double2 *const o = reinterpret_cast<double2 *>(ox + (size_t)YAWB_RSTRIDE * pos);
+    o[0] = make_double2(X, Y);
+    o[1] = make_double2(Z, 0.0);
     if (w) ow[pos] = w[i];
 }
 
@@ -642,9 +643,9 @@ __global__ void k_gather(const unsigned *__restrict__ perm, long long n, const d
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned j = perm[i];
-    ox[i] = x[3 * (size_t)j];
-    oy[i] = y[3 * (size_t)j];
-    oz[i] = z[3 * (size_t)j];
+    double2 *const o = reinterpret_cast<double2 *>(ox + (size_t)YAWB_RSTRIDE * i);
+    o[0] = make_double2(x[3 * (size_t)j], y[3 * (size_t)j]);
+    o[1] = make_double2(z[3 * (size_t)j], 0.0);
     if (w) ow[i] = w[j];
 }
 
@@ -715,9 +716,12 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     for (int r = 0; r < kRows; ++r) {
         const int k = lane + 32 * r;
         const bool ok = k < tl.count;
-        X[r] = ok ? x[tl.start + k] : 0.0;
-        Y[r] = ok ? y[tl.start + k] : 0.0;
-        Z[r] = ok ? z[tl.start + k] : 0.0;
+        X[r] = Y[r] = Z[r] = 0.0;
+        if (ok) {  // 32-byte row records
+            const double2 *const row = reinterpret_cast<const double2 *>(x + (size_t)YAWB_RSTRIDE * (tl.start + k));
+            const double2 a = row[0], b = row[1];
+            X[r] = a.x; Y[r] = a.y; Z[r] = b.x;
+        }
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -1267,7 +1271,10 @@ int yawb_index_build_second(yawb_cat *cat) {
     const long long n = cat->n;
     const int P = cat->n_patch, B = cat->n_bins;
 
-    if (dev_alloc(cat, &cat->rx, n) || dev_alloc(cat, &cat->ry, n) || dev_alloc(cat, &cat->rz, n)) return 1;
+    if (dev_alloc(cat, &cat->rrow, (size_t)n * YAWB_RSTRIDE)) return 1;
+    cat->rx = cat->rrow;
+    cat->ry = cat->rrow + 1;
+    cat->rz = cat->rrow + 2;
     if (cat->weighted && dev_alloc(cat, &cat->rw, n)) return 1;
     // 32-bit sort keys when (patch, bin) leaves at least 16 bits (an even number) for the Hilbert index
     {
@@ -1407,7 +1414,8 @@ void yawb_index_free(yawb_cat *cat, bool everything) {
     }
     yawb_findex_drop_fused(cat->ctx, cat);
     if (cat->has_rtiles || everything) {
-        dev_free(cat, cat->rx, n); dev_free(cat, cat->ry, n); dev_free(cat, cat->rz, n);
+        dev_free(cat, cat->rrow, n * YAWB_RSTRIDE);
+        cat->rx = cat->ry = cat->rz = nullptr;
         dev_free(cat, cat->rw, n);
         dev_free(cat, cat->d_tiles, (size_t)cat->n_tiles);
         dev_free(cat, cat->d_tile_box, (size_t)cat->n_tiles);

@@ -116,6 +116,7 @@ struct BinPar {
 
 constexpr int YAWB_RPL = 8;               // second-role points per lane
 constexpr int YAWB_TILE = 32 * YAWB_RPL;  // points per register tile (one warp)
+constexpr int YAWB_RSTRIDE = 4;           // doubles per second-role row record (x, y, z, unused): one 32-byte sector
 constexpr int YAWB_LCAP = 256;            // candidate list capacity per warp
 constexpr int YAWB_WARPS = 4;             // warps per CTA in the count kernel
 #ifndef YAWB_MIN_CTAS_VALUE
@@ -193,7 +194,9 @@ struct yawb_cat {
 
     // second-role index: rows sorted by (patch, bin, Hilbert index), cut into register tiles
     bool has_rtiles = false;
-    double *rx = nullptr, *ry = nullptr, *rz = nullptr, *rw = nullptr;
+    double *rrow = nullptr;                   // second-role rows in tile order, one 32-byte record (x, y, z, -) per row
+    double *rx = nullptr, *ry = nullptr, *rz = nullptr;  // views of rrow: row j is rx[4 j], ry[4 j], rz[4 j]
+    double *rw = nullptr;
     Tile *d_tiles = nullptr;
     TileBox *d_tile_box = nullptr;  // [n_tiles] bounding boxes in the frame of the tile's own patch
     std::vector<Tile> h_tiles;     // host copy of the tile table (source of an async upload)
