@@ -470,30 +470,33 @@ __global__ void k_keys_second(const double *__restrict__ x, const double *__rest
 
 // ---- counting sort ------------------------------------------------------------------------------------
 // The sort keys are bounded and dense (sky-cell ids, (patch, z-bin, Hilbert cell) ids: about as many keys as rows),
-// so the rows are put in order by ONE histogram pass, an in-place exclusive scan of the key counts, and ONE
-// scatter pass that recomputes the key, takes the next free slot of its key with an atomic and writes the row's
-// payload straight to its final position.  The order of rows with the same key is arbitrary (it has no meaning:
-// pair counts are sums over all rows of a cell).  cur[k] holds the count of key k after the histogram, the first
-// slot of key k after the scan and the first slot of key k + 1 after the scatter -- which makes (0, cur[0],
-// cur[1], ...) the cell_start table of a first-role index without another pass.
+// so the rows are put in order by ONE histogram pass that also hands every row its rank among the rows of its
+// key (the value the atomic returns), an in-place exclusive scan of the key counts, and ONE scatter pass without
+// atomics: position = first slot of the key + rank.  (key, rank) of a row travel from the first pass to the second
+// in an 8-byte side array, so the second pass neither walks the curve again nor waits for an atomic.  The order of
+// rows with the same key is arbitrary (it has no meaning: pair counts are sums over all rows of a cell).  After the
+// scan cur[k] is the first slot of key k, i.e. the cell_start table of a first-role index (entry n_keys = row count).
 __global__ void k_hist_first(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                              const int *__restrict__ bin, const int *__restrict__ patch, long long n, int n_bins,
                              const PatchFrame *__restrict__ frames, const SGrid *__restrict__ grids,
-                             int *__restrict__ cur) {
+                             int *__restrict__ cur, int2 *__restrict__ kr) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long key = key_first(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, frames, grids);
-    if (key >= 0) atomicAdd(&cur[key], 1);
+    int rank = 0;
+    if (key >= 0) rank = atomicAdd(&cur[key], 1);
+    kr[i] = make_int2((int)key, rank);  // -1: dropped row
 }
 
 __global__ void k_hist_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                               const int *__restrict__ bin, const int *__restrict__ patch, long long n, int n_bins,
-                              int hbits, const HMap *__restrict__ maps, int *__restrict__ cur, int *__restrict__ keys) {
+                              int hbits, const HMap *__restrict__ maps, int *__restrict__ cur, int2 *__restrict__ kr) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long key = key_second(x[3 * i], y[3 * i], z[3 * i], bin ? bin[i] : 0, patch[i], n_bins, hbits, maps);
-    keys[i] = (int)key;  // the scatter pass reads the key back instead of walking the curve again (-1: dropped row)
-    if (key >= 0) atomicAdd(&cur[key], 1);
+    int rank = 0;
+    if (key >= 0) rank = atomicAdd(&cur[key], 1);
+    kr[i] = make_int2((int)key, rank);  // -1: dropped row
 }
 
 // in-place exclusive scan of `cur[0, n)` in ONE pass over the data (decoupled look-back): a block takes the next
@@ -591,15 +594,15 @@ __global__ void __launch_bounds__(kThreads) k_scan_lookback(int *__restrict__ cu
 
 // second-role scatter: the row goes to the next free slot of its key
 __global__ void k_scatter_second(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-                                 const double *__restrict__ w, const int *__restrict__ keys, long long n,
-                                 int *__restrict__ cur, double *__restrict__ ox, double *__restrict__ oy,
+                                 const double *__restrict__ w, const int2 *__restrict__ kr, long long n,
+                                 const int *__restrict__ cur, double *__restrict__ ox, double *__restrict__ oy,
                                  double *__restrict__ oz, double *__restrict__ ow) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int key = keys[i];
-    if (key < 0) return;
+    const int2 k = kr[i];
+    if (k.x < 0) return;
     const double X = x[3 * i], Y = y[3 * i], Z = z[3 * i];
-    const int pos = atomicAdd(&cur[key], 1);
+    const int pos = cur[k.x] + k.y;
     // one 32-byte record per row: a full sector per scattered store (three separate arrays cost three partial ones)
     double2 *const o = reinterpret_cast<double2 *>(ox + (size_t)YAWB_RSTRIDE * pos);
     o[0] = make_double2(X, Y);
@@ -612,15 +615,15 @@ __global__ void k_scatter_second(const double *__restrict__ x, const double *__r
 __global__ void k_scatter_first(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                                 const double *__restrict__ w, const int *__restrict__ bin, const int *__restrict__ patch,
                                 long long n, int n_bins, unsigned type_bit, const PatchFrame *__restrict__ frames,
-                                const SGrid *__restrict__ grids, int *__restrict__ cur, double *__restrict__ ow,
-                                SRec *__restrict__ orec) {
+                                const SGrid *__restrict__ grids, const int *__restrict__ cur, const int2 *__restrict__ kr,
+                                double *__restrict__ ow, SRec *__restrict__ orec) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int2 k = kr[i];
+    if (k.x < 0) return;
     const double X = x[3 * i], Y = y[3 * i], Z = z[3 * i];
     const int p = patch[i];
-    const long long key = key_first(X, Y, Z, bin ? bin[i] : 0, p, n_bins, frames, grids);
-    if (key < 0) return;
-    const int pos = atomicAdd(&cur[key], 1);
+    const int pos = cur[k.x] + k.y;
     if (ow) ow[pos] = w ? w[i] : 1.0;  // fused index of a weighted and an unweighted catalog
     const PatchFrame &f = frames[p];
     const SGrid &g = grids[p];
@@ -827,18 +830,21 @@ int build_first_counting(FIndex *fi, long long base) {
     cudaStream_t st = ctx->stream;
     const yawb_cat *a = fi->a, *b = fi->b;
     Scratch scr(ctx, st);
-    int *cur = fi->cell_start + 1;  // see the note on cur[] above: cell_start = (0, cur[0], cur[1], ...) at the end
+    int *cur = fi->cell_start;  // key counts -> (exclusive scan over base + 1 entries) -> cell_start, the last entry = rows
+    const long long na = a && a->n_in > 0 ? a->n_in : 0, nb = b && b->n_in > 0 ? b->n_in : 0;
+    int2 *kr = scr.get<int2>((size_t)(na + nb));
+    YAWB_REQUIRE(kr != nullptr, "out of device memory (sort keys)");
     YAWB_CUDA(cudaMemsetAsync(fi->cell_start, 0, (size_t)(base + 1) * sizeof(int), st));
     for (const yawb_cat *c : {a, b})
         if (c && c->n_in > 0)
             k_hist_first<<<blocks_for(c->n_in), kThreads, 0, st>>>(c->x, c->y, c->z, c->bin, c->patch, c->n_in, fi->n_bins,
-                                                                   fi->d_frames, fi->d_sgrid, cur);
-    if (exclusive_scan_inplace(ctx, scr, cur, base)) return 1;
+                                                                   fi->d_frames, fi->d_sgrid, cur, kr + (c == b ? na : 0));
+    if (exclusive_scan_inplace(ctx, scr, cur, base + 1)) return 1;
     for (const yawb_cat *c : {a, b})
         if (c && c->n_in > 0)
             k_scatter_first<<<blocks_for(c->n_in), kThreads, 0, st>>>(c->x, c->y, c->z, c->w, c->bin, c->patch, c->n_in,
                                                                       fi->n_bins, c == b ? 0x80000000u : 0u, fi->d_frames,
-                                                                      fi->d_sgrid, cur, fi->sw, fi->rec);
+                                                                      fi->d_sgrid, cur, kr + (c == b ? na : 0), fi->sw, fi->rec);
     return 0;
 }
 
@@ -849,7 +855,7 @@ int build_second_counting(yawb_cat *cat, int hbits, long long n_keys) {
     if (cat->n_in <= 0) return 0;
     Scratch scr(ctx, st);
     int *cur = scr.get<int>((size_t)n_keys);
-    int *keys = scr.get<int>((size_t)cat->n_in);
+    int2 *keys = scr.get<int2>((size_t)cat->n_in);  // (key, rank among the rows of the key) of every row
     HMap *maps = scr.get<HMap>((size_t)cat->n_patch);
     YAWB_REQUIRE(cur && keys && maps, "out of device memory (key counts)");
     YAWB_CUDA(cudaMemsetAsync(cur, 0, (size_t)n_keys * sizeof(int), st));
