@@ -816,7 +816,8 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
         const size_t smem = STREAM_WARPS * per_warp;
         YAWB_REQUIRE(smem <= 227 * 1024, "too many z-bins x sub-bins for the shared-memory accumulators (%zu B)", smem);
         // persistent grid: a multiple of the SM count, warps pull items from a global counter
-        const int per_sm = std::max(1, std::min(STREAM_CTAS, (int)((227 * 1024) / (smem + 1024))));
+        int per_sm = std::max(1, std::min(STREAM_CTAS, (int)((227 * 1024) / (smem + 1024))));
+        if (const char *e = getenv("YAWB_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         const int ctas = ctx->sms * per_sm;
 #define LAUNCH(W, M, T)                                                                                      \
     do {                                                                                                     \
