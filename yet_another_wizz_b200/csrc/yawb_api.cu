@@ -193,6 +193,7 @@ int yawb_destroy(yawb_ctx *ctx) {
     cudaFree(ctx->d_counters);
     if (ctx->pin_base) cudaFreeHost(ctx->pin_base);
     if (ctx->h2d_base) cudaFreeHost(ctx->h2d_base);
+    if (ctx->res_pin) cudaFreeHost(ctx->res_pin);
     cudaStreamDestroy(ctx->copy_stream);
     yawb_dcache_destroy(ctx);
     cudaEventDestroy(ctx->ev0);
@@ -614,9 +615,24 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
 
     int launches = 0;
     unsigned long long h_counters[8] = {0};
-    const cudaMemcpyKind kind = (flags & YAWB_FLAG_OUT_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    double *d_tmp = nullptr;
-    if (!weighted && !(flags & YAWB_FLAG_OUT_DEVICE) && n_out && (out_f64[0] || out_f64[1])) DALLOC(d_tmp, n_out * sizeof(double));
+    const bool to_device = (flags & YAWB_FLAG_OUT_DEVICE) != 0;
+    // Host results land in page-locked memory of the context first (counters, counts, sums: one copy each, truly
+    // asynchronous) and are handed to the caller's -- usually pageable -- arrays after the one synchronisation of
+    // the call; a cudaMemcpyAsync into pageable memory is staged by the driver, one blocking round trip per array.
+    // Unweighted sums are the counts as doubles: converted on the host.
+    unsigned char *pin = nullptr;
+    const size_t pin_cnt = 64, pin_w = pin_cnt + std::max<size_t>(n_out, 1) * sizeof(unsigned long long);
+    if (!to_device) {
+        const size_t need = pin_w + (weighted ? std::max<size_t>(n_out, 1) * sizeof(double) : 0);
+        if (ctx->res_pin_size < need) {
+            if (ctx->res_pin) cudaFreeHost(ctx->res_pin);
+            ctx->res_pin = nullptr;
+            ctx->res_pin_size = 0;
+            TRY(cudaHostAlloc((void **)&ctx->res_pin, need + need / 2, cudaHostAllocDefault));
+            ctx->res_pin_size = need + need / 2;
+        }
+        pin = ctx->res_pin;
+    }
     for (int attempt = 0;; ++attempt) {
         TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
         if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
@@ -624,38 +640,54 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         TRY(cudaEventRecord(ctx->ev0, st));
         int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
                                                       : yawb_launch_count_fast(ctx, a, &launches);
-        if (rc) { cleanup(); if (d_tmp) yawb_dfree(ctx, d_tmp, st); return rc; }
+        if (rc) { cleanup(); return rc; }
         TRY(cudaEventRecord(ctx->ev1, st));
-        TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
         // the results travel right behind the counters (ONE synchronisation per call); should a work-item list have
         // been too small -- the host only learns that now -- the count is repeated with the exact sizes
-        for (int t = 0; t < n_types && n_out1; ++t) {
-            if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), kind, st));
-            if (out_f64[t]) {
-                if (weighted) {
-                    TRY(cudaMemcpyAsync(out_f64[t], d_w + t * n_out1, n_out1 * sizeof(double), kind, st));
-                } else if (flags & YAWB_FLAG_OUT_DEVICE) {
-                    k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, out_f64[t], (long long)n_out1);
-                    launches += 1;
-                } else {
-                    k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, d_tmp + t * n_out1, (long long)n_out1);
-                    launches += 1;
-                    TRY(cudaMemcpyAsync(out_f64[t], d_tmp + t * n_out1, n_out1 * sizeof(double), kind, st));
+        if (to_device) {
+            TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            for (int t = 0; t < n_types && n_out1; ++t) {
+                if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+                if (out_f64[t]) {
+                    if (weighted) {
+                        TRY(cudaMemcpyAsync(out_f64[t], d_w + t * n_out1, n_out1 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                    } else {
+                        k_u64_to_f64<<<(unsigned)((n_out1 + 255) / 256), 256, 0, st>>>(d_cnt + t * n_out1, out_f64[t], (long long)n_out1);
+                        launches += 1;
+                    }
                 }
             }
+            TRY(cudaStreamSynchronize(st));
+        } else {
+            TRY(cudaMemcpyAsync(pin, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            if (n_out) TRY(cudaMemcpyAsync(pin + pin_cnt, d_cnt, n_out * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            if (n_out && weighted) TRY(cudaMemcpyAsync(pin + pin_w, d_w, n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
+            TRY(cudaStreamSynchronize(st));
+            memcpy(h_counters, pin, sizeof(h_counters));
         }
-        TRY(cudaStreamSynchronize(st));
         if (!h_counters[6]) break;
         if (attempt > 0) {
             yawb_set_error("work-item lists overflowed twice (%llu + %llu items)", h_counters[4], h_counters[5]);
             cleanup();
-            if (d_tmp) yawb_dfree(ctx, d_tmp, st);
             return 2;
         }
         a.cap_heavy = (long long)h_counters[4] + 1024;
         a.cap_light = (long long)h_counters[5] + 1024;
     }
-    if (d_tmp) yawb_dfree(ctx, d_tmp, st);
+    if (!to_device) {
+        const unsigned long long *h_cnt = reinterpret_cast<const unsigned long long *>(pin + pin_cnt);
+        const double *h_w = reinterpret_cast<const double *>(pin + pin_w);
+        for (int t = 0; t < n_types && n_out1; ++t) {
+            if (out_i64[t]) memcpy(out_i64[t], h_cnt + t * n_out1, n_out1 * sizeof(int64_t));
+            if (out_f64[t]) {
+                if (weighted) {
+                    memcpy(out_f64[t], h_w + t * n_out1, n_out1 * sizeof(double));
+                } else {
+                    for (size_t k = 0; k < n_out1; ++k) out_f64[t][k] = (double)h_cnt[t * n_out1 + k];
+                }
+            }
+        }
+    }
     TRY(cudaGetLastError());
     float t_k = 0.f;
     TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));

@@ -143,6 +143,8 @@ struct yawb_ctx {
     int pin_live = 0;
     struct yawb_devcache *cache = nullptr;  // device blocks, recycled (yawb_alloc.cu)
     // pinned arena that small host tables pass through on their way to the device (yawb_h2d_small)
+    unsigned char *res_pin = nullptr;  // page-locked landing area of a count's results (grown on demand)
+    size_t res_pin_size = 0;
     unsigned char *h2d_base = nullptr;
     size_t h2d_size = 0, h2d_used = 0;
     std::vector<struct FIndex *> fused;  // first-role indexes over pairs of catalogs (yawb_count2)
