@@ -521,8 +521,10 @@ def run_gpu_arm(args):
         red = dict(full=torch.zeros((slabs, 4, n_pairs_max, plan.n_bins, n_sub), dtype=torch.float64 if any_weighted else torch.int64,
                                     device="cuda"),
                    own=torch.from_numpy(own).cuda(),
-                   buf={tag: (torch.zeros(shape_own, dtype=torch.float64, device="cuda"), torch.zeros(shape_own, dtype=torch.int64, device="cuda"))
-                        for tag in COUNT_TYPES})
+                   stack_f=torch.zeros((4,) + shape_own, dtype=torch.float64, device="cuda"),
+                   stack_i=torch.zeros((4,) + shape_own, dtype=torch.int64, device="cuda"))
+        # per count type (sums, counts): views of the two stacked tensors, so that ONE index_copy_ moves all four
+        red["buf"] = {tag: (red["stack_f"][t], red["stack_i"][t]) for t, tag in enumerate(COUNT_TYPES)}
 
     def count_all(dev, on_device: bool):
         results, stats = {}, {}
@@ -533,8 +535,8 @@ def run_gpu_arm(args):
         if fuse:
             for (ta, tb), k2 in ((("DD", "RD"), "unk"), (("DR", "RR"), "unk_rand")):
                 if on_device:
-                    ptrs = (red["buf"][ta][0].data_ptr(), red["buf"][ta][1].data_ptr(), red["buf"][tb][0].data_ptr(),
-                            red["buf"][tb][1].data_ptr())
+                    # only the array the reduce takes: sums of weighted catalogs, counts otherwise
+                    ptrs = tuple(red["buf"][tg][k].data_ptr() if (k == 0) == weighted_tag[tg] else 0 for tg in (ta, tb) for k in (0, 1))
                     _, _, st = eng.count2(dev["ref"], dev["ref_rand"], dev[k2], opi, opj, plan.r2, out_device=ptrs)
                 else:
                     (ia, fa), (ib, fb), st = eng.count2(dev["ref"], dev["ref_rand"], dev[k2], opi, opj, plan.r2)
@@ -544,7 +546,8 @@ def run_gpu_arm(args):
             for tag in ("DD", "RD", "DR", "RR"):
                 a, b = COUNT_TYPES[tag]
                 if on_device:
-                    st = eng.count_into_device(dev[a], dev[b], opi, opj, plan.r2, red["buf"][tag][0].data_ptr(), red["buf"][tag][1].data_ptr())
+                    st = eng.count_into_device(dev[a], dev[b], opi, opj, plan.r2, red["buf"][tag][0].data_ptr() if weighted_tag[tag] else 0,
+                                               0 if weighted_tag[tag] else red["buf"][tag][1].data_ptr())
                 else:
                     ci, cf, st = eng.count(dev[a], dev[b], opi, opj, plan.r2)
                     results[tag] = pick(tag, ci, cf)
@@ -555,9 +558,12 @@ def run_gpu_arm(args):
         """scatter this rank's rows into the job-wide tensor and sum-reduce it to rank 0 (NCCL over NVLink)"""
         full = red["full"]
         full.zero_()
-        for t, tag in enumerate(COUNT_TYPES):
-            src = red["buf"][tag][0 if weighted_tag[tag] else 1]
-            full[rank if weak else 0, t].index_copy_(0, red["own"], src.to(full.dtype))
+        if all(weighted_tag.values()) or not any_weighted:  # one scatter for the four count types
+            full[rank if weak else 0].index_copy_(1, red["own"], red["stack_f"] if any_weighted else red["stack_i"])
+        else:
+            for t, tag in enumerate(COUNT_TYPES):
+                src = red["buf"][tag][0 if weighted_tag[tag] else 1]
+                full[rank if weak else 0, t].index_copy_(0, red["own"], src.to(full.dtype))
         dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)
         return full
 

@@ -122,12 +122,15 @@ __global__ void k_patch_ids(const long long *__restrict__ patch_off, int n_patch
 }
 
 // per patch: sum of unit vectors; per (bin, patch): row count and sum of weights.
-// A block owns kSumRows consecutive rows; rows of the block's first patch are accumulated in shared
-// memory (rows are grouped by patch, so that is nearly all of them) and flushed with one global atomic
-// per z-bin; stragglers of the next patch go to global memory directly.
+// A block owns kSumRows consecutive rows.  Rows are grouped by patch, so a block nearly always meets one patch or
+// two (a boundary inside its range): the rows of its FIRST and of its LAST patch are accumulated in registers /
+// shared memory and flushed with one global atomic per quantity; only rows of a third patch in between (patches
+// smaller than a block) go to global memory one by one.  (Round 1 sent every row behind the boundary to global
+// atomics on the same few addresses: ~2000 serialised atomics per address and boundary, 90 us per launch
+// whatever the catalog size.)
 constexpr int kSumRows = 4096;
 constexpr int kSumBatch = 4;  // rows in flight per thread
-constexpr int kSumMaxBins = 2048;
+constexpr int kSumMaxBins = 1024;
 
 __global__ void __launch_bounds__(kThreads) k_patch_sums(
     const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
@@ -135,22 +138,23 @@ __global__ void __launch_bounds__(kThreads) k_patch_sums(
     int n_patch, int n_bins, double *__restrict__ sums /*[n_patch][3]*/, unsigned long long *__restrict__ counts,
     double *__restrict__ sumw) {
     extern __shared__ unsigned char sm_raw[];
-    double *s_xyz = (double *)sm_raw;                 // [3]
-    double *s_w = s_xyz + 4;                          // [n_bins] (if weighted and it fits)
     const bool use_smem = n_bins <= kSumMaxBins;
-    unsigned *s_cnt = (unsigned *)(s_w + (w && use_smem ? n_bins : 0));  // [n_bins]
+    const int nb = use_smem ? n_bins : 0;
+    // two slots (first / last patch of the block): [2][4] sums, [2][nb] weights (if weighted), [2][nb] counts
+    double *s_xyz = (double *)sm_raw;
+    double *s_w = s_xyz + 8;
+    unsigned *s_cnt = (unsigned *)(s_w + (w ? 2 * nb : 0));
     const long long row0 = (long long)blockIdx.x * kSumRows;
-    const int p_blk = patch[row0];
-    if (threadIdx.x < 3) s_xyz[threadIdx.x] = 0.0;
-    if (use_smem)
-        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
-            s_cnt[b] = 0u;
-            if (w) s_w[b] = 0.0;
-        }
+    const long long row1 = min(row0 + (long long)kSumRows, n);
+    const int p_blk = patch[row0], p_end = patch[row1 - 1];
+    if (threadIdx.x < 8) s_xyz[threadIdx.x] = 0.0;
+    for (int b = threadIdx.x; b < 2 * nb; b += blockDim.x) {
+        s_cnt[b] = 0u;
+        if (w) s_w[b] = 0.0;
+    }
     __syncthreads();
-    double ax = 0.0, ay = 0.0, az = 0.0;
-    // kSumBatch rows per thread and round, every load of a round requested before the first is used (a loop with one
-    // row in flight per thread is latency-bound: 2.7 TB/s)
+    double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+    // kSumBatch rows per thread and round, every load of a round requested before the first is used
     for (int k0 = threadIdx.x; k0 < kSumRows; k0 += kSumBatch * blockDim.x) {
         int p[kSumBatch], b[kSumBatch];
         double X[kSumBatch], Y[kSumBatch], Z[kSumBatch], W[kSumBatch];
@@ -169,22 +173,19 @@ __global__ void __launch_bounds__(kThreads) k_patch_sums(
         for (int q = 0; q < kSumBatch; ++q) {
             if (p[q] < 0) continue;
             const bool in_bin = b[q] >= 0 && b[q] < n_bins;
-            if (p[q] == p_blk) {
-                ax += X[q]; ay += Y[q]; az += Z[q];
-                if (in_bin) {
-                    if (use_smem) {
-                        atomicAdd(&s_cnt[b[q]], 1u);
-                        if (w) atomicAdd(&s_w[b[q]], W[q]);
-                    } else {
-                        atomicAdd(&counts[(size_t)b[q] * n_patch + p[q]], 1ull);
-                        if (w) atomicAdd(&sumw[(size_t)b[q] * n_patch + p[q]], W[q]);
-                    }
-                }
-            } else {
+            const int slot = p[q] == p_blk ? 0 : p[q] == p_end ? 1 : -1;
+            if (slot == 0) { ax += X[q]; ay += Y[q]; az += Z[q]; }
+            else if (slot == 1) { bx += X[q]; by += Y[q]; bz += Z[q]; }
+            else {
                 atomicAdd(&sums[3 * p[q]], X[q]);
                 atomicAdd(&sums[3 * p[q] + 1], Y[q]);
                 atomicAdd(&sums[3 * p[q] + 2], Z[q]);
-                if (in_bin) {
+            }
+            if (in_bin) {
+                if (slot >= 0 && use_smem) {
+                    atomicAdd(&s_cnt[slot * nb + b[q]], 1u);
+                    if (w) atomicAdd(&s_w[slot * nb + b[q]], W[q]);
+                } else {
                     atomicAdd(&counts[(size_t)b[q] * n_patch + p[q]], 1ull);
                     if (w) atomicAdd(&sumw[(size_t)b[q] * n_patch + p[q]], W[q]);
                 }
@@ -195,19 +196,29 @@ __global__ void __launch_bounds__(kThreads) k_patch_sums(
         ax += __shfl_xor_sync(0xffffffffu, ax, o);
         ay += __shfl_xor_sync(0xffffffffu, ay, o);
         az += __shfl_xor_sync(0xffffffffu, az, o);
+        bx += __shfl_xor_sync(0xffffffffu, bx, o);
+        by += __shfl_xor_sync(0xffffffffu, by, o);
+        bz += __shfl_xor_sync(0xffffffffu, bz, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&s_xyz[0], ax);
         atomicAdd(&s_xyz[1], ay);
         atomicAdd(&s_xyz[2], az);
+        if (p_end != p_blk) {
+            atomicAdd(&s_xyz[4], bx);
+            atomicAdd(&s_xyz[5], by);
+            atomicAdd(&s_xyz[6], bz);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 3) atomicAdd(&sums[3 * p_blk + threadIdx.x], s_xyz[threadIdx.x]);
-    if (use_smem)
-        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
-            if (s_cnt[b]) atomicAdd(&counts[(size_t)b * n_patch + p_blk], (unsigned long long)s_cnt[b]);
-            if (w && s_w[b] != 0.0) atomicAdd(&sumw[(size_t)b * n_patch + p_blk], s_w[b]);
-        }
+    if (p_end != p_blk && threadIdx.x >= 4 && threadIdx.x < 7) atomicAdd(&sums[3 * p_end + threadIdx.x - 4], s_xyz[threadIdx.x]);
+    for (int k = threadIdx.x; k < 2 * nb; k += blockDim.x) {
+        const int slot = k >= nb ? 1 : 0, b = k - slot * nb;
+        const int pp = slot ? p_end : p_blk;
+        if (s_cnt[k]) atomicAdd(&counts[(size_t)b * n_patch + pp], (unsigned long long)s_cnt[k]);
+        if (w && s_w[k] != 0.0) atomicAdd(&sumw[(size_t)b * n_patch + pp], s_w[k]);
+    }
 }
 
 // frames from the per-patch sums: centre = mean direction, e1/e2 any orthonormal tangent basis
@@ -261,17 +272,38 @@ __global__ void k_finish_frames(const unsigned long long *__restrict__ box, int 
 }
 
 // per patch: (u, v) bounding box and max squared chord distance from the centre.  Same blocking as
-// k_patch_sums: a block owns kSumRows consecutive rows, reduces the rows of its first patch in
-// registers / shuffles / shared memory and issues five atomics; stragglers of the next patch go direct.
+// k_patch_sums: a block owns kSumRows consecutive rows and reduces the rows of its first and of its last patch in
+// registers / shuffles / shared memory (six atomics per patch and block); rows of a third patch go direct.
+struct BoxAcc {
+    unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull, nmax = 0ull;
+    __device__ __forceinline__ void add(unsigned long long eu, unsigned long long ev, unsigned long long ed, unsigned long long en) {
+        umin = min(umin, eu); umax = max(umax, eu);
+        vmin = min(vmin, ev); vmax = max(vmax, ev);
+        dmax = max(dmax, ed);
+        nmax = max(nmax, en);
+    }
+    __device__ __forceinline__ void warp_reduce() {
+        for (int o = 16; o; o >>= 1) {
+            umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+            umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+            vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        }
+    }
+};
+
 __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restrict__ x, const double *__restrict__ y,
                                                          const double *__restrict__ z, const int *__restrict__ patch,
                                                          long long n, const PatchFrame *__restrict__ frames,
-                                                         unsigned long long *__restrict__ box /*[n_patch][5]*/) {
-    __shared__ unsigned long long s_box[kBox][kThreads / 32];
+                                                         unsigned long long *__restrict__ box /*[n_patch][kBox]*/) {
+    __shared__ unsigned long long s_box[2][kBox][kThreads / 32];
     const long long row0 = (long long)blockIdx.x * kSumRows;
-    const int p_blk = patch[row0];
-    const PatchFrame f = frames[p_blk];
-    unsigned long long umin = ~0ull, umax = 0ull, vmin = ~0ull, vmax = 0ull, dmax = 0ull, nmax = 0ull;
+    const long long row1 = min(row0 + (long long)kSumRows, n);
+    const int p_blk = patch[row0], p_end = patch[row1 - 1];
+    const PatchFrame f = frames[p_blk], f2 = frames[p_end];
+    BoxAcc A, B;
     for (int k0 = threadIdx.x; k0 < kSumRows; k0 += kSumBatch * blockDim.x) {
         int pq[kSumBatch];
         double X[kSumBatch], Y[kSumBatch], Z[kSumBatch];
@@ -288,7 +320,7 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
         for (int q = 0; q < kSumBatch; ++q) {
             const int p = pq[q];
             if (p < 0) continue;
-            const PatchFrame &g = p == p_blk ? f : frames[p];
+            const PatchFrame &g = p == p_blk ? f : p == p_end ? f2 : frames[p];
             const double dx = X[q] - g.c[0], dy = Y[q] - g.c[1], dz = Z[q] - g.c[2];
             const unsigned long long eu = enc_double(dx * g.e1[0] + dy * g.e1[1] + dz * g.e1[2]);
             const unsigned long long ev = enc_double(dx * g.e2[0] + dy * g.e2[1] + dz * g.e2[2]);
@@ -299,10 +331,9 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
                 enc_double(fabs(dx * (X[q] + g.c[0]) + dy * (Y[q] + g.c[1]) + dz * (Z[q] + g.c[2])) +
                            fabs(g.c[0] * g.c[0] + g.c[1] * g.c[1] + g.c[2] * g.c[2] - 1.0));
             if (p == p_blk) {
-                umin = min(umin, eu); umax = max(umax, eu);
-                vmin = min(vmin, ev); vmax = max(vmax, ev);
-                dmax = max(dmax, ed);
-                nmax = max(nmax, en);
+                A.add(eu, ev, ed, en);
+            } else if (p == p_end) {
+                B.add(eu, ev, ed, en);
             } else {
                 atomicMin(&box[kBox * p], eu);
                 atomicMax(&box[kBox * p + 1], eu);
@@ -313,25 +344,23 @@ __global__ void __launch_bounds__(kThreads) k_patch_bbox(const double *__restric
             }
         }
     }
-    for (int o = 16; o; o >>= 1) {
-        umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-        umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-        vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-    }
+    A.warp_reduce();
+    B.warp_reduce();
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        s_box[0][w] = umin; s_box[1][w] = umax; s_box[2][w] = vmin; s_box[3][w] = vmax; s_box[4][w] = dmax; s_box[5][w] = nmax;
+        s_box[0][0][w] = A.umin; s_box[0][1][w] = A.umax; s_box[0][2][w] = A.vmin; s_box[0][3][w] = A.vmax; s_box[0][4][w] = A.dmax; s_box[0][5][w] = A.nmax;
+        s_box[1][0][w] = B.umin; s_box[1][1][w] = B.umax; s_box[1][2][w] = B.vmin; s_box[1][3][w] = B.vmax; s_box[1][4][w] = B.dmax; s_box[1][5][w] = B.nmax;
     }
     __syncthreads();
-    if (threadIdx.x < kBox) {
-        unsigned long long v = s_box[threadIdx.x][0];
-        const bool is_min = threadIdx.x == 0 || threadIdx.x == 2;
-        for (int k = 1; k < kThreads / 32; ++k) v = is_min ? min(v, s_box[threadIdx.x][k]) : max(v, s_box[threadIdx.x][k]);
-        if (is_min) atomicMin(&box[kBox * p_blk + threadIdx.x], v);  // ~0 / 0 are the neutral initial values
-        else atomicMax(&box[kBox * p_blk + threadIdx.x], v);
+    if (threadIdx.x < 2 * kBox) {
+        const int slot = threadIdx.x / kBox, c = threadIdx.x % kBox;
+        if (slot == 1 && p_end == p_blk) return;
+        unsigned long long v = s_box[slot][c][0];
+        const bool is_min = c == 0 || c == 2;
+        for (int k = 1; k < kThreads / 32; ++k) v = is_min ? min(v, s_box[slot][c][k]) : max(v, s_box[slot][c][k]);
+        const int pp = slot ? p_end : p_blk;
+        if (is_min) atomicMin(&box[kBox * pp + c], v);  // ~0 / 0 are the neutral initial values
+        else atomicMax(&box[kBox * pp + c], v);
     }
 }
 
@@ -1026,7 +1055,7 @@ int yawb_cat_finalize(yawb_cat *cat) {
             }
             const bool use_smem = B <= kSumMaxBins;
             const size_t smem =
-                4 * sizeof(double) + (use_smem ? (size_t)B * (sizeof(unsigned) + (cat->w ? sizeof(double) : 0)) : 0);
+                8 * sizeof(double) + (use_smem ? 2 * (size_t)B * (sizeof(unsigned) + (cat->w ? sizeof(double) : 0)) : 0);
             k_patch_sums<<<blocks_for(n, kSumRows), kThreads, smem, st>>>(cat->x, cat->y, cat->z, cat->w, cat->bin,
                                                                            cat->patch, n, P, B, d_sums, d_counts, d_sumw);
         }
