@@ -546,28 +546,30 @@ __global__ void __launch_bounds__(kThreads) k_scan_lookback(int *__restrict__ cu
     __syncthreads();
     const long long tile = s_tile;
     volatile unsigned long long *const d = desc + 1;
-    const long long base = tile * kScanBlock + (long long)threadIdx.x * kScanPerThread;
-    int v[kScanPerThread];
-    int tot = 0;
-    if (base + kScanPerThread <= n) {  // cur is 4-byte aligned only (cell_start + 1): scalar loads, two full sectors per thread
-#pragma unroll
-        for (int k = 0; k < kScanPerThread; ++k) v[k] = cur[base + k];
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanPerThread; ++k) v[k] = base + k < n ? cur[base + k] : 0;
-    }
-#pragma unroll
-    for (int k = 0; k < kScanPerThread; ++k) tot += v[k];
-    int incl = tot;
+    // A warp owns kScanPerThread rows of 32 consecutive counts (coalesced loads and stores: with 16 consecutive counts
+    // per THREAD every load instruction touched 32 sectors and the kernel sat in the LSU queue); rows are scanned
+    // with shuffles, the row totals carried along in a register.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long base = tile * kScanBlock + (long long)warp * (32 * kScanPerThread) + lane;
+    int v[kScanPerThread];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    for (int r = 0; r < kScanPerThread; ++r) v[r] = base + 32 * r < n ? cur[base + 32 * r] : 0;
+    int excl[kScanPerThread];  // exclusive prefix of the element within the warp's 512 counts
+    int carry = 0;
+#pragma unroll
+    for (int r = 0; r < kScanPerThread; ++r) {
+        int incl = v[r];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        excl[r] = carry + incl - v[r];
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 31) s_w[warp] = incl;
+    if (lane == 0) s_w[warp] = carry;
     __syncthreads();
-    int before = 0, block_total = 0;  // rows of the warps before this one; of the whole tile
+    int before = 0, block_total = 0;  // counts of the warps before this one; of the whole tile
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) {
         const int t = s_w[w];
@@ -613,12 +615,10 @@ __global__ void __launch_bounds__(kThreads) k_scan_lookback(int *__restrict__ cu
         if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    int run = (int)s_prefix + before + incl - tot;
+    const int off = (int)s_prefix + before;
 #pragma unroll
-    for (int k = 0; k < kScanPerThread; ++k) {
-        if (base + k < n) cur[base + k] = run;
-        run += v[k];
-    }
+    for (int r = 0; r < kScanPerThread; ++r)
+        if (base + 32 * r < n) cur[base + 32 * r] = off + excl[r];
 }
 
 // second-role scatter: the row goes to the next free slot of its key
