@@ -511,6 +511,8 @@ def run_gpu_arm(args):
     # the reference sample and its randoms are counted in one pass against each unbinned catalog (yawb_count2)
     # unless only one of them carries weights
     fuse = (arrays["ref"]["weights"] is None) == (arrays["ref_rand"]["weights"] is None) and not args.no_fuse
+    # ... and both passes in one launch (yawb_count4) when the two unbinned catalogs are of the same kind as well
+    fuse4 = fuse and not args.no_fuse4 and (arrays["unk"]["weights"] is None) == (arrays["unk_rand"]["weights"] is None)
     d2h_bytes = 4 * len(opi) * plan.n_bins * n_sub * 16
 
     # multi-GPU: every rank counts into device buffers, ONE NCCL sum-reduce of the (4, n_pairs, n_bins, n_sub)
@@ -532,7 +534,18 @@ def run_gpu_arm(args):
         def pick(tag, ci, cf):
             return cf if weighted_tag[tag] else ci
 
-        if fuse:
+        if fuse and fuse4:
+            # all four counts in ONE launch (yawb_count4): (ref, ref_rand) x (unk, unk_rand) -> DD, RD, DR, RR
+            tags4 = ("DD", "RD", "DR", "RR")
+            if on_device:
+                ptrs = tuple(red["buf"][tg][k].data_ptr() if (k == 0) == weighted_tag[tg] else 0 for tg in tags4 for k in (0, 1))
+                _, st = eng.count4(dev["ref"], dev["ref_rand"], dev["unk"], dev["unk_rand"], opi, opj, plan.r2, out_device=ptrs)
+            else:
+                out4, st = eng.count4(dev["ref"], dev["ref_rand"], dev["unk"], dev["unk_rand"], opi, opj, plan.r2)
+                for tg, (ci, cf) in zip(tags4, out4):
+                    results[tg] = pick(tg, ci, cf)
+            stats["DD+RD+DR+RR"] = st
+        elif fuse:
             for (ta, tb), k2 in ((("DD", "RD"), "unk"), (("DR", "RR"), "unk_rand")):
                 if on_device:
                     # only the array the reduce takes: sums of weighted catalogs, counts otherwise
@@ -714,7 +727,7 @@ def run_gpu_arm(args):
                          f"the ONE job split over {world} GPUs: second-catalog patches dealt as compact equal-cost groups (the patch a cut falls into is shared by two ranks), each rank "
                          f"holds only the rows of its patches and the rows of the linked first-catalog patches within reach of them; ONE NCCL sum-reduce "
                          f"of the (4, n_pairs, n_bins, n_sub) count tensor to rank 0 inside the timed region"),
-            fused_counts=bool(fuse),
+            fused_counts=("one launch (yawb_count4)" if fuse and fuse4 else "two launches (yawb_count2)" if fuse else False),
         ),
         breakdown_ms=dict(index_build=float(np.mean(index_ms)), count_kernels=float(np.mean(kernel_ms)),
                           per_launch={tag: s["kernel_ms"] for tag, s in stats_last.items()},
@@ -770,6 +783,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="count DD, RD, DR, RR in four passes instead of two fused ones")
+    ap.add_argument("--no-fuse4", action="store_true", help="two fused launches (DD+RD, DR+RR: yawb_count2) instead of one (yawb_count4)")
     ap.add_argument("--full-reference", action="store_true", help="--impl reference: also time the full job once")
     ap.add_argument("--e2e-groups", type=int, default=1,
                     help="patch slices per unbinned catalog in the end-to-end schedule (1 = whole catalogs)")

@@ -176,6 +176,20 @@ int yawb_count2(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2,
                 const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
                 double *out_f64_a, int64_t *out_i64_a, double *out_f64_b, int64_t *out_i64_b, yawb_stats *stats);
 
+/* The four counts of a cross-correlation in ONE launch: two first catalogs (fused index, as in yawb_count2)
+ * against TWO second catalogs.  Results identical to
+ *     yawb_count(ctx, cat1a, cat2a) -> out[0]    yawb_count(ctx, cat1b, cat2a) -> out[1]
+ *     yawb_count(ctx, cat1a, cat2b) -> out[2]    yawb_count(ctx, cat1b, cat2b) -> out[3]
+ * i.e. DD, RD, DR, RR of src/yaw/correlation/measurements.py:623-626 for (cat1a, cat1b, cat2a, cat2b) =
+ * (reference, its randoms, unknown, its randoms).  The planner lists the work items of both second catalogs for
+ * one persistent kernel, so a small job (a GPU's share of a multi-GPU run) pays the ramp-up and the tail of a
+ * launch, the host synchronisation and the result transfer once instead of twice.  cat2a and cat2b need the same
+ * n_patch / n_bins.  out_f64 / out_i64: tables of four pointers each, any of which may be NULL.
+ * YAWB_FLAG_EXACT_BRUTEFORCE is not supported.  stats cover all four counts. */
+int yawb_count4(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2a, yawb_cat *cat2b, const int32_t *pair_i,
+                const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
+                double *const out_f64[4], int64_t *const out_i64[4], yawb_stats *stats);
+
 /* Pinned host memory helpers so callers can stage inputs for async copies. */
 int yawb_host_alloc(void **ptr, uint64_t bytes);
 int yawb_host_free(void *ptr);

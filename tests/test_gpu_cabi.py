@@ -283,6 +283,47 @@ def test_fused_count_equals_two_counts(engine):
             d.free()
 
 
+def test_four_counts_in_one_launch_equal_four_counts(engine):
+    """`yawb_count4` (two first catalogs x two second catalogs in one launch) must return exactly what four
+    `yawb_count` calls return: second catalogs of different sizes, weights on one of them only, dropped z-bins,
+    several edge counts (single bin, cumulative and general sub-bin kernels), results kept on the host"""
+    rng = np.random.default_rng(17)
+    n_patch, n_bins = 5, 3
+
+    def cat(n, binned, weighted):
+        ra = rng.uniform(0.0, 0.05, n); dec = np.arcsin(rng.uniform(-0.02, 0.02, n))
+        patch = np.minimum((ra / 0.05 * n_patch).astype(int), n_patch - 1)
+        order = np.argsort(patch, kind="stable")
+        xyz = oracle.radec_to_xyz(ra, dec)[order]
+        off = np.concatenate([[0], np.cumsum(np.bincount(patch, minlength=n_patch))])
+        zbin = rng.integers(-1, n_bins + 1, len(ra)).astype(np.int32) if binned else None
+        w = rng.uniform(0.5, 1.5, len(ra)) if weighted else None
+        return xyz, off, w, zbin
+
+    pi, pj = np.meshgrid(np.arange(n_patch), np.arange(n_patch), indexing="ij")
+    pi, pj = pi.ravel(), pj.ravel()
+    for w1, w2a, w2b, n_edges in ((False, False, False, 2), (False, False, False, 5), (False, True, False, 2), (True, False, True, 12)):
+        r2 = np.sort(rng.uniform(1e-8, 4e-6, (n_bins, n_edges)), axis=1)
+        xa, oa, wwa, za = cat(2500, True, w1)
+        xb, ob, wwb, zb = cat(30000, True, w1)
+        x2a, o2a, ww2a, _ = cat(20000, False, w2a)
+        x2b, o2b, ww2b, _ = cat(45000, False, w2b)
+        da = engine.upload_catalog(xa, oa, weights=wwa, zbin=za, n_bins=n_bins)
+        db = engine.upload_catalog(xb, ob, weights=wwb, zbin=zb, n_bins=n_bins)
+        d2a = engine.upload_catalog(x2a, o2a, weights=ww2a)
+        d2b = engine.upload_catalog(x2b, o2b, weights=ww2b)
+        out4, st = engine.count4(da, db, d2a, d2b, pi, pj, r2)
+        total = 0
+        for (ci, cf), (c1, c2) in zip(out4, ((da, d2a), (db, d2a), (da, d2b), (db, d2b))):
+            si, sf, _ = engine.count(c1, c2, pi, pj, r2)
+            assert_array_equal(ci, si)
+            assert_allclose(cf, sf, rtol=RTOL_WEIGHTED, atol=0)
+            total += int(si.sum())
+        assert total > 1000 and st["pair_tests"] > 0
+        for d in (da, db, d2a, d2b):
+            d.free()
+
+
 @pytest.mark.parametrize("variant", ["sat", "pred"])
 def test_pair_test_variants_exact(engine, variant, monkeypatch):
     """both FP32 pair-test formulations (7-instruction saturating ramp / 8-instruction predicated) must

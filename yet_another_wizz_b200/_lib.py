@@ -27,7 +27,7 @@ EXPORTS = (
     "yawb_build_index", "yawb_drop_index", "yawb_catalog_info", "yawb_sum_weights", "yawb_count",
     "yawb_host_alloc", "yawb_host_free", "yawb_sync", "yawb_version", "yawb_device_sms",
     "yawb_timer_start", "yawb_timer_stop", "yawb_assign_patches", "yawb_upload_catalog_u8", "yawb_count2",
-    "yawb_upload_catalog_z", "yawb_patch_metadata", "yawb_jackknife",
+    "yawb_upload_catalog_z", "yawb_patch_metadata", "yawb_jackknife", "yawb_count4",
 )
 
 
@@ -102,6 +102,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.yawb_count2.argtypes = [
         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_uint32,
         c_void_p, c_void_p, c_void_p, c_void_p, POINTER(YawbStats),
+    ]
+    lib.yawb_count4.argtypes = [
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_uint32,
+        POINTER(c_void_p), POINTER(c_void_p), POINTER(YawbStats),
     ]
     for name in EXPORTS:
         if name not in ("yawb_last_error",):

@@ -416,9 +416,9 @@ int yawb_patch_metadata(const yawb_cat *cat, double *center_xyz, double *radius_
 
 // Shared body of yawb_count (one first catalog) and yawb_count2 (two first catalogs counted against the same
 // second catalog in one pass over a fused first-role index).
-static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *cat2, const int32_t *pair_i,
+static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *cat2, yawb_cat *cat2b, const int32_t *pair_i,
                       const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
-                      double *const out_f64[2], int64_t *const out_i64[2], yawb_stats *stats) {
+                      double *const out_f64[4], int64_t *const out_i64[4], yawb_stats *stats) {
     YAWB_REQUIRE(ctx && cat1 && cat2, "yawb_count: NULL context or catalog");
     YAWB_REQUIRE(cat1->ctx == ctx && cat2->ctx == ctx && (!cat1b || cat1b->ctx == ctx), "catalogs belong to a different context");
     YAWB_REQUIRE(n_pairs >= 0, "n_pairs < 0");
@@ -435,8 +435,15 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
                      "yawb_count2: the two first catalogs need the same patches and z-bins");
         YAWB_REQUIRE(!(flags & YAWB_FLAG_EXACT_BRUTEFORCE), "yawb_count2: the exact cross-check counts one catalog at a time");
     }
+    if (cat2b) {
+        YAWB_REQUIRE(cat1b != nullptr, "yawb_count4 needs two first-role catalogs");
+        YAWB_REQUIRE(cat2b != cat2 && cat2b->ctx == ctx, "yawb_count4: the two second catalogs must differ and belong to the context");
+        YAWB_REQUIRE(cat2b->n_patch == cat2->n_patch && cat2b->n_bins == cat2->n_bins && cat2b->binned == cat2->binned,
+                     "yawb_count4: the two second catalogs need the same patches and z-bins");
+    }
     YAWB_REQUIRE(n_pairs == 0 || (pair_i && pair_j), "pair lists are NULL");
     const int n_types = cat1b ? 2 : 1;
+    const int n_src = cat2b ? 2 : 1;  // second catalogs of the launch
     const int B = cat1->n_bins, P = cat1->n_patch, nsub = n_edges - 1;
     for (int k = 0; k < n_pairs; ++k)
         YAWB_REQUIRE(pair_i[k] >= 0 && pair_i[k] < P && pair_j[k] >= 0 && pair_j[k] < P,
@@ -470,16 +477,18 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         if (first_built) YAWB_CUDA(cudaEventRecord(ctx->ev_f1, st));  // read after the final synchronisation
     }
     if (yawb_cat_finalize(cat2)) return 1;
-    const bool second_built = !cat2->has_rtiles;
+    if (cat2b && yawb_cat_finalize(cat2b)) return 1;
+    const bool second_built = !cat2->has_rtiles || (cat2b && !cat2b->has_rtiles);
     if (second_built) {
         YAWB_CUDA(cudaEventRecord(ctx->ev_i0, st));
         if (yawb_index_build_second(cat2)) return 1;
+        if (cat2b && yawb_index_build_second(cat2b)) return 1;
         YAWB_CUDA(cudaEventRecord(ctx->ev_i1, st));
     }
 
-    const bool weighted = fi->weighted || cat2->weighted;
-    const size_t n_out1 = (size_t)n_pairs * B * nsub;  // one catalog's results
-    const size_t n_out = n_out1 * n_types;
+    const bool weighted = fi->weighted || cat2->weighted || (cat2b && cat2b->weighted);
+    const size_t n_out1 = (size_t)n_pairs * B * nsub;  // one (first, second) catalog combination's results
+    const size_t n_out = n_out1 * n_types * n_src;     // [second catalog][first catalog][pair][bin][sub-bin]
 
     // host-side preparation of thresholds and the item table
     std::vector<BinPar> binpar(B);
@@ -528,22 +537,28 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     double rmax_all = 0.0;
     for (int b = 0; b < B; ++b)
         if (!binpar[b].empty) rmax_all = std::max(rmax_all, binpar[b].rmax);
-    std::vector<long long> item_base(n_pairs + 1, 0);
-    long long flat_diag = 0;
-    for (int k = 0; k < n_pairs; ++k) {
-        const int q = pair_j[k];
-        const long long nt = cat2->h_ptile_off[q + 1] - cat2->h_ptile_off[q];
-        item_base[k + 1] = item_base[k] + nt;
-        const int p = pair_i[k];
-        if (p == q) flat_diag += nt;
-        for (int b = 0; b < B; ++b) {
-            long long n1 = cat1->h_counts[(size_t)b * P + p];
-            if (cat1b) n1 += cat1b->h_counts[(size_t)b * P + p];
-            long long n2 = 0;
-            if (cat2->binned) n2 = cat2->h_counts[(size_t)b * P + q];
-            else n2 = cat2->h_counts[q];
-            s.pair_tests_naive += (uint64_t)(n1 * n2);
+    // per second catalog: prefix of tiles per pair ((patch pair, tile) combinations = threads of the planner)
+    std::vector<long long> item_base((size_t)n_src * (n_pairs + 1), 0);
+    long long flat_diag = 0, n_items_all = 0;
+    for (int sc = 0; sc < n_src; ++sc) {
+        const yawb_cat *c2 = sc ? cat2b : cat2;
+        long long *base = item_base.data() + (size_t)sc * (n_pairs + 1);
+        for (int k = 0; k < n_pairs; ++k) {
+            const int q = pair_j[k];
+            const long long nt = c2->h_ptile_off[q + 1] - c2->h_ptile_off[q];
+            base[k + 1] = base[k] + nt;
+            const int p = pair_i[k];
+            if (p == q) flat_diag += nt;
+            for (int b = 0; b < B; ++b) {
+                long long n1 = cat1->h_counts[(size_t)b * P + p];
+                if (cat1b) n1 += cat1b->h_counts[(size_t)b * P + p];
+                long long n2 = 0;
+                if (c2->binned) n2 = c2->h_counts[(size_t)b * P + q];
+                else n2 = c2->h_counts[q];
+                s.pair_tests_naive += (uint64_t)(n1 * n2);
+            }
         }
+        n_items_all += base[n_pairs];
     }
 
     // the six small tables of a count travel as ONE block (one allocation, one pull kernel): pair lists,
@@ -551,7 +566,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     const size_t np1 = std::max(n_pairs, 1);
     auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const size_t o_pi = 0, o_pj = o_pi + up16(np1 * sizeof(int)), o_base = o_pj + up16(np1 * sizeof(int)),
-                 o_r2 = o_base + up16((np1 + 1) * sizeof(long long)),
+                 o_r2 = o_base + up16((size_t)n_src * (np1 + 1) * sizeof(long long)),
                  o_r2f = o_r2 + up16((size_t)B * n_edges * sizeof(double)), o_bp = o_r2f + up16(r2f_words * sizeof(float)),
                  tab_bytes = o_bp + up16(B * sizeof(BinPar));
     std::vector<unsigned char> tab(tab_bytes, 0);
@@ -559,7 +574,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         memcpy(tab.data() + o_pi, pair_i, n_pairs * sizeof(int));
         memcpy(tab.data() + o_pj, pair_j, n_pairs * sizeof(int));
     }
-    memcpy(tab.data() + o_base, item_base.data(), (n_pairs + 1) * sizeof(long long));
+    memcpy(tab.data() + o_base, item_base.data(), (size_t)n_src * (n_pairs + 1) * sizeof(long long));
     memcpy(tab.data() + o_r2, r2_edges, (size_t)B * n_edges * sizeof(double));
     memcpy(tab.data() + o_r2f, r2f.data(), r2f_words * sizeof(float));
     memcpy(tab.data() + o_bp, binpar.data(), B * sizeof(BinPar));
@@ -601,14 +616,16 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     BinPar *d_bp = (BinPar *)(d_tab + o_bp);
 
     CountArgs a{};
-    a.c1 = fi; a.c1_cat = cat1; a.c2 = cat2;
+    a.c1 = fi; a.c1_cat = cat1; a.c2 = cat2; a.c2b = cat2b;
     a.d_pair_i = d_pi; a.d_pair_j = d_pj; a.d_pair_item_base = d_base;
+    a.d_pair_item_base_b = cat2b ? d_base + (n_pairs + 1) : nullptr;
     a.n_items = item_base[n_pairs];
+    a.n_items_b = cat2b ? item_base[(size_t)(n_pairs + 1) + n_pairs] : 0;
     // work-item lists: a patch with itself needs an item per tile (a few more where items are split), of the
     // tiles of neighbouring patches only the boundary strip survives; if a list turns out too small the
     // count is repeated with the exact sizes
     a.cap_heavy = 4 * flat_diag + 1024;
-    a.cap_light = 2 * (a.n_items - flat_diag) + 1024;
+    a.cap_light = 2 * (n_items_all - flat_diag) + 1024;
     a.n_pairs = n_pairs; a.n_bins = B; a.n_edges = n_edges;
     a.d_r2 = d_r2; a.d_r2f = d_r2f; a.d_binpar = d_bp; a.rmax_all = rmax_all;
     a.d_out_cnt = d_cnt; a.d_out_w = d_w; a.weighted = weighted;
@@ -646,7 +663,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         // been too small -- the host only learns that now -- the count is repeated with the exact sizes
         if (to_device) {
             TRY(cudaMemcpyAsync(h_counters, ctx->d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
-            for (int t = 0; t < n_types && n_out1; ++t) {
+            for (int t = 0; t < n_types * n_src && n_out1; ++t) {
                 if (out_i64[t]) TRY(cudaMemcpyAsync(out_i64[t], d_cnt + t * n_out1, n_out1 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
                 if (out_f64[t]) {
                     if (weighted) {
@@ -677,7 +694,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     if (!to_device) {
         const unsigned long long *h_cnt = reinterpret_cast<const unsigned long long *>(pin + pin_cnt);
         const double *h_w = reinterpret_cast<const double *>(pin + pin_w);
-        for (int t = 0; t < n_types && n_out1; ++t) {
+        for (int t = 0; t < n_types * n_src && n_out1; ++t) {
             if (out_i64[t]) memcpy(out_i64[t], h_cnt + t * n_out1, n_out1 * sizeof(int64_t));
             if (out_f64[t]) {
                 if (weighted) {
@@ -717,18 +734,26 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
 int yawb_count(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat2, const int32_t *pair_i, const int32_t *pair_j,
                int n_pairs, const double *r2_edges, int n_edges, uint32_t flags, double *out_f64,
                int64_t *out_i64, yawb_stats *stats) {
-    double *const of[2] = {out_f64, nullptr};
-    int64_t *const oi[2] = {out_i64, nullptr};
-    return count_impl(ctx, cat1, nullptr, cat2, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
+    double *const of[4] = {out_f64, nullptr, nullptr, nullptr};
+    int64_t *const oi[4] = {out_i64, nullptr, nullptr, nullptr};
+    return count_impl(ctx, cat1, nullptr, cat2, nullptr, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
 }
 
 int yawb_count2(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2, const int32_t *pair_i,
                 const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
                 double *out_f64_a, int64_t *out_i64_a, double *out_f64_b, int64_t *out_i64_b, yawb_stats *stats) {
     YAWB_REQUIRE(cat1b != nullptr, "yawb_count2: the second first-role catalog is NULL");
-    double *const of[2] = {out_f64_a, out_f64_b};
-    int64_t *const oi[2] = {out_i64_a, out_i64_b};
-    return count_impl(ctx, cat1a, cat1b, cat2, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
+    double *const of[4] = {out_f64_a, out_f64_b, nullptr, nullptr};
+    int64_t *const oi[4] = {out_i64_a, out_i64_b, nullptr, nullptr};
+    return count_impl(ctx, cat1a, cat1b, cat2, nullptr, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, of, oi, stats);
+}
+
+int yawb_count4(yawb_ctx *ctx, yawb_cat *cat1a, yawb_cat *cat1b, yawb_cat *cat2a, yawb_cat *cat2b, const int32_t *pair_i,
+                const int32_t *pair_j, int n_pairs, const double *r2_edges, int n_edges, uint32_t flags,
+                double *const out_f64[4], int64_t *const out_i64[4], yawb_stats *stats) {
+    YAWB_REQUIRE(cat1b != nullptr && cat2b != nullptr, "yawb_count4: a catalog is NULL");
+    YAWB_REQUIRE(out_f64 != nullptr && out_i64 != nullptr, "yawb_count4: the output pointer tables are NULL (their entries may be)");
+    return count_impl(ctx, cat1a, cat1b, cat2a, cat2b, pair_i, pair_j, n_pairs, r2_edges, n_edges, flags, out_f64, out_i64, stats);
 }
 
 }  // extern "C"

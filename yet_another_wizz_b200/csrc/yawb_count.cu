@@ -77,7 +77,7 @@ struct FastParams {
     int acc_global;               // general sub-bin path: segment histograms go straight to global atomics
     const BinPar *binpar;
     double rmax_all;              // largest search radius over the z-bins
-    unsigned long long *out_cnt;  // [n_types][n_pairs][n_bins][n_edges - 1]
+    unsigned long long *out_cnt;  // [n_src][n_types][n_pairs][n_bins][n_edges - 1] (n_src = second catalogs of the launch)
     double *out_w;
     size_t type_stride;           // n_pairs * n_bins * (n_edges - 1)
     unsigned long long *counters;  // [0] next item, [1] tests, [2] rechecks, [4] heavy items, [5] light items, [6] overflow
@@ -117,6 +117,11 @@ __device__ __forceinline__ BinRows bin_rows(const SGrid &G, double ulo, double u
         const size_t cand_o_ = 3 * (size_t)cand_i_; /* interleaved rows */     \
         X = cand_x_[cand_o_]; Y = cand_y_[cand_o_]; Z = cand_z_[cand_o_];      \
     } while (0)
+
+// Rows (and weights) of the second catalog a tile was cut from: `tl.patch` carries Item::src inside the streaming
+// kernel (0 = first, 1 = second catalog of a joint launch).
+#define YAWB_TILE_ROWS(P, tl) ((tl).patch ? (P).rx2 : (P).rx)
+#define YAWB_TILE_WEIGHTS(P, tl) ((tl).patch ? (P).rw2 : (P).rw)
 
 // The reference's comparison value: products rounded separately, summed x -> y -> z.
 __device__ __forceinline__ double exact_d2(double ax, double ay, double az, double bx, double by, double bz) {
@@ -187,6 +192,9 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
                                               unsigned &cnt_out, double &w_out, unsigned &n_recheck) {
     unsigned cnt = 0;
     double wsum = 0.0;
+    const double *const trow = YAWB_TILE_ROWS(P, tl);
+    const double *const tw = YAWB_TILE_WEIGHTS(P, tl);
+    (void)tw;
     for (int t = lane; t < CHUNK * YAWB_RPL; t += 32) {
         const int e = e0 + (t & (CHUNK - 1));
         const int k = src + 32 * (t / CHUNK);
@@ -194,10 +202,10 @@ __device__ __forceinline__ void recheck_chunk(const FastParams &P, const WarpSme
             const int i = S.lidx[e], j = tl.start + k;
             double cxx, cyy, czz;
             YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-            const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
+            const double d2 = exact_d2(cxx, cyy, czz, trow[(size_t)YAWB_RSTRIDE * j], trow[(size_t)YAWB_RSTRIDE * j + 1], trow[(size_t)YAWB_RSTRIDE * j + 2]);
             if (d2 > lo && d2 <= hi) {
                 cnt += 1;
-                if (WEIGHTED) wsum += S.lw[e] * (P.rw ? P.rw[j] : 1.0);
+                if (WEIGHTED) wsum += S.lw[e] * (tw ? tw[j] : 1.0);
             }
             n_recheck += 1;
         }
@@ -220,7 +228,10 @@ __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem
     const int k = src + 32 * (lane & 7);
     const bool row_ok = k < tl.count;
     const int j = tl.start + (row_ok ? k : 0);
-    const double bx = P.rx[(size_t)YAWB_RSTRIDE * j], by = P.ry[(size_t)YAWB_RSTRIDE * j], bz = P.rz[(size_t)YAWB_RSTRIDE * j];
+    const double *const trow = YAWB_TILE_ROWS(P, tl);
+    const double *const tw = YAWB_TILE_WEIGHTS(P, tl);
+    (void)tw;
+    const double bx = trow[(size_t)YAWB_RSTRIDE * j], by = trow[(size_t)YAWB_RSTRIDE * j + 1], bz = trow[(size_t)YAWB_RSTRIDE * j + 2];
     double ax[Q], ay[Q], az[Q];
     bool ok[Q];
 #pragma unroll
@@ -236,7 +247,7 @@ __device__ __forceinline__ void recheck_span(const FastParams &P, const WarpSmem
         if (ok[q]) {
             if (d2 > lo && d2 <= hi) {
                 cnt += 1;
-                if (WEIGHTED) wsum += S.lw[e0 + (lane >> 3) + 4 * q] * (P.rw ? P.rw[j] : 1.0);
+                if (WEIGHTED) wsum += S.lw[e0 + (lane >> 3) + 4 * q] * (tw ? tw[j] : 1.0);
             }
             n_recheck += 1;
         }
@@ -357,6 +368,7 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
     unsigned cnt[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) cnt[g] = 0;
+    const double *const trow = YAWB_TILE_ROWS(P, tl);
     for (int t = lane; t < CUM_CHUNK * YAWB_RPL; t += 32) {
         const int e = e0 + (t & (CUM_CHUNK - 1));
         const int k = src + 32 * (t / CUM_CHUNK);
@@ -364,7 +376,7 @@ __device__ __forceinline__ void recheck_cumul(const FastParams &P, const int *li
             const int i = lidx[e], j = tl.start + k;
             double cxx, cyy, czz;
             YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-            const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
+            const double d2 = exact_d2(cxx, cyy, czz, trow[(size_t)YAWB_RSTRIDE * j], trow[(size_t)YAWB_RSTRIDE * j + 1], trow[(size_t)YAWB_RSTRIDE * j + 2]);
 #pragma unroll
             for (int g = 0; g < G; ++g)
                 if (k0 + g < ne && d2 <= ed[k0 + g]) cnt[g] += 1;
@@ -471,6 +483,9 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
     const int nc = P.lg_cells;
     const float lg_scale = P.lgpar[2 * b], lg_off = P.lgpar[2 * b + 1];
     const unsigned short *lgT = P.lgT + (size_t)b * nc;
+    const double *const trow = YAWB_TILE_ROWS(P, tl);
+    const double *const tw = YAWB_TILE_WEIGHTS(P, tl);
+    (void)tw;
     for (int e = ea; e < eb; ++e) {
         const Cand c = S.list[e];
         const float2 sx = make_float2(c.x, c.x), sy = make_float2(c.y, c.y);
@@ -498,13 +513,13 @@ __device__ __forceinline__ void phase2_multi(const FastParams &P, const WarpSmem
                     const int i = S.lidx[e];
                     double cxx, cyy, czz;
                     YAWB_CAND_ROW(P, i, cxx, cyy, czz);
-                    const double d2 = exact_d2(cxx, cyy, czz, P.rx[(size_t)YAWB_RSTRIDE * j], P.ry[(size_t)YAWB_RSTRIDE * j], P.rz[(size_t)YAWB_RSTRIDE * j]);
+                    const double d2 = exact_d2(cxx, cyy, czz, trow[(size_t)YAWB_RSTRIDE * j], trow[(size_t)YAWB_RSTRIDE * j + 1], trow[(size_t)YAWB_RSTRIDE * j + 2]);
                     k = edges_below(ed, ne, d2);
                     n_recheck += 1;
                 }
                 if (k >= 1 && k < ne) {
                     atomicAdd(&S.hist[k - 1], 1u);
-                    if (WEIGHTED) atomicAdd(&S.histw[k - 1], S.lw[e] * (P.rw ? P.rw[j] : 1.0));
+                    if (WEIGHTED) atomicAdd(&S.histw[k - 1], S.lw[e] * (tw ? tw[j] : 1.0));
                 }
             }
         }
@@ -537,6 +552,7 @@ struct PlanParams {
     Item *heavy, *light;
     long long cap_heavy, cap_light;
     int ccap;  // (z-bin, cell row) runs per item: YAWB_CCAP, or less to cut a small job into more, shorter items
+    int src;   // which second catalog of a joint launch these tiles belong to (Item::src)
     unsigned long long *counters;
 };
 
@@ -611,7 +627,7 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
             }
             if (lo3[0] - rmax <= F1.umax && hi3[0] + rmax >= F1.umin && lo3[1] - rmax <= F1.vmax && hi3[1] + rmax >= F1.vmin) {
                 G = Q.sgrid[p1];
-                it.pair = k; it.p1 = p1; it.start = tl.start; it.count = tl.count; it.src = 0;
+                it.pair = k; it.p1 = p1; it.start = tl.start; it.count = tl.count; it.src = Q.src;
                 it.b_lo = tl.bin >= 0 ? tl.bin : 0;
                 it.b_hi = tl.bin >= 0 ? tl.bin + 1 : Q.n_bins;
 #pragma unroll
@@ -753,12 +769,15 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.cell_start = fi->cell_start; P.sgrid = fi->d_sgrid; P.sframe = fi->d_frames; P.n_types = fi->n_types;
     P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
     P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
+    if (a.c2b) { P.rx2 = a.c2b->rx; P.ry2 = a.c2b->ry; P.rz2 = a.c2b->rz; P.rw2 = a.c2b->rw; }
     {
         // the pair test takes |r|^2 of a tile row from the identity for unit vectors (yawb_count_stream.cuh); rows
         // off the unit sphere by zeta widen the band of tests that are re-evaluated in FP64 (1e-15: the frames'
         // own deviation from orthonormality)
         double zeta = 0.0;
         for (const PatchFrame &f : a.c2->h_frames) zeta = std::max(zeta, f.norm_dev);
+        if (a.c2b)
+            for (const PatchFrame &f : a.c2b->h_frames) zeta = std::max(zeta, f.norm_dev);
         P.zeta = (float)(zeta + 1.0e-15) * 1.000001f;
     }
     P.n_pairs = a.n_pairs; P.n_bins = a.n_bins; P.n_edges = a.n_edges;
@@ -768,7 +787,8 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.lgT = reinterpret_cast<const unsigned short *>(P.lgpar + 2 * (size_t)a.n_bins);
     P.out_cnt = a.d_out_cnt; P.out_w = a.d_out_w; P.counters = ctx->d_counters;
     P.type_stride = (size_t)a.n_pairs * a.n_bins * (a.n_edges - 1);
-    if (a.n_items == 0) return 0;
+    const long long n_items_all = a.n_items + a.n_items_b;
+    if (n_items_all == 0) return 0;
 
     // planner: self-contained work items (patch-diagonal ones first)
     // a small job (a rank's share of a strong-scaling run) is cut into more, shorter items, so that the warps of
@@ -776,7 +796,7 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     // items hold at most YAWB_CCAP_SMALL runs (swept on an eighth of C3: 16 / 24 / 32 / 48 / 72 / 112 runs ->
     // count kernels 1.02 / 1.01 / 1.05 / 1.10 / 1.18 / 1.17 ms); the lists grow by the same factor
     const long long warps = (long long)ctx->sms * STREAM_CTAS * STREAM_WARPS;
-    int ccap = a.n_items < YAWB_SMALL_JOB_ITEMS * warps ? YAWB_CCAP_SMALL : YAWB_CCAP;
+    int ccap = n_items_all < YAWB_SMALL_JOB_ITEMS * warps ? YAWB_CCAP_SMALL : YAWB_CCAP;
     if (const char *e = getenv("YAWB_CCAP_RUNTIME")) ccap = std::max(8, std::min(YAWB_CCAP, atoi(e)));
     const long long cap_scale = (YAWB_CCAP + ccap - 1) / ccap;
     const long long cap_heavy = a.cap_heavy * cap_scale, cap_light = a.cap_light * cap_scale;
@@ -785,16 +805,20 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.items_heavy = d_items;
     P.items_light = d_items + cap_heavy;
     P.cap_heavy = cap_heavy; P.cap_light = cap_light;
-    {
+    for (int sc = 0; sc < 2; ++sc) {  // one planner launch per second catalog, both append to the same two lists
+        const yawb_cat *c2 = sc ? a.c2b : a.c2;
+        const long long n_flat = sc ? a.n_items_b : a.n_items;
+        if (!c2 || n_flat == 0) continue;
         PlanParams Q{};
-        Q.tiles = a.c2->d_tiles; Q.tile_box = a.c2->d_tile_box; Q.ptile_off = a.c2->d_ptile_off;
-        Q.frames2 = a.c2->d_frames; Q.frames1 = fi->d_frames; Q.sgrid = fi->d_sgrid;
-        Q.pair_i = a.d_pair_i; Q.pair_j = a.d_pair_j; Q.pair_item_base = a.d_pair_item_base;
-        Q.n_pairs = a.n_pairs; Q.n_flat = a.n_items; Q.binpar = a.d_binpar; Q.n_bins = a.n_bins; Q.rmax_all = a.rmax_all;
+        Q.tiles = c2->d_tiles; Q.tile_box = c2->d_tile_box; Q.ptile_off = c2->d_ptile_off;
+        Q.frames2 = c2->d_frames; Q.frames1 = fi->d_frames; Q.sgrid = fi->d_sgrid;
+        Q.pair_i = a.d_pair_i; Q.pair_j = a.d_pair_j; Q.pair_item_base = sc ? a.d_pair_item_base_b : a.d_pair_item_base;
+        Q.n_pairs = a.n_pairs; Q.n_flat = n_flat; Q.binpar = a.d_binpar; Q.n_bins = a.n_bins; Q.rmax_all = a.rmax_all;
         Q.heavy = d_items; Q.light = d_items + cap_heavy; Q.cap_heavy = cap_heavy; Q.cap_light = cap_light;
         Q.counters = ctx->d_counters;
         Q.ccap = ccap;
-        k_plan<<<(unsigned)((a.n_items + 255) / 256), 256, 0, ctx->stream>>>(Q);
+        Q.src = sc;
+        k_plan<<<(unsigned)((n_flat + 255) / 256), 256, 0, ctx->stream>>>(Q);
         *launches += 1;
     }
 

@@ -496,7 +496,7 @@ template <bool WEIGHTED, bool MULTI, bool SAT>
 __device__ __forceinline__ void stream_test_generic(const FastParams &P, const StreamSmem<WEIGHTED> &S, int n_seg,
                                                     const float2 (&rx)[HPL], const float2 (&ry)[HPL],
                                                     const float2 (&rz)[HPL], const Tile &tl,
-                                                    int lane, int nsub, unsigned &n_recheck, int cur_pair,
+                                                    int lane, int nsub, unsigned &n_recheck, int cur_pair, size_t src_off,
                                                     const double (&rwt)[YAWB_RPL]) {
     const size_t nacc1 = (size_t)P.n_bins * nsub;  // accumulators of one type
     for (int sg = 0; sg < n_seg; ++sg) {
@@ -519,7 +519,7 @@ __device__ __forceinline__ void stream_test_generic(const FastParams &P, const S
             phase2_multi<WEIGHTED>(P, W, ea, eb, rx, ry, rz, thr.x, thr.y, S.binrec[b].w, tl, lane, b, n_recheck);
             __syncwarp();
             if (P.acc_global) {  // straight to the result: one atomic per non-empty sub-bin of the segment
-                const size_t o = (size_t)d.type * P.type_stride + ((size_t)cur_pair * P.n_bins + b) * nsub;
+                const size_t o = src_off + (size_t)d.type * P.type_stride + ((size_t)cur_pair * P.n_bins + b) * nsub;
                 for (int k = lane; k < nsub; k += 32) {
                     if (W.hist[k]) atomicAdd(&P.out_cnt[o + k], (unsigned long long)W.hist[k]);
                     if (WEIGHTED && W.histw[k] != 0.0) atomicAdd(&P.out_w[o + k], W.histw[k]);
@@ -606,13 +606,15 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
         const bool c_first = raw_first, c_last = raw_last;
         int n_seg = 0;
         int cur_pair = 0;
+        size_t src_off = 0;  // results of the second catalog of a joint launch follow those of the first
         if (c_cnt >= 0) {
             const Item &it = S.items[c_slot];
             cur_pair = it.pair;
+            src_off = (size_t)it.src * P.n_types * P.type_stride;
             double dx[YAWB_RPL], dy[YAWB_RPL], dz[YAWB_RPL];
             if (c_first) {
                 // rows of the tile: loads issued now, used after the conversion of the raw chunk
-                tl.start = it.start; tl.count = it.count; tl.patch = 0; tl.bin = 0;
+                tl.start = it.start; tl.count = it.count; tl.patch = it.src; tl.bin = 0;  // patch: the tile's catalog
                 const double *const rxs = it.src ? P.rx2 : P.rx, *const rws = it.src ? P.rw2 : P.rw;
 #pragma unroll
                 for (int r = 0; r < YAWB_RPL; ++r) {
@@ -703,14 +705,14 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32, STREAM_CTAS) k_count_stream
                 if constexpr (!WEIGHTED && !MULTI && SAT)
                     stream_test_sat(P, S, n_seg, rx, ry, rz, tl, lane, n_recheck);
                 else
-                    stream_test_generic<WEIGHTED, MULTI, SAT>(P, S, n_seg, rx, ry, rz, tl, lane, nsub, n_recheck, cur_pair, rwt);
+                    stream_test_generic<WEIGHTED, MULTI, SAT>(P, S, n_seg, rx, ry, rz, tl, lane, nsub, n_recheck, cur_pair, src_off, rwt);
             }
             if (c_last) {  // the item is complete: its counts go to the result of its patch pair
                 __syncwarp();
                 const size_t nacc1 = (size_t)P.n_bins * nsub;
                 for (int k = lane; k < nacc; k += 32) {
                     const int type = k >= (int)nacc1 ? 1 : 0;
-                    const size_t o = (size_t)type * P.type_stride + (size_t)cur_pair * nacc1 + (k - type * nacc1);
+                    const size_t o = src_off + (size_t)type * P.type_stride + (size_t)cur_pair * nacc1 + (k - type * nacc1);
                     const unsigned long long c = S.acc[k];
                     if (c) {
                         atomicAdd(&P.out_cnt[o], c);

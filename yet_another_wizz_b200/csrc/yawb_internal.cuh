@@ -252,10 +252,13 @@ void yawb_index_free(yawb_cat *cat, bool everything);
 struct CountArgs {
     const FIndex *c1;    // first-role index (one catalog, or two fused)
     const yawb_cat *c2;
+    const yawb_cat *c2b = nullptr;       // second second-role catalog of a joint launch (yawb_count4), or nullptr
     const int *d_pair_i;
     const int *d_pair_j;
     const long long *d_pair_item_base;  // [n_pairs + 1] prefix of tiles per pair
     long long n_items;                  // (patch pair, tile) combinations = threads of the planner
+    const long long *d_pair_item_base_b = nullptr;  // the same for c2b
+    long long n_items_b = 0;
     long long cap_heavy, cap_light;     // capacities of the two work-item lists
     int n_pairs;
     int n_bins;

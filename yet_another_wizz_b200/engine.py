@@ -274,6 +274,59 @@ class Engine:
         )
         return out[0], out[1], stats.as_dict()
 
+    def count4(
+        self,
+        cat1a: DeviceCatalog,
+        cat1b: DeviceCatalog,
+        cat2a: DeviceCatalog,
+        cat2b: DeviceCatalog,
+        pair_i: np.ndarray,
+        pair_j: np.ndarray,
+        r2_edges: np.ndarray,
+        *,
+        out_device: tuple | None = None,
+    ):
+        """The four counts of a cross-correlation in ONE launch (`yawb_count4`): `count(cat1a, cat2a)`,
+        `count(cat1b, cat2a)`, `count(cat1a, cat2b)`, `count(cat1b, cat2b)` -- DD, RD, DR, RR for (reference, its
+        randoms, unknown, its randoms), `src/yaw/correlation/measurements.py:623-626`.  Returns
+        `([(counts, sums)] * 4, stats)` in that order.
+
+        `out_device = (sums_0, counts_0, ..., sums_3, counts_3)`: raw device pointers (0 = not wanted); the results
+        stay on the device and the arrays returned are `None`."""
+        pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
+        pair_j = np.ascontiguousarray(pair_j, dtype=np.int32)
+        r2_edges = np.ascontiguousarray(r2_edges, dtype=np.float64)
+        n_bins = cat1a.n_bins
+        if r2_edges.ndim == 1:
+            r2_edges = np.ascontiguousarray(np.broadcast_to(r2_edges, (n_bins, len(r2_edges))))
+        if r2_edges.shape[0] != n_bins:
+            raise ValueError(f"r2_edges must have shape (n_bins={n_bins}, n_edges)")
+        n_edges = r2_edges.shape[1]
+        shape = (len(pair_i), n_bins, n_edges - 1)
+        stats = _lib.YawbStats()
+        tab_f, tab_i = (c_void_p * 4)(), (c_void_p * 4)()
+        out = None
+        if out_device is not None:
+            for t in range(4):
+                tab_f[t] = out_device[2 * t] or None
+                tab_i[t] = out_device[2 * t + 1] or None
+            flags = _lib.FLAG_OUT_DEVICE
+        else:
+            out = [(np.zeros(shape, dtype=np.int64), np.zeros(shape, dtype=np.float64)) for _ in range(4)]
+            for t in range(4):
+                tab_i[t] = out[t][0].ctypes.data
+                tab_f[t] = out[t][1].ctypes.data
+            flags = 0
+        _lib.check(
+            self.lib.yawb_count4(
+                self._h, cat1a._h, cat1b._h, cat2a._h, cat2b._h, _ptr(pair_i), _ptr(pair_j), len(pair_i), _ptr(r2_edges),
+                n_edges, flags, tab_f, tab_i, byref(stats),
+            )
+        )
+        if out is None:
+            return [(None, None)] * 4, stats.as_dict()
+        return out, stats.as_dict()
+
     def count_into_device(self, cat1, cat2, pair_i, pair_j, r2_edges, out_f64_ptr: int, out_i64_ptr: int):
         """Variant writing into caller-owned device buffers (raw pointers)."""
         pair_i = np.ascontiguousarray(pair_i, dtype=np.int32)
