@@ -38,14 +38,14 @@ typedef struct yawb_cat yawb_cat;
 #define YAWB_ROLE_SECOND 2 /* catalog used as second argument: Hilbert-ordered register tiles        */
 
 typedef struct {
-    double kernel_ms;          /* device time of the pair-count kernel(s), CUDA events on the ctx stream */
+    double kernel_ms;          /* device time of planner + pair-count kernel, CUDA events on the ctx stream */
     double index_ms;           /* device time of index builds triggered by this call (0 if prebuilt)      */
     uint64_t pair_tests;       /* pair tests executed (after sky-cell / tile pruning)                     */
     uint64_t pair_tests_naive; /* sum over requested patch pairs and z-bins of n1 * n2                    */
     uint64_t rechecks;         /* tests re-evaluated in exact FP64                                        */
     uint64_t work_items;       /* work items written by the planner (tile x linked patch, non-empty)      */
     uint64_t launches;         /* kernels launched by this call                                           */
-    uint64_t reserved;
+    double plan_ms;            /* part of kernel_ms spent in the planner (k_plan); the rest is the count kernel */
 } yawb_stats;
 
 /* Thread-local description of the last failure. */

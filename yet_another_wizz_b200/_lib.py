@@ -40,11 +40,11 @@ class YawbStats(ctypes.Structure):
         ("rechecks", c_uint64),
         ("work_items", c_uint64),
         ("launches", c_uint64),
-        ("reserved", c_uint64),
+        ("plan_ms", c_double),
     ]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 class YawbError(RuntimeError):

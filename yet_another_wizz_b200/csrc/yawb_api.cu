@@ -170,6 +170,7 @@ int yawb_create(int device, yawb_ctx **out) {
 
     YAWB_CUDA(cudaEventCreate(&ctx->ev0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev1));
+    YAWB_CUDA(cudaEventCreate(&ctx->ev_plan));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_i0));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_i1));
     YAWB_CUDA(cudaEventCreate(&ctx->ev_f0));
@@ -198,6 +199,7 @@ int yawb_destroy(yawb_ctx *ctx) {
     yawb_dcache_destroy(ctx);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
     cudaEventDestroy(ctx->ev_i0);
     cudaEventDestroy(ctx->ev_i1);
     cudaEventDestroy(ctx->ev_f0);
@@ -654,6 +656,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
         TRY(cudaMemsetAsync(d_cnt, 0, std::max<size_t>(n_out, 1) * sizeof(unsigned long long), st));
         if (weighted) TRY(cudaMemsetAsync(d_w, 0, std::max<size_t>(n_out, 1) * sizeof(double), st));
         TRY(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+        ctx->ev_plan_set = false;
         TRY(cudaEventRecord(ctx->ev0, st));
         int rc = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? yawb_launch_count_exact(ctx, a, &launches)
                                                       : yawb_launch_count_fast(ctx, a, &launches);
@@ -708,6 +711,8 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     TRY(cudaGetLastError());
     float t_k = 0.f;
     TRY(cudaEventElapsedTime(&t_k, ctx->ev0, ctx->ev1));
+    float t_plan = 0.f;
+    if (ctx->ev_plan_set) TRY(cudaEventElapsedTime(&t_plan, ctx->ev0, ctx->ev_plan));
     if (second_built) {
         float t = 0.f;
         TRY(cudaEventElapsedTime(&t, ctx->ev_i0, ctx->ev_i1));
@@ -723,6 +728,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
 #undef DALLOC
     cleanup();
     s.kernel_ms = t_k;
+    s.plan_ms = t_plan;
     s.pair_tests = h_counters[1];
     s.rechecks = h_counters[2];
     s.work_items = (flags & YAWB_FLAG_EXACT_BRUTEFORCE) ? (uint64_t)n_pairs * B : h_counters[4] + h_counters[5];

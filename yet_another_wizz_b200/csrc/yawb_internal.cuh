@@ -133,6 +133,8 @@ struct yawb_ctx {
     cudaStream_t stream = nullptr;       // all kernels and result copies
     cudaStream_t copy_stream = nullptr;  // host-to-device copies of catalog uploads (overlap with kernels)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_plan = nullptr;  // between the planner and the count kernel of the last fast count
+    bool ev_plan_set = false;
     cudaEvent_t ev_i0 = nullptr, ev_i1 = nullptr;  // lazy index builds inside yawb_count (second role)
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;  // ... (first role)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;  // user stopwatch
