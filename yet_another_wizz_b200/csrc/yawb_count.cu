@@ -556,23 +556,12 @@ struct PlanParams {
     unsigned long long *counters;
 };
 
-// `cache` (PLAN_CACHE entries, or nullptr): cell rows per z-bin, written by the first walk (FILL) and read by the
-// second -- the planner walks every surviving tile twice (count the items, then write them), and the cell rows
-// of a z-bin are four FP64 floors each.
-constexpr int PLAN_CACHE = 64;
-template <bool FILL, typename Emit>
+template <typename Emit>
 __device__ __forceinline__ void plan_walk(const SGrid &G, const BinPar *__restrict__ binpar, int b_lo, int b_hi, double ulo,
-                                          double uhi, double vlo, double vhi, int ccap, unsigned short *cache, Emit emit) {
+                                          double uhi, double vlo, double vhi, int ccap, Emit emit) {
     int acc = 0, seg = b_lo;
-    const bool cached = cache != nullptr && b_hi - b_lo <= PLAN_CACHE;
     for (int b = b_lo; b < b_hi; ++b) {
-        int r;
-        if (cached && !FILL) {
-            r = cache[b - b_lo];
-        } else {
-            r = bin_rows(G, ulo, uhi, vlo, vhi, binpar[b], 0, INT_MAX).nrows;
-            if (cached) cache[b - b_lo] = (unsigned short)min(r, 65535);
-        }
+        const int r = bin_rows(G, ulo, uhi, vlo, vhi, binpar[b], 0, INT_MAX).nrows;
         if (r > ccap) {
             if (acc > 0) emit(seg, b, 0, INT_MAX);
             for (int r0 = 0; r0 < r; r0 += ccap) emit(b, b + 1, r0, min(r0 + ccap, r));
@@ -594,7 +583,6 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
     const int lane = threadIdx.x & 31;
     int n_emit = 0;
     bool heavy = false;
-    unsigned short nrows_cache[PLAN_CACHE];
     Item it{};
     SGrid G{};
     if (f < Q.n_flat) {
@@ -645,7 +633,7 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d) { it.lo[d] = lo3[d]; it.hi[d] = hi3[d]; }
                 heavy = p1 == p2;
-                plan_walk<true>(G, Q.binpar, it.b_lo, it.b_hi, lo3[0], hi3[0], lo3[1], hi3[1], Q.ccap, nrows_cache, [&](int, int, int, int) { ++n_emit; });
+                plan_walk(G, Q.binpar, it.b_lo, it.b_hi, lo3[0], hi3[0], lo3[1], hi3[1], Q.ccap, [&](int, int, int, int) { ++n_emit; });
             }
         }
     }
@@ -669,7 +657,7 @@ __global__ void __launch_bounds__(256) k_plan(const PlanParams Q) {
     long long pos = heavy ? (long long)base_h + pre_h - n_emit : (long long)base_l + pre_l - n_emit;
     Item *const out = heavy ? Q.heavy : Q.light;
     const long long cap = heavy ? Q.cap_heavy : Q.cap_light;
-    plan_walk<false>(G, Q.binpar, it.b_lo, it.b_hi, it.lo[0], it.hi[0], it.lo[1], it.hi[1], Q.ccap, nrows_cache, [&](int b0, int b1, int r0, int r1) {
+    plan_walk(G, Q.binpar, it.b_lo, it.b_hi, it.lo[0], it.hi[0], it.lo[1], it.hi[1], Q.ccap, [&](int b0, int b1, int r0, int r1) {
         if (pos < cap) {
             Item w = it;
             w.b_lo = b0; w.b_hi = b1; w.row_lo = r0; w.row_hi = r1;
