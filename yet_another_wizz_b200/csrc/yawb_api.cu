@@ -497,7 +497,7 @@ static int count_impl(yawb_ctx *ctx, yawb_cat *cat1, yawb_cat *cat1b, yawb_cat *
     // float copy of the edges, followed (sub-bin paths only) by the arithmetic bin lookup of every z-bin:
     // (scale, offset) with cell = lg2(d2) * scale + offset, and a table [n_cells] of the number of edges
     // strictly below the start of each cell (a lower bound of the answer that the kernel fixes up)
-    const int lg_cells = n_edges > 2 ? 2 * n_edges : 0;
+    const int lg_cells = n_edges > 2 ? YAWB_LG_CELLS_PER_EDGE * n_edges : 0;
     const size_t r2f_words = (size_t)B * n_edges + 2 * (size_t)B + ((size_t)B * lg_cells + 1) / 2;
     std::vector<float> r2f(r2f_words, 0.f);
     for (int b = 0; b < B; ++b) {

@@ -126,7 +126,8 @@ __host__ __device__ inline size_t stream_carve(StreamSmem<WEIGHTED> *S, unsigned
     p = take(WEIGHTED ? nacc * sizeof(double) : 0); if (S) S->accw = WEIGHTED ? (double *)p : nullptr;
     p = take(multi ? nsub * sizeof(unsigned) : 0); if (S) S->hist = multi ? (unsigned *)p : nullptr;
     p = take(multi && WEIGHTED ? nsub * sizeof(double) : 0); if (S) S->histw = (multi && WEIGHTED) ? (double *)p : nullptr;
-    p = take(multi ? (size_t)n_bins * CUM_EDGES * sizeof(float) : 0); if (S) S->cum = multi ? (float *)p : nullptr;
+    // (at least 128 words: the general sub-bin path keeps its queue of in-range tests here, phase2_multi_queue)
+    p = take(multi ? ((size_t)n_bins * CUM_EDGES > 128 ? (size_t)n_bins * CUM_EDGES : 128) * sizeof(float) : 0); if (S) S->cum = multi ? (float *)p : nullptr;
     p = take(multi ? CUM_EDGES * sizeof(unsigned) : 0); if (S) S->cumtot = multi ? (unsigned *)p : nullptr;
     return o;
 }
@@ -516,7 +517,11 @@ __device__ __forceinline__ void stream_test_generic(const FastParams &P, const S
                 if (WEIGHTED) W.histw[k] = 0.0;
             }
             __syncwarp();
+#ifdef YAWB_MULTI_INPLACE  // round 1's form: classification inside the test loop (C3w count kernels 38.5 ms against 34.7)
             phase2_multi<WEIGHTED>(P, W, ea, eb, rx, ry, rz, thr.x, thr.y, S.binrec[b].w, tl, lane, b, n_recheck);
+#else
+            phase2_multi_queue<WEIGHTED>(P, W, ea, eb, rx, ry, rz, thr.x, thr.y, S.binrec[b].w, tl, lane, b, n_recheck);
+#endif
             __syncwarp();
             if (P.acc_global) {  // straight to the result: one atomic per non-empty sub-bin of the segment
                 const size_t o = src_off + (size_t)d.type * P.type_stride + ((size_t)cur_pair * P.n_bins + b) * nsub;

@@ -116,6 +116,7 @@ struct BinPar {
 
 constexpr int YAWB_RPL = 8;               // second-role points per lane
 constexpr int YAWB_TILE = 32 * YAWB_RPL;  // points per register tile (one warp)
+constexpr int YAWB_LG_CELLS_PER_EDGE = 4;  // cells of the lg2(d2) lookup per edge (sub-bin paths): finer cells = fewer fix-up steps
 constexpr int YAWB_RSTRIDE = 4;           // doubles per second-role row record (x, y, z, unused): one 32-byte sector
 constexpr int YAWB_LCAP = 256;            // candidate list capacity per warp
 constexpr int YAWB_WARPS = 4;             // warps per CTA in the count kernel
