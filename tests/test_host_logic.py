@@ -192,3 +192,46 @@ def test_pipelined_schedule_matches_whole_catalog_counts():
         assert ranges == expect
         assert ranges[0][0] == 0 and ranges[-1][1] == len(off) - 1
         assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
+
+
+def test_angle_and_pair_list_caches_return_fresh_equal_values():
+    """the per-configuration caches of the host path (scale -> angle conversion per z-bin, pair list of a linkage)
+    return what an uncached evaluation returns, do not call the cosmology again, and hand out copies"""
+    from yet_another_wizz_b200 import measurements
+
+    class CountingCosmology:
+        def __init__(self, inner):
+            self.inner, self.calls = inner, 0
+
+        def comoving_distance(self, z):
+            self.calls += 1
+            return self.inner.comoving_distance(z)
+
+        def angular_diameter_distance(self, z):
+            self.calls += 1
+            return self.inner.angular_diameter_distance(z)
+
+    cosmo = CountingCosmology(yb.cosmology.get_default_cosmology())
+    config = yb.Configuration.create(rmin=100, rmax=1000, zmin=0.1, zmax=1.0, num_bins=7, cosmology=cosmo)
+    a0, b0 = measurements._angles_per_bin(config)
+    calls = cosmo.calls
+    assert calls > 0
+    a1, b1 = measurements._angles_per_bin(config)
+    assert cosmo.calls == calls  # answered from the cache
+    assert_array_equal(a0, a1)
+    assert_array_equal(b0, b1)
+    a1[:] = -1.0  # a copy: the cache is not poisoned
+    a2, _ = measurements._angles_per_bin(config)
+    assert_array_equal(a0, a2)
+    # another binning of the same cosmology is a different entry
+    config2 = yb.Configuration.create(rmin=100, rmax=1000, zmin=0.1, zmax=1.0, num_bins=5, cosmology=cosmo)
+    a3, _ = measurements._angles_per_bin(config2)
+    assert len(a3) == 5 and cosmo.calls > calls
+
+    links = PatchLinkage(config, {0: {0, 1}, 1: {0, 1, 2}, 2: {1, 2}})
+    for auto in (False, True):
+        want = list(links.iter_patch_id_pairs(auto=auto))
+        for _ in range(2):  # the second answer comes from the cache
+            pi, pj = links.get_patch_id_pairs(auto=auto)
+            assert list(zip(pi.tolist(), pj.tolist())) == want
+            pi[:] = 99  # copies

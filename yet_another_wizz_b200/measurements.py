@@ -78,16 +78,38 @@ def _patch_rows(patch):
     return ra, dec, weights, redshifts, kappa
 
 
+_ANGLE_CACHE: dict = {}  # (id(cosmology), scales, z-bin centres) -> (cosmology, result): a few entries per process
+
+
 def _angles_per_bin(config) -> tuple[np.ndarray, np.ndarray]:
     """`get_angle_radian(zmid)` of every z-bin, evaluated once (the reference re-evaluates it
-    for every patch pair, `measurements.py:110-112`)."""
+    for every patch pair, `measurements.py:110-112`).  The conversion integrates the cosmology numerically per
+    redshift (a third of the host time of a call whose catalogs are already on the device), so the result is kept
+    per (cosmology object, scales, z-bin centres): a loop of calls over tomographic bins with the same
+    configuration (`cli/tasks.py:536-550`) evaluates it once.  Identical inputs, identical doubles."""
     zmids = _as_binning(config).mids
+    scales = config.scales.scales
+    cosmology = config.cosmology
+    key = None
+    try:
+        key = (id(cosmology), str(getattr(scales, "unit", None)), tuple(np.atleast_1d(scales.scale_min).tolist()),
+               tuple(np.atleast_1d(scales.scale_max).tolist()), tuple(np.asarray(zmids, dtype=np.float64).tolist()))
+        hit = _ANGLE_CACHE.get(key)
+        if hit is not None and hit[0] is cosmology:
+            return hit[1][0].copy(), hit[1][1].copy()
+    except Exception:  # foreign scales objects without these attributes: no caching
+        key = None
     amin, amax = [], []
     for z in zmids:
         lo, hi = config.scales.scales.get_angle_radian(z, cosmology=config.cosmology)
         amin.append(np.atleast_1d(lo))
         amax.append(np.atleast_1d(hi))
-    return np.array(amin, dtype=np.float64), np.array(amax, dtype=np.float64)
+    out = np.array(amin, dtype=np.float64), np.array(amax, dtype=np.float64)
+    if key is not None:
+        if len(_ANGLE_CACHE) > 16:
+            _ANGLE_CACHE.clear()
+        _ANGLE_CACHE[key] = (cosmology, (out[0].copy(), out[1].copy()))
+    return out
 
 
 def prepare_catalog_arrays(catalog, binning: Binning | None, *, kappa: bool = False,
@@ -360,10 +382,16 @@ class PatchLinkage:
                 patch_links.pop(i)
 
     def get_patch_id_pairs(self, *, auto: bool) -> tuple[np.ndarray, np.ndarray]:
+        """the pair list as two arrays; walked once per linkage and `auto` (every count of a call asks for it)"""
+        cache = self.__dict__.setdefault("_pair_cache", {})
+        hit = cache.get(bool(auto))
+        if hit is not None and hit[0] == self.num_links:
+            return hit[1].copy(), hit[2].copy()
         pairs = list(self.iter_patch_id_pairs(auto=auto))
         if not pairs:
             return np.empty(0, dtype=np.int32), np.empty(0, dtype=np.int32)
         arr = np.array(pairs, dtype=np.int32)
+        cache[bool(auto)] = (self.num_links, arr[:, 0].copy(), arr[:, 1].copy())
         return arr[:, 0].copy(), arr[:, 1].copy()
 
     # ---- the count driver --------------------------------------------------------------------------
