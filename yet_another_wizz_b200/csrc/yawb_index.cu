@@ -806,6 +806,27 @@ __global__ void k_tile_spheres(const double *__restrict__ x, const double *__res
     }
 }
 
+// tile table of a second-role index: tile t covers YAWB_TILE rows (the last tile of a segment fewer) of the
+// (patch, z-bin) segment s with seg_tile_off[s] <= t < seg_tile_off[s + 1].  Written on the device: the host loop
+// over the tiles and the 32 bytes per tile it had to send sat on the critical path of every index build.
+__global__ void k_make_tiles(const int *__restrict__ seg_off, const int *__restrict__ seg_tile_off, int n_seg, int n_bins,
+                             int binned, int n_tiles, Tile *__restrict__ tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    int lo = 0, hi = n_seg;  // last segment with seg_tile_off[s] <= t
+    while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (seg_tile_off[m] <= t) lo = m; else hi = m;
+    }
+    const int s = lo;
+    Tile tl{};
+    tl.start = seg_off[s] + (t - seg_tile_off[s]) * YAWB_TILE;
+    tl.count = min(YAWB_TILE, seg_off[s + 1] - tl.start);
+    tl.patch = s / n_bins;
+    tl.bin = binned ? s % n_bins : -1;
+    tiles[t] = tl;
+}
+
 __global__ void k_count_oversized(const Tile *__restrict__ tiles, int n_tiles, const float *__restrict__ thr,
                                   unsigned *__restrict__ n_big) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1340,25 +1361,21 @@ int yawb_index_build_second(yawb_cat *cat) {
         }
     }
 
-    // tiles: chunks of YAWB_TILE rows inside each (patch, bin) segment
-    std::vector<Tile> &tiles = cat->h_tiles;
+    // tiles: chunks of YAWB_TILE rows inside each (patch, bin) segment; the host only needs their number per segment
+    // (the table itself is written on the device, k_make_tiles) and per patch
+    std::vector<Tile> &tiles = cat->h_tiles;  // filled only if tiles have to be split (straggler guard below)
     tiles.clear();
     cat->h_ptile_off.assign(P + 1, 0);
+    std::vector<int> seg_tile_off((size_t)P * B + 1, 0);
     for (int p = 0; p < P; ++p) {
-        cat->h_ptile_off[p] = (int)tiles.size();
+        cat->h_ptile_off[p] = seg_tile_off[(size_t)p * B];
         for (int b = 0; b < B; ++b) {
-            int s = cat->h_seg_off[(size_t)p * B + b], e = cat->h_seg_off[(size_t)p * B + b + 1];
-            for (int t = s; t < e; t += YAWB_TILE) {
-                Tile tl{};
-                tl.start = t;
-                tl.count = std::min(YAWB_TILE, e - t);
-                tl.patch = p;
-                tl.bin = cat->binned ? b : -1;
-                tiles.push_back(tl);
-            }
+            const int len = cat->h_seg_off[(size_t)p * B + b + 1] - cat->h_seg_off[(size_t)p * B + b];
+            seg_tile_off[(size_t)p * B + b + 1] = seg_tile_off[(size_t)p * B + b] + (len + YAWB_TILE - 1) / YAWB_TILE;
         }
     }
-    cat->h_ptile_off[P] = (int)tiles.size();
+    const int n_tiles0 = seg_tile_off[(size_t)P * B];
+    cat->h_ptile_off[P] = n_tiles0;
 
     // Straggler guard: a chunk of consecutive rows can straddle a place where the Hilbert curve leaves the
     // populated part of the patch box and re-enters elsewhere (irregular footprints, masks).  Such a tile
@@ -1367,14 +1384,16 @@ int yawb_index_build_second(yawb_cat *cat) {
     // sub-tiles of 32 rows (rare; they run the same kernel with most register rows padded).  The common
     // case costs one 4-byte read-back.
     bool table_on_device = false;
-    if (!tiles.empty()) {
+    int n_tiles_final = n_tiles0;
+    if (n_tiles0 > 0) {
         Scratch scr(ctx, st);
-        if (dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;  // becomes the final table unless tiles are split
+        if (dev_alloc(cat, &cat->d_tiles, (size_t)n_tiles0)) return 1;  // becomes the final table unless tiles are split
         Tile *d_tmp = cat->d_tiles;
-        const size_t n_tmp = tiles.size();
+        const size_t n_tmp = (size_t)n_tiles0;
         float *d_thr = scr.get<float>(P);
         unsigned *d_nbig = scr.get<unsigned>(1);
-        YAWB_REQUIRE(d_thr && d_nbig, "out of device memory (tile table)");
+        int *d_seg_tile_off = scr.get<int>((size_t)P * B + 1);
+        YAWB_REQUIRE(d_thr && d_nbig && d_seg_tile_off, "out of device memory (tile table)");
         std::vector<float> thr(P, 3.0e38f);
         for (int p = 0; p < P; ++p) {
             const PatchFrame &f = cat->h_frames[p];
@@ -1383,20 +1402,23 @@ int yawb_index_build_second(yawb_cat *cat) {
             if (np >= 8 * YAWB_TILE && area > 0.0)  // radius of a disc holding YAWB_TILE rows of one z-bin
                 thr[p] = (float)(3.0 * std::sqrt((double)YAWB_TILE * B * area / (3.14159265358979 * (double)np)));
         }
-        if (yawb_h2d_small(ctx, d_tmp, tiles.data(), tiles.size() * sizeof(Tile))) return 1;
+        if (yawb_h2d_small(ctx, d_seg_tile_off, seg_tile_off.data(), seg_tile_off.size() * sizeof(int))) return 1;
         if (yawb_h2d_small(ctx, d_thr, thr.data(), P * sizeof(float))) return 1;
         YAWB_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
+        k_make_tiles<<<blocks_for((long long)n_tiles0), kThreads, 0, st>>>(cat->d_seg_off, d_seg_tile_off, P * B, B,
+                                                                          cat->binned ? 1 : 0, n_tiles0, d_tmp);
         TileBox *d_box_tmp = nullptr;
-        if (dev_alloc(cat, &d_box_tmp, tiles.size())) return 1;
+        if (dev_alloc(cat, &d_box_tmp, (size_t)n_tiles0)) return 1;
         cat->d_tile_box = d_box_tmp;
-        k_tile_spheres<<<blocks_for((long long)tiles.size() * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, d_tmp,
-                                                                                      (int)tiles.size(), cat->d_frames, d_box_tmp);
-        k_count_oversized<<<blocks_for((long long)tiles.size()), kThreads, 0, st>>>(d_tmp, (int)tiles.size(), d_thr, d_nbig);
+        k_tile_spheres<<<blocks_for((long long)n_tiles0 * 32), kThreads, 0, st>>>(cat->rx, cat->ry, cat->rz, d_tmp, n_tiles0,
+                                                                                 cat->d_frames, d_box_tmp);
+        k_count_oversized<<<blocks_for((long long)n_tiles0), kThreads, 0, st>>>(d_tmp, n_tiles0, d_thr, d_nbig);
         unsigned n_big = 0;
         YAWB_CUDA(cudaMemcpyAsync(&n_big, d_nbig, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         YAWB_CUDA(cudaStreamSynchronize(st));
         table_on_device = n_big == 0;
         if (n_big > 0) {
+            tiles.resize((size_t)n_tiles0);
             YAWB_CUDA(cudaMemcpyAsync(tiles.data(), d_tmp, tiles.size() * sizeof(Tile), cudaMemcpyDeviceToHost, st));
             YAWB_CUDA(cudaStreamSynchronize(st));
             dev_free(cat, cat->d_tiles, n_tmp);
@@ -1423,10 +1445,11 @@ int yawb_index_build_second(yawb_cat *cat) {
             new_off[P] = (int)out.size();
             tiles.swap(out);
             cat->h_ptile_off = new_off;
+            n_tiles_final = (int)tiles.size();
         }
     }
-    cat->n_tiles = (int)tiles.size();
-    if (!table_on_device && dev_alloc(cat, &cat->d_tiles, tiles.size())) return 1;
+    cat->n_tiles = n_tiles_final;
+    if (!table_on_device && dev_alloc(cat, &cat->d_tiles, (size_t)n_tiles_final)) return 1;
     if (dev_alloc(cat, &cat->d_ptile_off, P + 1)) return 1;
     if (yawb_h2d_small(ctx, cat->d_ptile_off, cat->h_ptile_off.data(), (P + 1) * sizeof(int))) return 1;
     if (!table_on_device && dev_alloc(cat, &cat->d_tile_box, tiles.size())) return 1;
