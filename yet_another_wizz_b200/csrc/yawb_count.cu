@@ -61,9 +61,10 @@ struct FastParams {
     const PatchFrame *sframe;
     int n_types;
     float zeta;  // max | |P|^2 - 1 | over the rows of the second catalog(s), rounded up: part of the FP32 error bound
-    // second catalog (register tiles); rx2.. = second catalog of a joint launch (Item::src == 1)
-    const double *rx, *ry, *rz, *rw;
-    const double *rx2, *ry2, *rz2, *rw2;
+    // second catalog (register tiles): 32-byte row records (row j = rx[4 j .. 4 j + 2]) and optional weights;
+    // rx2 / rw2 = second catalog of a joint launch (Item::src == 1, yawb_count4)
+    const double *rx, *rw;
+    const double *rx2, *rw2;
     // work items written by the planner: patch-diagonal items first, then the boundary items
     const Item *items_heavy, *items_light;
     long long cap_heavy, cap_light;
@@ -141,14 +142,6 @@ __device__ __forceinline__ int edges_below(const double *__restrict__ e, int n, 
 
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v) {
-    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
 
@@ -862,9 +855,9 @@ int yawb_launch_count_fast(yawb_ctx *ctx, const CountArgs &a, int *launches) {
     P.cx[1] = fi->b ? fi->b->x : fi->a->x; P.cy[1] = fi->b ? fi->b->y : fi->a->y; P.cz[1] = fi->b ? fi->b->z : fi->a->z;
     P.sw = fi->sw; P.rec = fi->rec;
     P.cell_start = fi->cell_start; P.sgrid = fi->d_sgrid; P.sframe = fi->d_frames; P.n_types = fi->n_types;
-    P.rx = a.c2->rx; P.ry = a.c2->ry; P.rz = a.c2->rz; P.rw = a.c2->rw;
-    P.rx2 = P.rx; P.ry2 = P.ry; P.rz2 = P.rz; P.rw2 = P.rw;
-    if (a.c2b) { P.rx2 = a.c2b->rx; P.ry2 = a.c2b->ry; P.rz2 = a.c2b->rz; P.rw2 = a.c2b->rw; }
+    P.rx = a.c2->rx; P.rw = a.c2->rw;
+    P.rx2 = P.rx; P.rw2 = P.rw;
+    if (a.c2b) { P.rx2 = a.c2b->rx; P.rw2 = a.c2b->rw; }
     {
         // the pair test takes |r|^2 of a tile row from the identity for unit vectors (yawb_count_stream.cuh); rows
         // off the unit sphere by zeta widen the band of tests that are re-evaluated in FP64 (1e-15: the frames'
